@@ -1,0 +1,3 @@
+"""lsio-b200: B200-native drop-in for light-speed-io's batched byte-range read."""
+from . import _native  # noqa: F401  (raises if liblsio_b200.so is missing: no CPU fallback)
+from . import cuda_ops  # noqa: F401

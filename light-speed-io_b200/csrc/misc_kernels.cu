@@ -1,0 +1,194 @@
+// misc_kernels.cu -- xxh64_chunks and verify_pattern kernels for sm_100a.
+//
+// xxh64_chunks: XXH64 is a sequential recurrence per accumulator, so a chunk offers only 4-way
+// parallelism (the four 8-byte lanes of each 32-byte stripe).  The kernel therefore runs 4
+// threads per chunk and parallelises ACROSS chunks; it is HBM-bound only when a launch holds
+// >= ~75k chunks and is latency-bound otherwise, which is why crc32c is the default proof.
+// Algorithmic bytes: sum(len) (read only).
+//
+// verify_pattern: recomputes the synthetic content byte(file_id, off) (generator
+// restated in tests, never linked from oracle/) and counts mismatching bytes.  Test aid.
+#include "common.hpp"
+#include "lsio_cuda.h"
+
+#include <vector>
+
+namespace lsio {
+namespace {
+
+constexpr uint64_t XP1 = 0x9E3779B185EBCA87ull, XP2 = 0xC2B2AE3D27D4EB4Full, XP3 = 0x165667B19E3779F9ull,
+                   XP4 = 0x85EBCA77C2B2AE63ull, XP5 = 0x27D4EB2F165667C5ull;
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t xround(uint64_t acc, uint64_t in) { return rotl64(acc + in * XP2, 31) * XP1; }
+__device__ __forceinline__ uint64_t xmerge(uint64_t acc, uint64_t v) { return (acc ^ xround(0, v)) * XP1 + XP4; }
+
+// 8 bytes at an arbitrary address, via aligned 8-byte loads of the aligned superset.
+__device__ __forceinline__ uint64_t ld64_any(uint64_t addr) {
+    const uint64_t* q = (const uint64_t*)(addr & ~7ull);
+    const int s = (int)(addr & 7) * 8;
+    const uint64_t lo = __ldg(q);
+    if (s == 0) return lo;
+    const uint64_t hi = __ldg(q + 1);
+    return (lo >> s) | (hi << (64 - s));
+}
+__device__ __forceinline__ uint32_t ld8(uint64_t addr) { return *(const uint8_t*)addr; }
+
+__global__ void __launch_bounds__(256) xxh64_kernel(const uint64_t* __restrict__ ptrs, const uint64_t* __restrict__ lens,
+                                                    uint64_t n, uint64_t* __restrict__ out) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t chunk = gid >> 2;
+    const int j = (int)(gid & 3);
+    const bool live = chunk < n;
+    const uint64_t p = live ? ptrs[chunk] : 0, len = live ? lens[chunk] : 0;
+    const uint64_t seed = 0;
+    uint64_t v = j == 0 ? seed + XP1 + XP2 : j == 1 ? seed + XP2 : j == 2 ? seed : seed - XP1;
+    const uint64_t nstripes = len >> 5;
+    uint64_t a = p + 8 * j;
+    uint64_t i = 0;
+    for (; i + 4 <= nstripes; i += 4, a += 128) {  // four loads in flight per thread
+        const uint64_t w0 = ld64_any(a), w1 = ld64_any(a + 32), w2 = ld64_any(a + 64), w3 = ld64_any(a + 96);
+        v = xround(v, w0); v = xround(v, w1); v = xround(v, w2); v = xround(v, w3);
+    }
+    for (; i < nstripes; i++, a += 32) v = xround(v, ld64_any(a));
+    // gather the four accumulators of this chunk into its lane 0 (groups of 4 lanes)
+    const unsigned full = 0xFFFFFFFFu;
+    const int base = (threadIdx.x & 31) & ~3;
+    const uint64_t v1 = __shfl_sync(full, v, base), v2 = __shfl_sync(full, v, base + 1), v3 = __shfl_sync(full, v, base + 2),
+                   v4 = __shfl_sync(full, v, base + 3);
+    if (!live || j != 0) return;
+    uint64_t h;
+    if (len >= 32) {
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = xmerge(h, v1); h = xmerge(h, v2); h = xmerge(h, v3); h = xmerge(h, v4);
+    } else {
+        h = seed + XP5;
+    }
+    h += len;
+    uint64_t q = p + (nstripes << 5);
+    const uint64_t end = p + len;
+    for (; q + 8 <= end; q += 8) {
+        uint64_t w = 0;
+        for (int b = 0; b < 8; b++) w |= (uint64_t)ld8(q + b) << (8 * b);
+        h ^= xround(0, w);
+        h = rotl64(h, 27) * XP1 + XP4;
+    }
+    if (q + 4 <= end) {
+        uint32_t w = 0;
+        for (int b = 0; b < 4; b++) w |= ld8(q + b) << (8 * b);
+        h ^= (uint64_t)w * XP1;
+        h = rotl64(h, 23) * XP2 + XP3;
+        q += 4;
+    }
+    for (; q < end; q++) {
+        h ^= (uint64_t)ld8(q) * XP5;
+        h = rotl64(h, 11) * XP1;
+    }
+    h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+    out[chunk] = h;
+}
+
+// ---- verify_pattern ------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t pattern_word(uint64_t file_id, uint64_t word_idx) {
+    return splitmix64(0x4C53494Full ^ (file_id * 0x9E3779B97F4A7C15ull) ^ word_idx);
+}
+struct Piece {  // <= 256 KiB of one span
+    uint64_t ptr, len, file_id, file_off;
+};
+__global__ void __launch_bounds__(256) verify_kernel(const Piece* __restrict__ pieces, uint32_t npieces,
+                                                     unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (uint32_t pi = blockIdx.x; pi < npieces; pi += gridDim.x) {
+        const Piece pc = pieces[pi];
+        // iterate over the file's 8-byte words that intersect [file_off, file_off + len)
+        const uint64_t w0 = pc.file_off >> 3, w1 = (pc.file_off + pc.len + 7) >> 3;
+        for (uint64_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+            const uint64_t expect = pattern_word(pc.file_id, w);
+            const int64_t rel = (int64_t)(w << 3) - (int64_t)pc.file_off;  // may be negative for the first word
+            const uint64_t addr = pc.ptr + (uint64_t)rel;
+            if (rel >= 0 && (uint64_t)rel + 8 <= pc.len && (addr & 7) == 0) {
+                uint64_t x = *(const uint64_t*)addr ^ expect;
+                // count non-zero bytes
+                x |= x >> 4; x |= x >> 2; x |= x >> 1;
+                bad += __popcll(x & 0x0101010101010101ull);
+            } else {
+                for (int b = 0; b < 8; b++) {
+                    const int64_t r = rel + b;
+                    if (r >= 0 && (uint64_t)r < pc.len) bad += ld8(pc.ptr + (uint64_t)r) != (uint8_t)(expect >> (8 * b));
+                }
+            }
+        }
+    }
+    // warp then block reduce, one atomic per block
+    for (int o = 16; o; o >>= 1) bad += __shfl_down_sync(0xFFFFFFFFu, bad, o);
+    __shared__ unsigned long long sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = bad;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; i++) t += sh[i];
+        if (t) atomicAdd(mismatches, t);
+    }
+}
+
+}  // namespace
+}  // namespace lsio
+
+extern "C" {
+
+int lsio_cuda_xxh64(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n, uint64_t* out_dev, void* stream) {
+    using namespace lsio;
+    if ((!ptrs || !lens || !out_dev) && n) return -EINVAL;
+    if (n == 0) return 0;
+    DeviceGuard dg(device);
+    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t* d = nullptr;
+    LSIO_CUDA_TRY(cudaMallocAsync(&d, 2 * n * sizeof(uint64_t), st));
+    LSIO_CUDA_TRY(cudaMemcpyAsync(d, ptrs, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    LSIO_CUDA_TRY(cudaMemcpyAsync(d + n, lens, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const uint64_t threads = 4 * (uint64_t)n;
+    xxh64_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, d + n, n, out_dev);
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    LSIO_CUDA_TRY(cudaGetLastError());
+    LSIO_CUDA_TRY(cudaFreeAsync(d, st));
+    LSIO_CUDA_TRY(cudaStreamSynchronize(st));  // ptrs/lens are pageable host memory: keep the call self-contained
+    return 0;
+}
+
+int lsio_cuda_verify_pattern(int device, const uint64_t* ptrs, const uint64_t* lens, const uint64_t* file_ids,
+                             const uint64_t* file_offs, size_t n, uint64_t* mismatch_dev, void* stream) {
+    using namespace lsio;
+    if ((!ptrs || !lens || !file_ids || !file_offs) && n) return -EINVAL;
+    if (!mismatch_dev) return -EINVAL;
+    DeviceGuard dg(device);
+    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr uint64_t kPiece = 256 << 10;
+    std::vector<Piece> pieces;
+    for (size_t i = 0; i < n; i++)
+        for (uint64_t o = 0; o < lens[i]; o += kPiece)
+            pieces.push_back(Piece{ptrs[i] + o, std::min<uint64_t>(kPiece, lens[i] - o), file_ids[i], file_offs[i] + o});
+    LSIO_CUDA_TRY(cudaMemsetAsync(mismatch_dev, 0, sizeof(uint64_t), st));
+    if (pieces.empty()) return (int)cudaStreamSynchronize(st);
+    Piece* d = nullptr;
+    LSIO_CUDA_TRY(cudaMallocAsync(&d, pieces.size() * sizeof(Piece), st));
+    LSIO_CUDA_TRY(cudaMemcpyAsync(d, pieces.data(), pieces.size() * sizeof(Piece), cudaMemcpyHostToDevice, st));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const unsigned grid = (unsigned)std::min<size_t>(pieces.size(), (size_t)sms * 8);
+    verify_kernel<<<grid, 256, 0, st>>>(d, (uint32_t)pieces.size(), (unsigned long long*)mismatch_dev);
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    LSIO_CUDA_TRY(cudaGetLastError());
+    LSIO_CUDA_TRY(cudaFreeAsync(d, st));
+    LSIO_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"
