@@ -1,0 +1,94 @@
+/*
+ * lsio_uring_cuda.h -- C ABI of the B200 backend: a drop-in for the reference's
+ * `lsio_uring::IoUring` (crates/lsio_uring/src/io_uring.rs:9-49) whose chunks land in GPU HBM.
+ *
+ *   reference item                                   (file:line)              here
+ *   IoUring::new(n_worker_threads)                   io_uring.rs:15-27        lsio_uring_cuda_new
+ *   impl Reader for IoUring :: get_ranges            io_uring.rs:36-49        lsio_uring_cuda_get_ranges
+ *   impl Completion for IoUring :: completion        io_uring.rs:30-34        lsio_uring_cuda_completion
+ *   Drop (ThreadPool joins workers)                  threadpool.rs:140-165    lsio_uring_cuda_free
+ *   compile-time knobs SQ_RING_SIZE, ALIGN, channel  worker.rs:14-22,         lsio_uring_cuda_config
+ *     bound, SQPOLL idle                             sqe.rs:12, io_uring.rs:16
+ *
+ * Submit/complete semantics are the reference's: get_ranges copies its inputs and returns
+ * immediately; exactly one Ok chunk per successful range, `user_data` echoed, completions
+ * unordered; failures arrive in-band as Err items; the channel is bounded (back-pressure) and
+ * disconnects once the backend is freed.  Differences, all deliberate:
+ * chunk.buffer is a DEVICE view; unaligned starts/lengths work (the reference panics / gets
+ * EINVAL); short reads are retried; bad ranges are Err items, not panics.
+ */
+#ifndef LSIO_URING_CUDA_H
+#define LSIO_URING_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "lsio_io.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsio_uring_cuda lsio_uring_cuda;
+
+#define LSIO_MAX_DEVICES 16
+
+typedef struct lsio_uring_cuda_config {
+    uint32_t n_worker_threads;  /* io_uring worker threads PER DEVICE group (IoUring::new's argument)      */
+    uint32_t n_devices;         /* number of entries used in devices[]                                      */
+    int32_t devices[LSIO_MAX_DEVICES]; /* CUDA ordinals; files are dealt to groups round-robin unless routed */
+    uint32_t sq_entries;        /* per-worker SQ size (reference: 64, worker.rs:17)                          */
+    uint32_t sqpoll;            /* 1 = IORING_SETUP_SQPOLL with 1000 ms idle as the reference (worker.rs:40) */
+    uint32_t completion_bound;  /* bounded channel capacity (reference: 1024, io_uring.rs:16)                */
+    uint32_t checksum;          /* LSIO_CHECKSUM_* bits computed on the device per chunk                     */
+    uint32_t pack_align;        /* each chunk starts at a multiple of this in its request buffer (1 = tight) */
+    uint32_t pin_threads;       /* 1 = pin each group's threads to the CPUs of its GPU's NUMA node           */
+    uint32_t o_direct;          /* 1 = O_RDONLY|O_DIRECT as the reference (sqe.rs:25); 0 = buffered          */
+    uint64_t staging_bytes;     /* pinned + io_uring-registered staging ring per device                      */
+    uint64_t arena_bytes;       /* HBM arena per device that request buffers are carved from                 */
+    uint64_t max_read_bytes;    /* reads longer than this are split (reference: panics > 2 GiB)              */
+    uint64_t min_copy_bytes;    /* H2D copies are coalesced up to at least this many bytes                   */
+    uint32_t flush_us;          /* ...or until the oldest landed read has waited this long                   */
+    uint32_t reserved;
+} lsio_uring_cuda_config;
+
+typedef struct lsio_uring_cuda_stats {
+    uint64_t requests, ranges, reads, short_reads, read_bytes;
+    uint64_t h2d_copies, h2d_bytes, pack_launches, kernel_launches, payload_bytes;
+    uint64_t chunks_ok, errors;
+    uint64_t staging_stalls, arena_stalls;
+} lsio_uring_cuda_stats;
+
+void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg);
+/* IoUring::new(n_worker_threads): device 0, default config. Returns 0 or an error code. */
+int lsio_uring_cuda_new(size_t n_worker_threads, lsio_uring_cuda** out);
+int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfg, lsio_uring_cuda** out);
+
+/* Reader::get_ranges (lsio_io lib.rs:36-44).  `location` must be absolute (the reference opens
+ * with dirfd -1, sqe.rs:22).  range i is [range_start[i], range_end[i]); negative values are
+ * relative to the file size exactly as in the reference (lib.rs:19-23, sqe.rs:64-81).
+ * Returns 0 after enqueueing; -EINVAL if n_ranges != n_user_data (the reference asserts,
+ * get_ranges.rs:28) or location is NULL/relative; -ESHUTDOWN after lsio_uring_cuda_free. */
+int lsio_uring_cuda_get_ranges(lsio_uring_cuda* self, const char* location, const int64_t* range_start,
+                               const int64_t* range_end, size_t n_ranges, const uint64_t* user_data,
+                               size_t n_user_data);
+/* Same, routed to devices[group] instead of round-robin (file -> GPU affinity map). */
+int lsio_uring_cuda_get_ranges_on(lsio_uring_cuda* self, uint32_t group, const char* location,
+                                  const int64_t* range_start, const int64_t* range_end, size_t n_ranges,
+                                  const uint64_t* user_data, size_t n_user_data);
+
+/* Completion::completion(): a new handle on the backend's receiver (drop it yourself). */
+lsio_completion* lsio_uring_cuda_completion(lsio_uring_cuda* self);
+
+int lsio_uring_cuda_get_stats(const lsio_uring_cuda* self, lsio_uring_cuda_stats* out);
+/* Text of the last construction error on this thread. */
+const char* lsio_uring_cuda_last_error(void);
+
+/* Drop: finishes in-flight work, joins every thread, disconnects the channel.  Chunks already
+ * received stay valid until dropped. */
+void lsio_uring_cuda_free(lsio_uring_cuda* self);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

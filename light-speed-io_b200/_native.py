@@ -73,3 +73,88 @@ def check(rc, what):
     if rc > 0:
         raise LsioCudaError(f"{what}: CUDA error {rc}: {lib.lsio_cuda_last_error().decode(errors='replace')}")
     raise LsioCudaError(f"{what}: {os.strerror(-rc)} (rc={rc})")
+
+
+# ---- include/lsio_aligned_bytes.h ------------------------------------------------------------
+MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
+AB_ERR_NOT_IN_RANGE, AB_ERR_ZERO, AB_ERR_UNALIGNED, AB_ERR_SHARED, AB_ERR_BAD_SLICE = -1, -2, -3, -4, -5
+_vp = ctypes.c_void_p
+for _name, _res, _args in [
+    ("lsio_aligned_bytes_mut_new", _vp, [ctypes.c_size_t, ctypes.c_size_t]),
+    ("lsio_aligned_bytes_mut_new_pinned", _vp, [ctypes.c_size_t, ctypes.c_size_t]),
+    ("lsio_aligned_bytes_mut_new_device", _vp, [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]),
+    ("lsio_aligned_bytes_mut_len", ctypes.c_size_t, [_vp]),
+    ("lsio_aligned_bytes_mut_as_mut_ptr", _vp, [_vp]),
+    ("lsio_aligned_bytes_mut_split_to", ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    ("lsio_aligned_bytes_mut_freeze", ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    ("lsio_aligned_bytes_mut_drop", None, [_vp]),
+    ("lsio_aligned_bytes_clone", _vp, [_vp]),
+    ("lsio_aligned_bytes_set_slice", ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_size_t]),
+    ("lsio_aligned_bytes_reset_slice", None, [_vp]),
+    ("lsio_aligned_bytes_len", ctypes.c_size_t, [_vp]),
+    ("lsio_aligned_bytes_as_ptr", _vp, [_vp]),
+    ("lsio_aligned_bytes_memory_kind", ctypes.c_int, [_vp]),
+    ("lsio_aligned_bytes_device", ctypes.c_int, [_vp]),
+    ("lsio_aligned_bytes_backing_len", ctypes.c_size_t, [_vp]),
+    ("lsio_aligned_bytes_copy_to_host", ctypes.c_int64, [_vp, _vp, ctypes.c_size_t]),
+    ("lsio_aligned_bytes_drop", None, [_vp]),
+]:
+    getattr(lib, _name).restype = _res
+    getattr(lib, _name).argtypes = _args
+
+
+# ---- include/lsio_io.h --------------------------------------------------------------------------
+class CChunk(ctypes.Structure):
+    _fields_ = [("buffer", ctypes.c_void_p), ("user_data", ctypes.c_uint64)]
+
+
+class COutput(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int32), ("opcode", ctypes.c_uint8), ("kind", ctypes.c_uint8), ("checksums", ctypes.c_uint16),
+                ("device", ctypes.c_int32), ("crc32c", ctypes.c_uint32), ("xxh64", ctypes.c_uint64), ("chunk", CChunk),
+                ("context", ctypes.c_char * 256)]
+
+
+CHECKSUM_NONE, CHECKSUM_CRC32C, CHECKSUM_XXH64 = 0, 1, 2
+RECV_OK, RECV_TIMEOUT, RECV_DISCONNECTED = 0, 1, 2
+for _name, _res, _args in [
+    ("lsio_completion_clone", _vp, [_vp]),
+    ("lsio_completion_recv", ctypes.c_int, [_vp, ctypes.POINTER(COutput), ctypes.c_int]),
+    ("lsio_completion_try_recv", ctypes.c_int, [_vp, ctypes.POINTER(COutput)]),
+    ("lsio_completion_len", ctypes.c_size_t, [_vp]),
+    ("lsio_completion_drop", None, [_vp]),
+]:
+    getattr(lib, _name).restype = _res
+    getattr(lib, _name).argtypes = _args
+
+# ---- include/lsio_uring_cuda.h ---------------------------------------------------------------
+MAX_DEVICES = 16
+
+
+class CConfig(ctypes.Structure):
+    _fields_ = [("n_worker_threads", ctypes.c_uint32), ("n_devices", ctypes.c_uint32), ("devices", ctypes.c_int32 * MAX_DEVICES),
+                ("sq_entries", ctypes.c_uint32), ("sqpoll", ctypes.c_uint32), ("completion_bound", ctypes.c_uint32),
+                ("checksum", ctypes.c_uint32), ("pack_align", ctypes.c_uint32), ("pin_threads", ctypes.c_uint32),
+                ("o_direct", ctypes.c_uint32), ("staging_bytes", ctypes.c_uint64), ("arena_bytes", ctypes.c_uint64),
+                ("max_read_bytes", ctypes.c_uint64), ("min_copy_bytes", ctypes.c_uint64), ("flush_us", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
+
+
+class CStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("requests", "ranges", "reads", "short_reads", "read_bytes", "h2d_copies", "h2d_bytes",
+                                               "pack_launches", "kernel_launches", "payload_bytes", "chunks_ok", "errors",
+                                               "staging_stalls", "arena_stalls")]
+
+
+for _name, _res, _args in [
+    ("lsio_uring_cuda_config_default", None, [ctypes.POINTER(CConfig)]),
+    ("lsio_uring_cuda_new", ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    ("lsio_uring_cuda_new_with_config", ctypes.c_int, [ctypes.POINTER(CConfig), ctypes.POINTER(_vp)]),
+    ("lsio_uring_cuda_get_ranges", ctypes.c_int, [_vp, ctypes.c_char_p, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t]),
+    ("lsio_uring_cuda_get_ranges_on", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_char_p, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t]),
+    ("lsio_uring_cuda_completion", _vp, [_vp]),
+    ("lsio_uring_cuda_get_stats", ctypes.c_int, [_vp, ctypes.POINTER(CStats)]),
+    ("lsio_uring_cuda_last_error", ctypes.c_char_p, []),
+    ("lsio_uring_cuda_free", None, [_vp]),
+]:
+    getattr(lib, _name).restype = _res
+    getattr(lib, _name).argtypes = _args

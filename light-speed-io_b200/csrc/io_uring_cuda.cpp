@@ -1,0 +1,978 @@
+// io_uring_cuda.cpp -- the B200 backend: a from-scratch re-design of the reference's
+// `lsio_uring` hot path (crates/lsio_uring/src/{io_uring,worker,operation,get_ranges,get_range,
+// close,sqe,open_file}.rs) whose per-range chunks land in GPU HBM.
+//
+// Per device group (one group per GPU, threads pinned to that GPU's NUMA node):
+//
+//   caller ── get_ranges ─▶ injector ─▶ k io workers (work-stealing pool, private io_uring each)
+//        openat(O_DIRECT)+statx ─▶ plan: resolve ranges (sqe.rs:64-83), lay the request out in one
+//        HBM buffer (arena), split into reads ─▶ READ_FIXED into the pinned staging LOG
+//                                                         │ landed (CQE, short reads retried)
+//                                                         ▼
+//   device thread:  coalesce contiguous landed slots ─▶ ONE cudaMemcpyAsync H2D (copy stream)
+//        ─▶ pack_strip_crc32c over the batch (pack stream, after the copy's event)
+//        ─▶ event ─▶ one Chunk{device view, user_data, crc32c} per range on the bounded channel
+//
+// What is kept from the reference: submit/complete semantics, one chunk per range, unordered
+// completions, in-band errors (one per failed CQE: operation.rs:82-100), user_data packing,
+// tracker slots, openat+statx per file, close by the last reader, work stealing of per-range
+// reads between workers, bounded(1024) completion channel.  What changes: no allocation per
+// read, registered buffers, batched submission, the device boundary after the read CQE.
+#include <fcntl.h>
+#include <linux/stat.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <deque>
+#include <fstream>
+#include <sstream>
+#include <thread>
+
+#include "aligned_bytes.hpp"
+#include "channel.hpp"
+#include "common.hpp"
+#include "gf2.hpp"
+#include "lsio_uring_cuda.h"
+#include "pack_batch.hpp"
+#include "staging.hpp"
+#include "threadpool.hpp"
+#include "tracker.hpp"
+#include "uring.hpp"
+
+namespace lsio {
+
+static inline uint64_t now_ns() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+constexpr uint64_t kAlign = 512;  // crates/lsio_uring/src/sqe.rs:12
+
+struct Group;
+
+// One read = one segment of one range.
+struct SegPlan {
+    uint32_t range = 0;
+    uint64_t file_off = 0;     // 512-aligned
+    uint32_t read_len = 0;     // multiple of 512
+    uint32_t head = 0;         // padding bytes before the payload in the slot
+    uint64_t payload_len = 0;  // bytes of the range this read carries
+    uint64_t dst_off = 0;      // where they go in the request buffer
+    uint32_t crc = 0;
+};
+struct RangePlan {
+    int64_t start_off = 0, end_off = 0;
+    uint64_t dst_off = 0, len = 0;
+    uint32_t first_seg = 0, nsegs = 0;
+    uint64_t user_data = 0;
+    bool valid = false;
+    std::atomic<uint32_t> segs_left{0};
+    std::atomic<bool> failed{false};
+};
+
+// One get_ranges call (GetRanges, get_ranges.rs:15-25 + OpenFile, open_file.rs:4-12).
+struct Request {
+    std::string path;
+    std::vector<int64_t> starts, ends;
+    std::vector<uint64_t> user_data;
+    Group* grp = nullptr;
+    struct statx stx;
+    int fd = -1;
+    bool have_fd = false, have_statx = false, planned = false;
+    uint8_t n_cqes_received = 0;
+    uint64_t total_bytes = 0;
+    std::shared_ptr<InnerBuffer> buffer;  // the request's HBM buffer
+    std::unique_ptr<RangePlan[]> ranges;
+    std::vector<SegPlan> segs;
+    std::atomic<uint32_t> reads_left{0};  // Arc<OpenFile> strong count, get_range.rs:78
+    ~Request() {
+        if (fd >= 0) close(fd);  // only reached when the backend is torn down with reads still queued
+    }
+};
+
+// operation.rs:7-12, plus Plan (a request that is open but still waits for HBM).
+struct Op {
+    enum Kind : uint8_t { GetRanges, Plan, Read, Close } kind = GetRanges;
+    std::shared_ptr<Request> req;
+    uint32_t seg = 0;
+    StageEntry* entry = nullptr;
+    uint32_t done = 0;  // bytes of this read that have landed (short-read continuation)
+};
+
+struct Batch {
+    PackBatchLayout lay;
+    PackBatchCounts counts;
+    char* host_desc = nullptr;  // pinned
+    char* dev_desc = nullptr;
+    uint32_t* crc_host = nullptr;  // pinned + mapped: the kernel writes results straight to the host
+    uint32_t* crc_dev = nullptr;   // device alias of crc_host
+    cudaEvent_t copied = nullptr, done = nullptr;
+    uint64_t seq_begin = 0, seq_end = 0;
+    std::vector<uint64_t> seg_seq;  // staging entry of each descriptor
+};
+
+struct Stats {
+    std::atomic<uint64_t> requests{0}, ranges{0}, reads{0}, short_reads{0}, read_bytes{0}, h2d_copies{0}, h2d_bytes{0}, pack_launches{0},
+        kernel_launches{0}, payload_bytes{0}, chunks_ok{0}, errors{0}, staging_stalls{0}, arena_stalls{0};
+};
+
+struct Backend;
+
+struct Group {
+    Backend* be = nullptr;
+    int index = 0, device = 0;
+    std::vector<int> cpus;
+    std::shared_ptr<DeviceArena> arena;
+    uint8_t* host_ring = nullptr;
+    uint8_t* dev_ring = nullptr;
+    StagingLog log;
+    cudaStream_t s_copy = nullptr, s_pack = nullptr;
+    std::vector<Batch> batches;
+    std::deque<Batch*> free_batches, inflight;
+    std::unique_ptr<ThreadPool<Op>> pool;
+    std::thread device_thread;
+    std::atomic<bool> stop_device{false};
+    std::atomic<uint32_t> workers_alive{0};
+    uint64_t copy_seq = 0;  // device thread: next staging entry to copy
+    std::string init_error;
+};
+
+using OutChannel = Channel<lsio_output>;
+
+struct Backend {
+    lsio_uring_cuda_config cfg;
+    std::shared_ptr<OutChannel> out;
+    std::vector<std::unique_ptr<Group>> groups;
+    std::atomic<uint64_t> rr{0};
+    std::atomic<bool> closing{false};
+    Stats stats;
+};
+
+static thread_local std::string g_last_error;
+static void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+// ---- completion items ----------------------------------------------------------------------
+static void send_output(Backend* be, lsio_output& o) {
+    if (o.status != 0) be->stats.errors++;
+    else be->stats.chunks_ok++;
+    be->out->send(o);
+}
+
+// operation.rs:82-100 maybe_send_error: one Err per failed CQE, with context.
+static void send_error(Backend* be, int status, uint8_t opcode, const Request& r, int range, const char* what) {
+    lsio_output o;
+    memset(&o, 0, sizeof o);
+    o.status = status;
+    o.opcode = opcode;
+    o.device = r.grp ? r.grp->device : -1;
+    if (range >= 0) {
+        o.chunk.user_data = r.user_data[range];
+        snprintf(o.context, sizeof o.context, "%s: %s (io_uring opcode %u, result %d). path=%s range=%lld..%lld user_data=%llu", what,
+                 status < 0 ? strerror(-status) : "CUDA error", opcode, status, r.path.c_str(), (long long)r.starts[range], (long long)r.ends[range],
+                 (unsigned long long)r.user_data[range]);
+    } else {
+        snprintf(o.context, sizeof o.context, "%s: %s (io_uring opcode %u, result %d). path=%s n_ranges=%zu", what,
+                 status < 0 ? strerror(-status) : "CUDA error", opcode, status, r.path.c_str(), r.starts.size());
+    }
+    send_output(be, o);
+}
+
+// ---- planning: sqe.rs:59-122 re-stated for a whole request -----------------------------------
+enum class Start { Started, Finished, Retry };
+
+static Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op>& wt) {
+    Request& r = *rp;
+    Backend* be = g.be;
+    const lsio_uring_cuda_config& cfg = be->cfg;
+    const int64_t filesize = (int64_t)r.stx.stx_size;
+    const size_t n = r.starts.size();
+    if (!r.planned) {
+        r.ranges.reset(new RangePlan[n ? n : 1]);
+        uint64_t dst = 0;
+        const uint64_t pa = cfg.pack_align ? cfg.pack_align : 1;
+        for (size_t i = 0; i < n; i++) {
+            RangePlan& p = r.ranges[i];
+            p.user_data = r.user_data[i];
+            const int64_t s = r.starts[i], e = r.ends[i];
+            const int64_t start_off = s >= 0 ? s : filesize + s;  // sqe.rs:64-70
+            const int64_t end_off = e >= 0 ? e : filesize + e + 1;  // sqe.rs:73-80
+            // The reference asserts (panics) on these; here they are in-band errors (Appendix A).
+            if (start_off < 0 || end_off < 0 || end_off <= start_off || end_off > filesize) {
+                send_error(be, -EINVAL, 0, r, (int)i, "invalid byte range for this file");
+                continue;
+            }
+            p.valid = true;
+            p.start_off = start_off;
+            p.end_off = end_off;
+            p.len = (uint64_t)(end_off - start_off);
+            dst = (dst + pa - 1) / pa * pa;
+            p.dst_off = dst;
+            dst += p.len;
+        }
+        r.total_bytes = dst;
+        r.planned = true;
+        be->stats.ranges += n;
+    }
+    if (r.total_bytes == 0) {  // nothing to read
+        close(r.fd);
+        r.fd = -1;
+        return Start::Finished;
+    }
+    uint8_t* block = g.arena->alloc(r.total_bytes + 16);
+    if (!block) {
+        if (r.total_bytes + 16 > g.arena->capacity()) {
+            for (size_t i = 0; i < n; i++)
+                if (r.ranges[i].valid) send_error(be, -ENOMEM, 0, r, (int)i, "request larger than the HBM arena (arena_bytes)");
+            close(r.fd);
+            r.fd = -1;
+            return Start::Finished;
+        }
+        be->stats.arena_stalls++;
+        return Start::Retry;  // wait for the consumer to drop chunks
+    }
+    auto buf = std::make_shared<InnerBuffer>();
+    buf->buf = block;
+    buf->size = r.total_bytes;
+    buf->align = kAlign;
+    buf->kind = MemKind::Device;
+    buf->device = g.device;
+    buf->release = [arena = g.arena, block](InnerBuffer&) { arena->release(block); };
+    r.buffer = std::move(buf);
+
+    // split every range into reads of at most max_read_bytes (reference: one read per range,
+    // panics above 2 GiB, get_range.rs:23-30)
+    const uint64_t max_read = std::max<uint64_t>(kAlign, cfg.max_read_bytes / kAlign * kAlign);
+    for (size_t i = 0; i < n; i++) {
+        RangePlan& p = r.ranges[i];
+        if (!p.valid) continue;
+        const uint64_t aligned_start = (uint64_t)p.start_off / kAlign * kAlign;                  // sqe.rs:83
+        const uint64_t aligned_end = ((uint64_t)p.end_off + kAlign - 1) / kAlign * kAlign;      // padded length
+        p.first_seg = (uint32_t)r.segs.size();
+        for (uint64_t fo = aligned_start; fo < aligned_end; fo += max_read) {
+            SegPlan sp;
+            sp.range = (uint32_t)i;
+            sp.file_off = fo;
+            sp.read_len = (uint32_t)std::min<uint64_t>(max_read, aligned_end - fo);
+            const uint64_t lo = std::max<uint64_t>(fo, (uint64_t)p.start_off), hi = std::min<uint64_t>(fo + sp.read_len, (uint64_t)p.end_off);
+            sp.head = (uint32_t)(lo - fo);  // sqe.rs:116: view starts at start_off - aligned_start
+            sp.payload_len = hi - lo;
+            sp.dst_off = p.dst_off + (lo - (uint64_t)p.start_off);
+            r.segs.push_back(sp);
+        }
+        p.nsegs = (uint32_t)r.segs.size() - p.first_seg;
+        p.segs_left.store(p.nsegs, std::memory_order_relaxed);
+    }
+    r.reads_left.store((uint32_t)r.segs.size(), std::memory_order_release);
+    // get_ranges.rs:39-45: one read op per segment onto THIS worker's deque; peers steal them.
+    for (uint32_t s = 0; s < r.segs.size(); s++) {
+        Op op;
+        op.kind = Op::Read;
+        op.req = rp;
+        op.seg = s;
+        wt.push(std::move(op));
+    }
+    return Start::Finished;
+}
+
+// ---- io worker (UringWorker, worker.rs:24-135) ------------------------------------------------
+struct Worker {
+    Group& g;
+    WorkerThread<Op>& wt;
+    Ring ring;
+    Tracker<Op> tracker;
+    std::deque<Op> stalled;
+    Worker(Group& grp, WorkerThread<Op>& w) : g(grp), wt(w), tracker(grp.be->cfg.sq_entries) {}
+
+    // An SQE slot, flushing the SQ first if a burst of completions filled it.
+    io_uring_sqe* must_get_sqe() {
+        io_uring_sqe* e;
+        while (!(e = ring.get_sqe())) {
+            ring.submit();
+            __builtin_ia32_pause();
+        }
+        return e;
+    }
+
+    void push_read_sqe(size_t idx, Op& op) {
+        const SegPlan& sp = op.req->segs[op.seg];
+        const uint64_t phys = op.entry->log_off % g.log.capacity() + op.done;
+        io_uring_sqe* e = must_get_sqe();
+        e->opcode = IORING_OP_READ_FIXED;  // north star: READ_FIXED into the registered ring (reference: Read, sqe.rs:95)
+        e->fd = op.req->fd;
+        e->addr = (uint64_t)(uintptr_t)(g.host_ring + phys);
+        e->len = sp.read_len - op.done;
+        e->off = sp.file_off + op.done;
+        e->buf_index = (uint16_t)(phys / StagingLog::kRegBoundary);
+        e->user_data = UringUserData::pack((uint32_t)idx, IORING_OP_READ_FIXED);
+    }
+
+    Start start(Op& op) {
+        Backend* be = g.be;
+        switch (op.kind) {
+        case Op::GetRanges: {  // get_ranges.rs:49-65: two unlinked SQEs, same slot
+            auto idx = tracker.get_next_index();
+            Request& r = *op.req;
+            memset(&r.stx, 0, sizeof r.stx);
+            io_uring_sqe* e = must_get_sqe();  // sqe.rs:17-28
+            e->opcode = IORING_OP_OPENAT;
+            e->fd = -1;  // dirfd ignored for absolute paths
+            e->addr = (uint64_t)(uintptr_t)r.path.c_str();
+            e->open_flags = O_RDONLY | (be->cfg.o_direct ? O_DIRECT : 0);
+            e->user_data = UringUserData::pack((uint32_t)*idx, IORING_OP_OPENAT);
+            e = must_get_sqe();  // sqe.rs:40-57
+            e->opcode = IORING_OP_STATX;
+            e->fd = -1;
+            e->addr = (uint64_t)(uintptr_t)r.path.c_str();
+            e->off = (uint64_t)(uintptr_t)&r.stx;
+            e->len = STATX_SIZE | STATX_DIOALIGN;
+            e->user_data = UringUserData::pack((uint32_t)*idx, IORING_OP_STATX);
+            tracker.put(*idx, std::move(op));
+            be->stats.requests++;
+            return Start::Started;
+        }
+        case Op::Plan:
+            return plan_request(g, op.req, wt);
+        case Op::Read: {  // get_range.rs:43-51 + sqe.rs:59-122
+            const SegPlan& sp = op.req->segs[op.seg];
+            StageEntry* ent = g.log.alloc(sp.read_len, op.req, op.seg);
+            if (!ent) {
+                be->stats.staging_stalls++;
+                return Start::Retry;
+            }
+            op.entry = ent;
+            op.done = 0;
+            auto idx = tracker.get_next_index();
+            push_read_sqe(*idx, op);
+            tracker.put(*idx, std::move(op));
+            be->stats.reads++;
+            return Start::Started;
+        }
+        case Op::Close:
+            break;
+        }
+        return Start::Finished;
+    }
+
+    void finish_read_accounting(size_t idx, Op& op) {
+        // get_range.rs:78-90: the last reader of the file closes it, re-using this tracker slot
+        Request& r = *op.req;
+        if (r.reads_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+            io_uring_sqe* e = must_get_sqe();  // sqe.rs:126-133
+            e->opcode = IORING_OP_CLOSE;
+            e->fd = r.fd;
+            e->user_data = UringUserData::pack((uint32_t)idx, IORING_OP_CLOSE);
+            r.fd = -1;
+            Op c;
+            c.kind = Op::Close;
+            c.req = op.req;
+            tracker.replace(idx, std::move(c));  // NextStep::ReplaceWith
+            return;
+        }
+        tracker.remove(idx);  // NextStep::Done
+    }
+
+    void handle(const io_uring_cqe& cqe) {
+        Backend* be = g.be;
+        const UringUserData ud = UringUserData::unpack(cqe.user_data);
+        Op* op = tracker.get(ud.index_of_op);
+        if (!op) return;
+        Request& r = *op->req;
+        switch (op->kind) {
+        case Op::GetRanges: {  // get_ranges.rs:67-110
+            if (cqe.res < 0) send_error(be, cqe.res, ud.opcode, r, -1, ud.opcode == IORING_OP_OPENAT ? "openat failed" : "statx failed");
+            r.n_cqes_received++;
+            if (cqe.res >= 0) {
+                if (ud.opcode == IORING_OP_OPENAT) {
+                    r.fd = cqe.res;
+                    r.have_fd = true;
+                } else if (ud.opcode == IORING_OP_STATX) {
+                    r.have_statx = true;
+                }
+            }
+            if (r.n_cqes_received < 2) return;  // NextStep::Pending
+            Op done = tracker.remove(ud.index_of_op);
+            if (r.have_fd && r.have_statx) {
+                done.kind = Op::Plan;
+                if (plan_request(g, done.req, wt) == Start::Retry) stalled.push_back(std::move(done));
+            } else if (r.have_fd) {
+                close(r.fd);  // the reference leaks this fd (Appendix A)
+                r.fd = -1;
+            }
+            return;
+        }
+        case Op::Read: {  // get_range.rs:53-91
+            const SegPlan& sp = r.segs[op->seg];
+            RangePlan& rp = r.ranges[sp.range];
+            if (cqe.res < 0) {
+                send_error(be, cqe.res, IORING_OP_READ_FIXED, r, (int)sp.range, "read failed");
+                rp.failed.store(true, std::memory_order_relaxed);
+                op->entry->state.store(kStageFailed, std::memory_order_release);
+                finish_read_accounting(ud.index_of_op, *op);
+                return;
+            }
+            op->done += (uint32_t)cqe.res;
+            be->stats.read_bytes += (uint64_t)cqe.res;
+            const uint64_t needed = sp.head + sp.payload_len;
+            if (op->done < needed) {  // the reference does not check (get_range.rs:66-68, issue #100)
+                if (cqe.res == 0 || (op->done % kAlign) != 0) {
+                    send_error(be, -EIO, IORING_OP_READ_FIXED, r, (int)sp.range, "short read (unexpected end of file)");
+                    rp.failed.store(true, std::memory_order_relaxed);
+                    op->entry->state.store(kStageFailed, std::memory_order_release);
+                    finish_read_accounting(ud.index_of_op, *op);
+                    return;
+                }
+                be->stats.short_reads++;
+                push_read_sqe(ud.index_of_op, *op);  // read the remainder into the same slot
+                return;
+            }
+            op->entry->landed_ns = now_ns();
+            op->entry->state.store(kStageLanded, std::memory_order_release);
+            finish_read_accounting(ud.index_of_op, *op);
+            return;
+        }
+        case Op::Close:  // close.rs:33-44
+            tracker.remove(ud.index_of_op);
+            return;
+        case Op::Plan:
+            return;
+        }
+    }
+
+    void run() {
+        Backend* be = g.be;
+        const lsio_uring_cuda_config& cfg = be->cfg;
+        int rc = ring.init(cfg.sq_entries, cfg.sqpoll ? 1000 : 0);
+        if (rc == 0) {
+            std::vector<iovec> iov;
+            for (uint64_t o = 0; o < g.log.capacity(); o += StagingLog::kRegBoundary)
+                iov.push_back(iovec{g.host_ring + o, (size_t)std::min<uint64_t>(StagingLog::kRegBoundary, g.log.capacity() - o)});
+            rc = ring.register_buffers(iov.data(), (unsigned)iov.size());
+        }
+        if (rc != 0) {
+            fprintf(stderr, "lsio_b200: io_uring set-up failed on worker %zu: %s\n", wt.id(), strerror(-rc));
+            // keep consuming tasks so callers see errors rather than a hang
+        }
+        const bool ring_ok = rc == 0;
+        const unsigned sq = ring_ok ? ring.sq_entries() : 0;
+        while (true) {
+            const bool running = wt.keep_running();
+            if (!running && tracker.is_empty()) break;
+            unsigned started = 0;
+            if (running) {
+                // top up the SQ (worker.rs:65-88), two SQEs of headroom (MAX_SQ_ENTRIES_PER_ITERATION)
+                while (true) {
+                    if (ring_ok && (tracker.is_full() || ring.sq_len() + 2 > sq || ring.sq_len() + ring.cq_len() + 2 > sq)) break;
+                    Op op;
+                    if (!stalled.empty()) {
+                        op = std::move(stalled.front());
+                        stalled.pop_front();
+                    } else if (auto t = wt.find_task()) {
+                        op = std::move(*t);
+                    } else {
+                        break;
+                    }
+                    if (!ring_ok) {
+                        send_error(be, rc, 0, *op.req, -1, "io_uring unavailable");
+                        continue;
+                    }
+                    const Start s = start(op);
+                    if (s == Start::Retry) {
+                        stalled.push_front(std::move(op));
+                        break;
+                    }
+                    if (s == Start::Started) started++;
+                }
+            }
+            if (ring_ok && ring.unsubmitted()) ring.submit();  // one enter per batch (reference: per op, worker.rs:79)
+            bool got = false;
+            io_uring_cqe cqe;
+            while (ring_ok && ring.pop_cqe(&cqe)) {  // worker.rs:104-122
+                got = true;
+                handle(cqe);
+            }
+            if (ring_ok && ring.unsubmitted()) ring.submit();
+            if (got || started) continue;
+            if (tracker.is_empty() && stalled.empty()) {
+                if (running) wt.park();  // worker.rs:93-99
+                continue;
+            }
+            if (!tracker.is_empty()) ring.submit(1, 200);  // submit_and_wait(1), bounded so new tasks are noticed
+            else std::this_thread::sleep_for(std::chrono::microseconds(50));  // only waiting for staging / HBM space
+        }
+    }
+};
+
+// ---- device thread -----------------------------------------------------------------------------
+static void emit_range(Group& g, Request& r, uint32_t range_idx) {
+    Backend* be = g.be;
+    RangePlan& p = r.ranges[range_idx];
+    if (p.failed.load(std::memory_order_relaxed)) return;  // its errors were already sent; no Chunk (get_range.rs:63)
+    uint32_t crc = 0;
+    for (uint32_t s = 0; s < p.nsegs; s++) {
+        const SegPlan& sp = r.segs[p.first_seg + s];
+        crc = s == 0 ? sp.crc : gf2::crc32c_combine(crc, sp.crc, sp.payload_len);
+    }
+    lsio_output o;
+    memset(&o, 0, sizeof o);
+    o.status = 0;
+    o.kind = LSIO_OUTPUT_CHUNK;
+    o.device = g.device;
+    if (be->cfg.checksum & LSIO_CHECKSUM_CRC32C) {
+        o.checksums |= LSIO_CHECKSUM_CRC32C;
+        o.crc32c = crc;
+    }
+    auto* view = new lsio_aligned_bytes();
+    view->buf = r.buffer;
+    view->start = p.dst_off;
+    view->end = p.dst_off + p.len;
+    o.chunk.buffer = view;
+    o.chunk.user_data = p.user_data;
+    be->stats.payload_bytes += p.len;
+    send_output(be, o);
+}
+
+static void retire_batch(Group& g, Batch& b) {
+    for (uint32_t i = 0; i < b.counts.nsegs; i++) {
+        StageEntry& e = g.log.at(b.seg_seq[i]);
+        Request& r = *e.req;
+        SegPlan& sp = r.segs[e.seg];
+        sp.crc = b.crc_host[i];
+        RangePlan& p = r.ranges[sp.range];
+        if (p.segs_left.fetch_sub(1, std::memory_order_acq_rel) == 1) emit_range(g, r, sp.range);
+    }
+    // failed reads carry no descriptor but still count towards their range
+    for (uint64_t s = b.seq_begin; s < b.seq_end; s++) {
+        StageEntry& e = g.log.at(s);
+        if (e.state.load(std::memory_order_relaxed) == kStageFailed) {
+            RangePlan& p = e.req->ranges[e.req->segs[e.seg].range];
+            p.segs_left.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    g.log.retire_through(b.seq_end);
+}
+
+static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
+    Backend* be = g.be;
+    Batch* b = g.free_batches.front();
+    g.free_batches.pop_front();
+    b->counts = PackBatchCounts();
+    b->seg_seq.clear();
+    b->seq_begin = seq_begin;
+    b->seq_end = seq_end;
+    const uint64_t cap = g.log.capacity();
+    const StageEntry& first = g.log.at(seq_begin);
+    const StageEntry& last = g.log.at(seq_end - 1);
+    const uint64_t phys = first.log_off % cap, bytes = last.log_off + last.len - first.log_off;
+    const bool store = true;
+    const uint32_t flags = LSIO_CUDA_PACK_STORE | ((be->cfg.checksum & LSIO_CHECKSUM_CRC32C) ? LSIO_CUDA_PACK_CRC32C : 0);
+    uint64_t landed_bytes = 0;
+    for (uint64_t s = seq_begin; s < seq_end; s++) {
+        StageEntry& e = g.log.at(s);
+        if (e.state.load(std::memory_order_acquire) != kStageLanded) continue;
+        const SegPlan& sp = e.req->segs[e.seg];
+        lsio_cuda_segment seg;
+        seg.src = (uint64_t)(uintptr_t)(g.dev_ring + e.log_off % cap + sp.head);
+        seg.dst = (uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off);
+        seg.len = sp.payload_len;
+        pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store);  // sized by the caller's limits
+        b->seg_seq.push_back(s);
+        landed_bytes += e.len;
+    }
+    if (landed_bytes) {
+        LSIO_CUDA_TRY(cudaMemcpyAsync(g.dev_ring + phys, g.host_ring + phys, bytes, cudaMemcpyHostToDevice, g.s_copy));
+        LSIO_CUDA_TRY(cudaEventRecord(b->copied, g.s_copy));
+        be->stats.h2d_copies++;
+        be->stats.h2d_bytes += bytes;
+        LSIO_CUDA_TRY(cudaStreamWaitEvent(g.s_pack, b->copied, 0));
+        LSIO_CUDA_TRY(cudaMemcpyAsync(b->dev_desc, b->host_desc, b->lay.upload_bytes, cudaMemcpyHostToDevice, g.s_pack));
+        unsigned launches = 0;
+        int rc = pack_batch_launch(g.device, b->lay, b->dev_desc, b->counts, flags, b->crc_dev, g.s_pack, &launches);
+        if (rc) return rc;
+        be->stats.pack_launches++;
+        be->stats.kernel_launches += launches;
+    }
+    LSIO_CUDA_TRY(cudaEventRecord(b->done, g.s_pack));
+    g.inflight.push_back(b);
+    return 0;
+}
+
+static void device_main(Group& g) {
+    Backend* be = g.be;
+    const lsio_uring_cuda_config& cfg = be->cfg;
+    if (!g.cpus.empty()) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        for (int c : g.cpus) CPU_SET(c, &set);
+        pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+    }
+    cudaSetDevice(g.device);
+    const uint64_t cap = g.log.capacity();
+    const size_t max_segs = g.batches[0].lay.max_segs, max_tiles = g.batches[0].lay.max_tiles;
+    const uint64_t max_batch_bytes = std::max<uint64_t>(cfg.min_copy_bytes * 4, 64ull << 20);
+    unsigned idle_spins = 0;
+    while (true) {
+        bool progressed = false;
+        // 1. retire finished batches in order
+        while (!g.inflight.empty()) {
+            Batch* b = g.inflight.front();
+            cudaError_t q = cudaEventQuery(b->done);
+            if (q == cudaErrorNotReady) break;
+            if (q != cudaSuccess) {
+                cuda_fail(q, "pack batch", __FILE__, __LINE__);
+                fprintf(stderr, "lsio_b200: %s\n", last_error_text().c_str());
+                for (uint32_t i = 0; i < b->counts.nsegs; i++) {
+                    StageEntry& e = g.log.at(b->seg_seq[i]);
+                    RangePlan& p = e.req->ranges[e.req->segs[e.seg].range];
+                    if (!p.failed.exchange(true)) send_error(be, (int)q, 0, *e.req, (int)e.req->segs[e.seg].range, "CUDA error in the H2D/pack stage");
+                }
+            }
+            g.inflight.pop_front();
+            retire_batch(g, *b);
+            g.free_batches.push_back(b);
+            progressed = true;
+        }
+        // 2. extend the copy frontier over landed reads
+        const uint64_t avail = g.log.alloc_seq();
+        if (g.copy_seq < avail && !g.free_batches.empty()) {
+            uint64_t s = g.copy_seq, bytes = 0, run_phys0 = g.log.at(s).log_off % cap;
+            size_t nsegs = 0, ntiles = 0;
+            uint64_t oldest = 0;
+            bool hit_limit = false;
+            for (; s < avail; s++) {
+                StageEntry& e = g.log.at(s);
+                const uint32_t st = e.state.load(std::memory_order_acquire);
+                if (st == kStageReading) break;
+                if (e.log_off % cap < run_phys0) {  // the ring wrapped: a copy must be physically contiguous
+                    hit_limit = true;
+                    break;
+                }
+                size_t t = 0;
+                if (st == kStageLanded) {
+                    const SegPlan& sp = e.req->segs[e.seg];
+                    t = pack_tile_count((uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off), sp.payload_len);
+                    if (!oldest) oldest = e.landed_ns;
+                }
+                if (nsegs + 1 > max_segs || ntiles + t > max_tiles || (bytes && bytes + e.len > max_batch_bytes)) {
+                    hit_limit = true;
+                    break;
+                }
+                nsegs++;
+                ntiles += t;
+                bytes = e.log_off + e.len - g.log.at(g.copy_seq).log_off;
+            }
+            if (s > g.copy_seq) {
+                const bool draining = g.stop_device.load(std::memory_order_relaxed);
+                const bool timed_out = oldest && now_ns() - oldest > (uint64_t)cfg.flush_us * 1000;
+                if (hit_limit || bytes >= cfg.min_copy_bytes || timed_out || draining || (!oldest)) {
+                    int rc = flush_run(g, g.copy_seq, s);
+                    if (rc) fprintf(stderr, "lsio_b200: flush failed: %s\n", last_error_text().c_str());
+                    g.copy_seq = s;
+                    progressed = true;
+                }
+            }
+        }
+        if (progressed) {
+            idle_spins = 0;
+            continue;
+        }
+        if (g.stop_device.load(std::memory_order_acquire) && g.workers_alive.load(std::memory_order_acquire) == 0 && g.inflight.empty() &&
+            g.copy_seq == g.log.alloc_seq())
+            break;
+        // 3. wait: spin briefly while work is in flight, sleep when idle
+        if (g.log.empty() && g.inflight.empty()) std::this_thread::sleep_for(std::chrono::microseconds(100));
+        else if (++idle_spins > 200) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        else
+            for (int i = 0; i < 50; i++) __builtin_ia32_pause();
+    }
+}
+
+// ---- construction / teardown ----------------------------------------------------------------------
+static std::vector<int> numa_cpus_of_device(int device) {
+    std::vector<int> cpus;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return cpus;
+    std::string b(bus);
+    std::transform(b.begin(), b.end(), b.begin(), ::tolower);
+    int node = -1;
+    {
+        std::ifstream f("/sys/bus/pci/devices/" + b + "/numa_node");
+        if (!(f >> node)) node = -1;
+    }
+    if (node < 0) return cpus;
+    std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+    std::string list;
+    if (!std::getline(f, list)) return cpus;
+    std::stringstream ss(list);
+    std::string part;
+    while (std::getline(ss, part, ',')) {
+        int a, z;
+        if (sscanf(part.c_str(), "%d-%d", &a, &z) == 2) for (int c = a; c <= z; c++) cpus.push_back(c);
+        else if (sscanf(part.c_str(), "%d", &a) == 1) cpus.push_back(a);
+    }
+    return cpus;
+}
+
+static void free_group_cuda(Group& g) {
+    DeviceGuard dg(g.device);
+    for (Batch& b : g.batches) {
+        if (b.host_desc) cudaFreeHost(b.host_desc);
+        if (b.dev_desc) cudaFree(b.dev_desc);
+        if (b.crc_host) cudaFreeHost(b.crc_host);
+        if (b.copied) cudaEventDestroy(b.copied);
+        if (b.done) cudaEventDestroy(b.done);
+    }
+    g.batches.clear();
+    if (g.s_copy) cudaStreamDestroy(g.s_copy);
+    if (g.s_pack) cudaStreamDestroy(g.s_pack);
+    if (g.host_ring) cudaFreeHost(g.host_ring);
+    if (g.dev_ring) cudaFree(g.dev_ring);
+    g.s_copy = g.s_pack = nullptr;
+    g.host_ring = g.dev_ring = nullptr;
+}
+
+static int init_group(Group& g) {
+    const lsio_uring_cuda_config& cfg = g.be->cfg;
+    DeviceGuard dg(g.device);
+    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+    int rc = pack_prepare_device(g.device);
+    if (rc) return rc;
+    if (cfg.pin_threads) g.cpus = numa_cpus_of_device(g.device);
+    const uint64_t ring_bytes = cfg.staging_bytes / 4096 * 4096;
+    // pinned (page-locked, DMA-able) and later registered with every worker's io_uring
+    LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.host_ring, ring_bytes, cudaHostAllocPortable));
+    LSIO_CUDA_TRY(cudaMalloc((void**)&g.dev_ring, ring_bytes));
+    g.log.init(ring_bytes, 1 << 16);
+    uint8_t* arena_base = nullptr;
+    LSIO_CUDA_TRY(cudaMalloc((void**)&arena_base, cfg.arena_bytes));
+    g.arena = std::make_shared<DeviceArena>(g.device, arena_base, cfg.arena_bytes, [](int dev, void* p) {
+        DeviceGuard d(dev);
+        cudaFree(p);
+    });
+    LSIO_CUDA_TRY(cudaStreamCreateWithFlags(&g.s_copy, cudaStreamNonBlocking));
+    LSIO_CUDA_TRY(cudaStreamCreateWithFlags(&g.s_pack, cudaStreamNonBlocking));
+    const size_t max_segs = 8192, max_tiles = 1 << 16;
+    g.batches.resize(8);
+    for (Batch& b : g.batches) {
+        b.lay = pack_batch_layout(max_segs, max_tiles);
+        LSIO_CUDA_TRY(cudaHostAlloc((void**)&b.host_desc, b.lay.upload_bytes, cudaHostAllocPortable));
+        LSIO_CUDA_TRY(cudaMalloc((void**)&b.dev_desc, b.lay.total_bytes));
+        LSIO_CUDA_TRY(cudaHostAlloc((void**)&b.crc_host, max_segs * 4, cudaHostAllocPortable | cudaHostAllocMapped));
+        LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&b.crc_dev, b.crc_host, 0));
+        LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
+        LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        b.seg_seq.reserve(max_segs);
+        g.free_batches.push_back(&b);
+    }
+    return 0;
+}
+
+}  // namespace lsio
+
+struct lsio_uring_cuda {
+    std::unique_ptr<lsio::Backend> be;
+};
+struct lsio_completion {
+    std::shared_ptr<lsio::OutChannel> ch;
+};
+
+using namespace lsio;
+
+extern "C" {
+
+void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->n_worker_threads = 4;
+    cfg->n_devices = 1;
+    cfg->devices[0] = 0;
+    cfg->sq_entries = 64;          // worker.rs:17
+    cfg->sqpoll = 0;               // the reference uses SQPOLL (one kernel thread per ring); off here: submissions are batched
+    cfg->completion_bound = 1024;  // io_uring.rs:16
+    cfg->checksum = LSIO_CHECKSUM_CRC32C;
+    cfg->pack_align = 1;
+    cfg->pin_threads = 1;
+    cfg->o_direct = 1;             // sqe.rs:25
+    cfg->staging_bytes = 1ull << 30;
+    cfg->arena_bytes = 8ull << 30;
+    cfg->max_read_bytes = 8ull << 20;
+    cfg->min_copy_bytes = 8ull << 20;
+    cfg->flush_us = 200;
+}
+
+int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {
+    if (!cfgp || !out) return -EINVAL;
+    lsio_uring_cuda_config cfg = *cfgp;
+    if (cfg.n_worker_threads == 0 || cfg.n_devices == 0 || cfg.n_devices > LSIO_MAX_DEVICES || cfg.sq_entries < 4 ||
+        (cfg.sq_entries & (cfg.sq_entries - 1)) || cfg.staging_bytes < (4ull << 20) || cfg.arena_bytes < (1ull << 20) || cfg.max_read_bytes < kAlign ||
+        cfg.max_read_bytes > (1ull << 31) - kAlign || cfg.max_read_bytes > cfg.staging_bytes / 4) {
+        set_error("invalid lsio_uring_cuda_config");
+        return -EINVAL;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no usable CUDA device (%s): this backend has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return e == cudaSuccess ? -ENODEV : (int)e;
+    }
+    auto be = std::make_unique<Backend>();
+    be->cfg = cfg;
+    be->out = std::make_shared<OutChannel>(cfg.completion_bound ? cfg.completion_bound : 1024);
+    for (uint32_t i = 0; i < cfg.n_devices; i++) {
+        if (cfg.devices[i] < 0 || cfg.devices[i] >= ndev) {
+            set_error("device %d not present (%d devices)", cfg.devices[i], ndev);
+            for (auto& g : be->groups) free_group_cuda(*g);
+            return -ENODEV;
+        }
+        auto g = std::make_unique<Group>();
+        g->be = be.get();
+        g->index = (int)i;
+        g->device = cfg.devices[i];
+        int rc = init_group(*g);
+        if (rc) {
+            set_error("device %d set-up failed: %s", g->device, last_error_text().c_str());
+            free_group_cuda(*g);
+            for (auto& o : be->groups) free_group_cuda(*o);
+            return rc;
+        }
+        be->groups.push_back(std::move(g));
+    }
+    // senders: every io worker and every device thread
+    for (auto& gp : be->groups) {
+        Group* g = gp.get();
+        for (uint32_t w = 0; w < cfg.n_worker_threads + 1; w++) be->out->add_sender();
+        g->workers_alive.store(cfg.n_worker_threads);
+        g->device_thread = std::thread([g] {
+            device_main(*g);
+            g->be->out->remove_sender();
+        });
+        g->pool = std::make_unique<ThreadPool<Op>>(cfg.n_worker_threads, [g](WorkerThread<Op>& wt) {
+            {
+                Worker w(*g, wt);
+                w.run();
+            }
+            g->workers_alive.fetch_sub(1, std::memory_order_acq_rel);
+            g->be->out->remove_sender();
+        }, g->cpus);
+    }
+    auto* h = new lsio_uring_cuda();
+    h->be = std::move(be);
+    *out = h;
+    return 0;
+}
+
+int lsio_uring_cuda_new(size_t n_worker_threads, lsio_uring_cuda** out) {
+    lsio_uring_cuda_config cfg;
+    lsio_uring_cuda_config_default(&cfg);
+    cfg.n_worker_threads = (uint32_t)n_worker_threads;
+    return lsio_uring_cuda_new_with_config(&cfg, out);
+}
+
+static int submit(lsio_uring_cuda* self, int group, const char* location, const int64_t* rs, const int64_t* re, size_t n, const uint64_t* ud,
+                  size_t nud) {
+    if (!self || !location || ((!rs || !re || !ud) && n)) return -EINVAL;
+    if (n != nud) return -EINVAL;           // assert_eq!(ranges.len(), user_data.len()), get_ranges.rs:28
+    if (location[0] != '/') return -EINVAL;  // dirfd = -1: the path must be absolute (sqe.rs:22)
+    Backend* be = self->be.get();
+    if (be->closing.load()) return -ESHUTDOWN;
+    auto r = std::make_shared<Request>();
+    r->path = location;  // the reference takes ownership of its inputs; we copy (lsio_io lib.rs:38-40)
+    r->starts.assign(rs, rs + n);
+    r->ends.assign(re, re + n);
+    r->user_data.assign(ud, ud + n);
+    const size_t gi = group >= 0 ? (size_t)group : (size_t)(be->rr.fetch_add(1) % be->groups.size());
+    if (gi >= be->groups.size()) return -EINVAL;
+    r->grp = be->groups[gi].get();
+    Op op;
+    op.kind = Op::GetRanges;
+    op.req = std::move(r);
+    be->groups[gi]->pool->push(std::move(op));  // threadpool.rs:134-137
+    return 0;
+}
+
+int lsio_uring_cuda_get_ranges(lsio_uring_cuda* self, const char* location, const int64_t* range_start, const int64_t* range_end, size_t n_ranges,
+                               const uint64_t* user_data, size_t n_user_data) {
+    return submit(self, -1, location, range_start, range_end, n_ranges, user_data, n_user_data);
+}
+int lsio_uring_cuda_get_ranges_on(lsio_uring_cuda* self, uint32_t group, const char* location, const int64_t* range_start, const int64_t* range_end,
+                                  size_t n_ranges, const uint64_t* user_data, size_t n_user_data) {
+    return submit(self, (int)group, location, range_start, range_end, n_ranges, user_data, n_user_data);
+}
+
+lsio_completion* lsio_uring_cuda_completion(lsio_uring_cuda* self) {
+    if (!self) return nullptr;
+    auto* c = new lsio_completion();
+    c->ch = self->be->out;
+    return c;
+}
+
+int lsio_uring_cuda_get_stats(const lsio_uring_cuda* self, lsio_uring_cuda_stats* o) {
+    if (!self || !o) return -EINVAL;
+    const Stats& s = self->be->stats;
+    o->requests = s.requests; o->ranges = s.ranges; o->reads = s.reads; o->short_reads = s.short_reads; o->read_bytes = s.read_bytes;
+    o->h2d_copies = s.h2d_copies; o->h2d_bytes = s.h2d_bytes; o->pack_launches = s.pack_launches; o->kernel_launches = s.kernel_launches;
+    o->payload_bytes = s.payload_bytes; o->chunks_ok = s.chunks_ok; o->errors = s.errors; o->staging_stalls = s.staging_stalls;
+    o->arena_stalls = s.arena_stalls;
+    return 0;
+}
+
+const char* lsio_uring_cuda_last_error(void) { return g_last_error.c_str(); }
+
+void lsio_uring_cuda_free(lsio_uring_cuda* self) {
+    if (!self) return;
+    Backend* be = self->be.get();
+    be->closing.store(true);
+    // A consumer that stopped reading must not wedge the teardown: drain undelivered items while joining.
+    std::atomic<bool> joined{false};
+    std::thread drainer([&] {
+        lsio_output o;
+        while (!joined.load()) {
+            if (be->out->len() >= be->cfg.completion_bound && be->out->try_pop(&o)) {
+                if (o.status == 0 && o.chunk.buffer) delete o.chunk.buffer;
+            } else {
+                std::this_thread::sleep_for(std::chrono::milliseconds(1));
+            }
+        }
+    });
+    for (auto& g : be->groups) g->pool->shutdown();  // Drop for ThreadPool, threadpool.rs:140-165
+    for (auto& g : be->groups) {
+        g->stop_device.store(true, std::memory_order_release);
+        if (g->device_thread.joinable()) g->device_thread.join();
+    }
+    joined.store(true);
+    drainer.join();
+    for (auto& g : be->groups) free_group_cuda(*g);
+    delete self;  // chunks already handed out keep the arena alive through their InnerBuffer
+}
+
+lsio_completion* lsio_completion_clone(const lsio_completion* self) { return self ? new lsio_completion(*self) : nullptr; }
+int lsio_completion_recv(lsio_completion* self, lsio_output* out, int timeout_ms) {
+    if (!self || !out) return -EINVAL;
+    return (int)self->ch->recv(out, timeout_ms);
+}
+int lsio_completion_try_recv(lsio_completion* self, lsio_output* out) {
+    if (!self || !out) return -EINVAL;
+    return (int)self->ch->recv(out, 0);
+}
+size_t lsio_completion_len(const lsio_completion* self) { return self ? self->ch->len() : 0; }
+void lsio_completion_drop(lsio_completion* self) {
+    if (!self) return;
+    // the last receiver releases chunks nobody will ever read
+    if (self->ch.use_count() == 1) {
+        lsio_output o;
+        while (self->ch->try_pop(&o))
+            if (o.status == 0 && o.chunk.buffer) delete o.chunk.buffer;
+    }
+    delete self;
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+// pack_batch.hpp -- host-side batch building/launching for the pack_strip_crc32c kernel
+// (pack_crc.cu), shared by the public plan API and the pipeline (io_uring_cuda.cpp).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "lsio_cuda.h"
+
+namespace lsio {
+
+// Memory layout of one batch's descriptor block (same offsets on host and device):
+//   Seg[max_segs] | uint2 tiles[max_tiles] | u32 multi[max_segs] || u32 partials[max_tiles]
+// Only the part before `||` (upload_bytes) is written by the host and copied to the device.
+struct PackBatchLayout {
+    size_t max_segs = 0, max_tiles = 0;
+    size_t off_tiles = 0, off_multi = 0, off_partials = 0;
+    size_t upload_bytes = 0, total_bytes = 0;
+};
+PackBatchLayout pack_batch_layout(size_t max_segs, size_t max_tiles);
+
+// Tiles the kernel cuts a segment into (destination-space geometry; >= 1).
+size_t pack_tile_count(uint64_t dst, uint64_t len);
+
+struct PackBatchCounts {
+    uint32_t nsegs = 0, ntiles = 0, nmulti = 0;
+    uint64_t payload = 0;
+};
+// Appends one segment to a host block; returns false if it does not fit the layout.
+bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCounts* c, const lsio_cuda_segment& seg, bool store);
+
+// One-time per-device set-up (GF(2) tables to the device, kernel attributes). 0 or error code.
+int pack_prepare_device(int device);
+// Enqueues the pack kernel (+ fold kernel if any segment spans several tiles). The device must
+// be current. Returns 0 or a cudaError_t.
+int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, const PackBatchCounts& c, uint32_t flags,
+                      uint32_t* crc_out, cudaStream_t stream, unsigned* launches);
+
+}  // namespace lsio

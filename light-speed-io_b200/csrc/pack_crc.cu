@@ -34,7 +34,9 @@
 //    message; xorout is a final NOT.  Segments shorter than 4 bytes take a scalar path.
 //  * Grid: one 1024-thread CTA per SM (persistent), tiles dealt round-robin to warps.
 #include "common.hpp"
+#include "gf2.hpp"
 #include "lsio_cuda.h"
+#include "pack_batch.hpp"
 
 #include <mutex>
 #include <vector>
@@ -42,7 +44,7 @@
 namespace lsio {
 namespace {
 
-constexpr uint32_t kPoly = 0x82F63B78u;  // CRC-32C, reflected
+constexpr uint32_t kPoly = gf2::kPoly;  // CRC-32C, reflected
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTileRows = 32;                 // rows of 512 B per tile
@@ -66,31 +68,9 @@ constexpr int kSmF = kSmZ + 32;
 constexpr int kSmWords = kSmF + 16 * 32;
 constexpr size_t kSmBytes = (size_t)kSmWords * 4;
 
-// ---- host GF(2)[x]/P arithmetic, reflected representation: bit 31 <-> x^0 ------------------
-uint32_t mul_x(uint32_t b) { return (b >> 1) ^ (kPoly & (0u - (b & 1u))); }
-uint32_t div_x(uint32_t b) { return (b & 0x80000000u) ? (((b ^ kPoly) << 1) | 1u) : (b << 1); }
-uint32_t multmodp(uint32_t a, uint32_t b) {
-    uint32_t p = 0;
-    for (uint32_t m = 0x80000000u; m; m >>= 1) {
-        if (a & m) p ^= b;
-        b = mul_x(b);
-    }
-    return p;
-}
-uint32_t xpow(int64_t n) {  // x^n mod P (n may be negative: x is invertible since P(0) = 1)
-    uint32_t r = 0x80000000u;
-    if (n < 0) {
-        for (int64_t i = 0; i < -n; i++) r = div_x(r);
-        return r;
-    }
-    uint32_t base = 0x40000000u;  // x
-    while (n) {
-        if (n & 1) r = multmodp(r, base);
-        base = multmodp(base, base);
-        n >>= 1;
-    }
-    return r;
-}
+using gf2::mul_x;
+using gf2::multmodp;
+using gf2::xpow;
 void fill_byte_tables(uint32_t* t, uint32_t k) {  // t[b][v] = (v << 8b) * k
     for (int b = 0; b < 4; b++)
         for (uint32_t v = 0; v < 256; v++) t[b * 256 + v] = multmodp(v << (8 * b), k);
@@ -410,24 +390,8 @@ __global__ void __launch_bounds__(256) fold_kernel(const Params p) {
 
 }  // namespace
 
-// ---- plan ---------------------------------------------------------------------------------
+// ---- host side: batches and plans ------------------------------------------------------------
 }  // namespace lsio
-
-struct lsio_cuda_pack_plan {
-    int device = 0;
-    uint32_t flags = 0;
-    size_t nsegs = 0;
-    uint32_t ntiles = 0;
-    uint64_t payload = 0;
-    int sms = 0;
-    void* dev_block = nullptr;  // one allocation: segs | tiles | partials | multi
-    lsio::Seg* d_segs = nullptr;
-    uint2* d_tiles = nullptr;
-    uint32_t* d_partials = nullptr;
-    uint32_t* d_multi = nullptr;
-    uint32_t nmulti = 0;
-    const uint32_t* d_tables = nullptr;
-};
 
 namespace lsio {
 
@@ -436,6 +400,8 @@ static int get_device_tables(int device, const uint32_t** out, int* sms) {
     DeviceTables& dt = device_tables();
     std::lock_guard<std::mutex> lk(dt.mu);
     if (!dt.dev[device]) {
+        DeviceGuard dg(device);
+        if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
         const std::vector<uint32_t>& h = host_tables();
         uint32_t* d = nullptr;
         LSIO_CUDA_TRY(cudaMalloc(&d, h.size() * 4));
@@ -452,8 +418,12 @@ static int get_device_tables(int device, const uint32_t** out, int* sms) {
     return 0;
 }
 
-// Host-side tiling shared by the plan API and the pipeline (pipeline.cpp builds its batches
-// in pinned memory with the same routine).
+int pack_prepare_device(int device) {
+    const uint32_t* t;
+    int sms;
+    return get_device_tables(device, &t, &sms);
+}
+
 size_t pack_tile_count(uint64_t dst, uint64_t len) {
     if (len < 4) return 1;
     const uint64_t a0 = dst & ~15ull, a1 = (dst + len + 15ull) & ~15ull;
@@ -461,48 +431,104 @@ size_t pack_tile_count(uint64_t dst, uint64_t len) {
     return (size_t)((nvec + kTileVecs - 1) / kTileVecs);
 }
 
+PackBatchLayout pack_batch_layout(size_t max_segs, size_t max_tiles) {
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    PackBatchLayout l;
+    l.max_segs = max_segs;
+    l.max_tiles = max_tiles;
+    l.off_tiles = up(max_segs * sizeof(Seg));
+    l.off_multi = l.off_tiles + up(max_tiles * sizeof(uint2));
+    l.upload_bytes = l.off_multi + up(max_segs * 4);
+    l.off_partials = l.upload_bytes;
+    l.total_bytes = l.off_partials + up(max_tiles * 4);
+    return l;
+}
+
+bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCounts* c, const lsio_cuda_segment& seg, bool store) {
+    const uint64_t d = store ? seg.dst : seg.src;
+    const size_t nt = pack_tile_count(d, seg.len);
+    if (c->nsegs + 1 > lay.max_segs || c->ntiles + nt > lay.max_tiles) return false;
+    char* base = (char*)host_block;
+    Seg* segs = (Seg*)base;
+    uint2* tiles = (uint2*)(base + lay.off_tiles);
+    uint32_t* multi = (uint32_t*)(base + lay.off_multi);
+    segs[c->nsegs] = Seg{seg.src, seg.dst, seg.len, c->ntiles, (uint32_t)nt};
+    // first tile in memory order first, so neighbouring warps touch neighbouring memory
+    for (size_t k = nt; k-- > 0;) tiles[c->ntiles++] = make_uint2(c->nsegs, (unsigned)k);
+    if (nt > 1) multi[c->nmulti++] = c->nsegs;
+    c->nsegs++;
+    c->payload += seg.len;
+    return true;
+}
+
+int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, const PackBatchCounts& c, uint32_t flags,
+                      uint32_t* crc_out, cudaStream_t st, unsigned* launches) {
+    const bool store = flags & LSIO_CUDA_PACK_STORE, crc = flags & LSIO_CUDA_PACK_CRC32C;
+    if (launches) *launches = 0;
+    if (c.ntiles == 0) return 0;
+    const uint32_t* tables = nullptr;
+    int sms = 0;
+    int rc = get_device_tables(device, &tables, &sms);
+    if (rc) return rc;
+    char* base = (char*)dev_block;
+    Params p{(const Seg*)base, (const uint2*)(base + lay.off_tiles), c.ntiles, (uint32_t*)(base + lay.off_partials),
+             (const uint32_t*)(base + lay.off_multi), c.nmulti, crc_out, tables};
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms, c.ntiles);
+    if (store && crc) pack_kernel<true, true><<<grid, kThreads, kSmBytes, st>>>(p);
+    else if (crc) pack_kernel<false, true><<<grid, kThreads, kSmBytes, st>>>(p);
+    else pack_kernel<true, false><<<grid, kThreads, 0, st>>>(p);
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    if (launches) ++*launches;
+    LSIO_CUDA_TRY(cudaGetLastError());
+    if (crc && c.nmulti) {
+        const unsigned fgrid = (c.nmulti + 7) / 8;
+        if (store) fold_kernel<true><<<fgrid, 256, 0, st>>>(p);
+        else fold_kernel<false><<<fgrid, 256, 0, st>>>(p);
+        launch_counter().fetch_add(1, std::memory_order_relaxed);
+        if (launches) ++*launches;
+        LSIO_CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
 }  // namespace lsio
+
+struct lsio_cuda_pack_plan {
+    int device = 0;
+    uint32_t flags = 0;
+    lsio::PackBatchLayout lay;
+    lsio::PackBatchCounts counts;
+    void* dev_block = nullptr;
+};
 
 extern "C" {
 
 int lsio_cuda_pack_plan_create(int device, const lsio_cuda_segment* segs, size_t n, uint32_t flags, lsio_cuda_pack_plan** out) {
     using namespace lsio;
     if (!out || (!segs && n) || !(flags & (LSIO_CUDA_PACK_STORE | LSIO_CUDA_PACK_CRC32C))) return -EINVAL;
-    DeviceGuard dg(device);
-    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
     const bool store = flags & LSIO_CUDA_PACK_STORE;
-    std::vector<Seg> hs(n);
-    std::vector<uint2> ht;
-    std::vector<uint32_t> hm;
-    uint64_t payload = 0;
+    size_t ntiles = 0;
     for (size_t i = 0; i < n; i++) {
         if (segs[i].len >= (1ull << 34)) return -EFBIG;  // vector indices are 32-bit in the kernel
-        const uint64_t d = store ? segs[i].dst : segs[i].src;
-        const size_t nt = pack_tile_count(d, segs[i].len);
-        if (ht.size() + nt > 0xFFFFFFF0ull) return -EFBIG;
-        hs[i] = Seg{segs[i].src, segs[i].dst, segs[i].len, (uint32_t)ht.size(), (uint32_t)nt};
-        // first tile in memory order first, so neighbouring warps touch neighbouring memory
-        for (size_t k = nt; k-- > 0;) ht.push_back(make_uint2((unsigned)i, (unsigned)k));
-        if (nt > 1) hm.push_back((uint32_t)i);
-        payload += segs[i].len;
+        ntiles += pack_tile_count(store ? segs[i].dst : segs[i].src, segs[i].len);
     }
+    if (ntiles > 0xFFFFFFF0ull || n > 0xFFFFFFF0ull) return -EFBIG;
+    int rc = pack_prepare_device(device);
+    if (rc) return rc;
+    DeviceGuard dg(device);
+    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
     auto* plan = new lsio_cuda_pack_plan();
-    plan->device = device; plan->flags = flags; plan->nsegs = n; plan->ntiles = (uint32_t)ht.size(); plan->payload = payload;
-    int rc = get_device_tables(device, &plan->d_tables, &plan->sms);
-    if (rc) { delete plan; return rc; }
-    const size_t b_segs = (n * sizeof(Seg) + 255) & ~size_t(255), b_tiles = (ht.size() * sizeof(uint2) + 255) & ~size_t(255);
-    const size_t b_parts = (ht.size() * 4 + 255) & ~size_t(255), b_cnt = (hm.size() * 4 + 255) & ~size_t(255);
-    cudaError_t e = cudaMalloc(&plan->dev_block, b_segs + b_tiles + b_parts + b_cnt + 256);
-    if (e != cudaSuccess) { delete plan; return cuda_fail(e, "cudaMalloc(plan)", __FILE__, __LINE__); }
-    char* base = (char*)plan->dev_block;
-    plan->d_segs = (Seg*)base; plan->d_tiles = (uint2*)(base + b_segs);
-    plan->d_partials = (uint32_t*)(base + b_segs + b_tiles); plan->d_multi = (uint32_t*)(base + b_segs + b_tiles + b_parts);
-    plan->nmulti = (uint32_t)hm.size();
-    if (n) {
-        e = cudaMemcpy(plan->d_segs, hs.data(), n * sizeof(Seg), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(plan->d_tiles, ht.data(), ht.size() * sizeof(uint2), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && !hm.empty()) e = cudaMemcpy(plan->d_multi, hm.data(), hm.size() * 4, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cudaFree(plan->dev_block); delete plan; return cuda_fail(e, "plan upload", __FILE__, __LINE__); }
+    plan->device = device;
+    plan->flags = flags;
+    plan->lay = pack_batch_layout(n ? n : 1, ntiles ? ntiles : 1);
+    std::vector<char> host(plan->lay.upload_bytes);
+    for (size_t i = 0; i < n; i++) pack_batch_append(plan->lay, host.data(), &plan->counts, segs[i], store);
+    cudaError_t e = cudaMalloc(&plan->dev_block, plan->lay.total_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(plan->dev_block, host.data(), plan->lay.upload_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (plan->dev_block) cudaFree(plan->dev_block);
+        delete plan;
+        return cuda_fail(e, "plan upload", __FILE__, __LINE__);
     }
     *out = plan;
     return 0;
@@ -511,34 +537,17 @@ int lsio_cuda_pack_plan_create(int device, const lsio_cuda_segment* segs, size_t
 int lsio_cuda_pack_plan_launch(lsio_cuda_pack_plan* plan, uint32_t* crc_out_dev, void* stream) {
     using namespace lsio;
     if (!plan) return -EINVAL;
-    const bool store = plan->flags & LSIO_CUDA_PACK_STORE, crc = plan->flags & LSIO_CUDA_PACK_CRC32C;
-    if (crc && !crc_out_dev && plan->nsegs) return -EINVAL;
-    if (plan->ntiles == 0) return 0;
+    if ((plan->flags & LSIO_CUDA_PACK_CRC32C) && !crc_out_dev && plan->counts.nsegs) return -EINVAL;
     DeviceGuard dg(plan->device);
     if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
-    Params p{plan->d_segs, plan->d_tiles, plan->ntiles, plan->d_partials, plan->d_multi, plan->nmulti, crc_out_dev, plan->d_tables};
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)plan->sms, plan->ntiles);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (store && crc) pack_kernel<true, true><<<grid, kThreads, kSmBytes, st>>>(p);
-    else if (crc) pack_kernel<false, true><<<grid, kThreads, kSmBytes, st>>>(p);
-    else pack_kernel<true, false><<<grid, kThreads, 0, st>>>(p);
-    launch_counter().fetch_add(1, std::memory_order_relaxed);
-    LSIO_CUDA_TRY(cudaGetLastError());
-    if (crc && plan->nmulti) {
-        const unsigned fgrid = (plan->nmulti + 7) / 8;
-        if (store) fold_kernel<true><<<fgrid, 256, 0, st>>>(p);
-        else fold_kernel<false><<<fgrid, 256, 0, st>>>(p);
-        launch_counter().fetch_add(1, std::memory_order_relaxed);
-        LSIO_CUDA_TRY(cudaGetLastError());
-    }
-    return 0;
+    return pack_batch_launch(plan->device, plan->lay, plan->dev_block, plan->counts, plan->flags, crc_out_dev, (cudaStream_t)stream, nullptr);
 }
 
 uint64_t lsio_cuda_pack_plan_algorithmic_bytes(const lsio_cuda_pack_plan* plan) {
     if (!plan) return 0;
-    return (plan->flags & LSIO_CUDA_PACK_STORE) ? 2 * plan->payload : plan->payload;
+    return (plan->flags & LSIO_CUDA_PACK_STORE) ? 2 * plan->counts.payload : plan->counts.payload;
 }
-uint64_t lsio_cuda_pack_plan_num_tiles(const lsio_cuda_pack_plan* plan) { return plan ? plan->ntiles : 0; }
+uint64_t lsio_cuda_pack_plan_num_tiles(const lsio_cuda_pack_plan* plan) { return plan ? plan->counts.ntiles : 0; }
 
 void lsio_cuda_pack_plan_destroy(lsio_cuda_pack_plan* plan) {
     if (!plan) return;

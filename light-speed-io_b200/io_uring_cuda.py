@@ -1,0 +1,197 @@
+"""Python mirror of `lsio_io` (Reader / Completion / Chunk / Output) and of the backend
+`lsio_uring::IoUring`, over include/lsio_io.h and include/lsio_uring_cuda.h.
+
+    reference                                                here
+    IoUring::new(n_worker_threads)   io_uring.rs:15          IoUringCuda(n_worker_threads, ...)
+    Reader::get_ranges               lsio_io lib.rs:36-44    IoUringCuda.get_ranges(location, ranges, user_data)
+    Completion::completion           lsio_io lib.rs:11-13    IoUringCuda.completion() -> Receiver
+    Receiver::recv_timeout / recv    crossbeam-channel       Receiver.recv_timeout(seconds) / recv() / try_recv()
+    Chunk { buffer, user_data }      lsio_io lib.rs:50-56    Chunk.buffer (AlignedBytes, device view), Chunk.user_data
+    Err(anyhow::Error)               operation.rs:82-100     IoError item (returned, not raised -- it is a channel item)
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _native as N
+from .aligned_bytes import AlignedBytes
+
+
+class RecvTimeoutError(Exception):
+    """crossbeam_channel::RecvTimeoutError::Timeout"""
+
+
+class Disconnected(Exception):
+    """crossbeam_channel::RecvTimeoutError::Disconnected / RecvError"""
+
+
+class Chunk:
+    """lsio_io::Chunk (lib.rs:50-56), plus the device-side proof of its bytes."""
+
+    __slots__ = ("buffer", "user_data", "crc32c", "xxh64", "device")
+
+    def __init__(self, buffer, user_data, crc32c, xxh64, device):
+        self.buffer, self.user_data, self.crc32c, self.xxh64, self.device = buffer, user_data, crc32c, xxh64, device
+
+    def is_ok(self):
+        return True
+
+    def __repr__(self):
+        return f"Chunk(user_data={self.user_data}, len={self.buffer.len()}, device={self.device}, crc32c={self.crc32c})"
+
+
+class IoError:
+    """An `Err(anyhow::Error)` item of the completion channel (operation.rs:82-100)."""
+
+    __slots__ = ("status", "opcode", "user_data", "context")
+
+    def __init__(self, status, opcode, user_data, context):
+        self.status, self.opcode, self.user_data, self.context = status, opcode, user_data, context
+
+    @property
+    def errno(self):
+        return -self.status if self.status < 0 else None
+
+    def is_ok(self):
+        return False
+
+    def __repr__(self):
+        return f"IoError(status={self.status}, opcode={self.opcode}, user_data={self.user_data}, context={self.context!r})"
+
+
+def _convert(o):
+    if o.status == 0:
+        crc = o.crc32c if (o.checksums & N.CHECKSUM_CRC32C) else None
+        xx = o.xxh64 if (o.checksums & N.CHECKSUM_XXH64) else None
+        return Chunk(AlignedBytes(o.chunk.buffer), o.chunk.user_data, crc, xx, o.device)
+    return IoError(o.status, o.opcode, o.chunk.user_data, o.context.decode(errors="replace"))
+
+
+class Receiver:
+    """The backend's completion queue: cloneable, usable from any thread, outlives the backend."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def clone(self):
+        return Receiver(N.lib.lsio_completion_clone(self._h))
+
+    def _recv(self, timeout_ms):
+        o = N.COutput()
+        rc = N.lib.lsio_completion_recv(self._h, ctypes.byref(o), timeout_ms)
+        if rc == N.RECV_TIMEOUT:
+            raise RecvTimeoutError()
+        if rc == N.RECV_DISCONNECTED:
+            raise Disconnected()
+        if rc != N.RECV_OK:
+            raise RuntimeError(f"lsio_completion_recv: {rc}")
+        return _convert(o)
+
+    def recv(self):
+        return self._recv(-1)
+
+    def recv_timeout(self, seconds):
+        return self._recv(max(0, int(seconds * 1000)))
+
+    def try_recv(self):
+        return self._recv(0)
+
+    def __len__(self):
+        return N.lib.lsio_completion_len(self._h)
+
+    def drop(self):
+        if self._h:
+            N.lib.lsio_completion_drop(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.drop()
+        except Exception:
+            pass
+
+
+class IoUringCuda:
+    """Drop-in for `lsio_uring::IoUring` whose chunks land in B200 HBM."""
+
+    def __init__(self, n_worker_threads, devices=(0,), **config):
+        cfg = N.CConfig()
+        N.lib.lsio_uring_cuda_config_default(ctypes.byref(cfg))
+        cfg.n_worker_threads = n_worker_threads
+        devices = list(devices)
+        cfg.n_devices = len(devices)
+        for i, d in enumerate(devices):
+            cfg.devices[i] = d
+        for k, v in config.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown config field {k}")
+            setattr(cfg, k, int(v))
+        self._h = ctypes.c_void_p()
+        rc = N.lib.lsio_uring_cuda_new_with_config(ctypes.byref(cfg), ctypes.byref(self._h))
+        if rc:
+            self._h = None
+            raise N.LsioCudaError(f"IoUringCuda::new failed (rc={rc}): {N.lib.lsio_uring_cuda_last_error().decode(errors='replace')}")
+        self._rx = Receiver(N.lib.lsio_uring_cuda_completion(self._h))
+        self.devices = devices
+
+    @classmethod
+    def new(cls, n_worker_threads, **kw):
+        return cls(n_worker_threads, **kw)
+
+    def get_ranges(self, location, ranges, user_data, group=None):
+        """`ranges`: iterable of (start, end) half-open pairs (Range<isize>); negative = from the end."""
+        if self._h is None:
+            raise RuntimeError("backend dropped")
+        starts = np.array([r[0] for r in ranges], dtype=np.int64)
+        ends = np.array([r[1] for r in ranges], dtype=np.int64)
+        ud = np.array(list(user_data), dtype=np.uint64)
+        loc = os.fsencode(os.fspath(location))
+        if group is None:
+            rc = N.lib.lsio_uring_cuda_get_ranges(self._h, loc, starts.ctypes.data, ends.ctypes.data, len(starts), ud.ctypes.data, len(ud))
+        else:
+            rc = N.lib.lsio_uring_cuda_get_ranges_on(self._h, group, loc, starts.ctypes.data, ends.ctypes.data, len(starts), ud.ctypes.data, len(ud))
+        if rc:
+            # the reference panics on a length mismatch (get_ranges.rs:28); raise instead
+            raise ValueError(f"get_ranges rejected (rc={rc}): ranges/user_data length mismatch, relative path, or backend closed")
+
+    def get_ranges_arrays(self, location, starts, ends, user_data, group=None):
+        """Same, taking int64/int64/uint64 numpy arrays (no per-range Python objects)."""
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        ends = np.ascontiguousarray(ends, dtype=np.int64)
+        ud = np.ascontiguousarray(user_data, dtype=np.uint64)
+        loc = os.fsencode(os.fspath(location))
+        if group is None:
+            rc = N.lib.lsio_uring_cuda_get_ranges(self._h, loc, starts.ctypes.data, ends.ctypes.data, len(starts), ud.ctypes.data, len(ud))
+        else:
+            rc = N.lib.lsio_uring_cuda_get_ranges_on(self._h, group, loc, starts.ctypes.data, ends.ctypes.data, len(starts), ud.ctypes.data, len(ud))
+        if rc:
+            raise ValueError(f"get_ranges rejected (rc={rc})")
+
+    def completion(self):
+        return self._rx
+
+    def stats(self):
+        s = N.CStats()
+        N.lib.lsio_uring_cuda_get_stats(self._h, ctypes.byref(s))
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def drop(self):
+        """Drop: joins the workers; receivers see Disconnected once drained."""
+        if self._h is not None:
+            N.lib.lsio_uring_cuda_free(self._h)
+            self._h = None
+
+    close = drop
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.drop()
+
+    def __del__(self):
+        try:
+            self.drop()
+        except Exception:
+            pass
