@@ -68,6 +68,8 @@ size_t lsio_aligned_bytes_backing_len(const lsio_aligned_bytes* self); /* padded
 /* Copies the view to host memory (cudaMemcpy for DEVICE views). Returns bytes copied or <0. */
 int64_t lsio_aligned_bytes_copy_to_host(const lsio_aligned_bytes* self, void* dst, size_t cap);
 void lsio_aligned_bytes_drop(lsio_aligned_bytes* self);
+/* Drops the `buffer` of n consecutive lsio_output-like records: views[i] may be NULL. */
+void lsio_aligned_bytes_drop_many(lsio_aligned_bytes* const* views, size_t n);
 
 #ifdef __cplusplus
 }

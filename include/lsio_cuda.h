@@ -67,6 +67,10 @@ int lsio_cuda_verify_pattern(int device, const uint64_t* ptrs, const uint64_t* l
                              const uint64_t* file_ids, const uint64_t* file_offs, size_t n,
                              uint64_t* mismatch_dev, void* stream);
 
+/* Test aid: the generator side of verify_pattern -- writes byte(file_id, file_off + i) to
+ * dst_dev[i] for i in [0, len). Used to create the synthetic files and staging images. */
+int lsio_cuda_fill_pattern(int device, void* dst_dev, uint64_t len, uint64_t file_id, uint64_t file_off, void* stream);
+
 /* Number of kernel launches this library has issued in this process (bench `gpu_launches`). */
 uint64_t lsio_cuda_launch_count(void);
 /* Human-readable text for the last CUDA error seen by this library on the calling thread. */

@@ -60,6 +60,10 @@ lsio_completion* lsio_completion_clone(const lsio_completion* self);
 /* timeout_ms < 0 blocks (Receiver::recv), otherwise Receiver::recv_timeout. */
 int lsio_completion_recv(lsio_completion* self, lsio_output* out, int timeout_ms);
 int lsio_completion_try_recv(lsio_completion* self, lsio_output* out);
+/* Receives up to `max` items with one call: blocks (up to timeout_ms, <0 = forever) for the
+ * first one, then takes whatever else is already queued (Receiver::try_iter). *n_out items are
+ * written. Returns LSIO_RECV_OK if *n_out > 0. */
+int lsio_completion_recv_batch(lsio_completion* self, lsio_output* out, size_t max, int timeout_ms, size_t* n_out);
 /* Number of items waiting (Receiver::len). */
 size_t lsio_completion_len(const lsio_completion* self);
 void lsio_completion_drop(lsio_completion* self);

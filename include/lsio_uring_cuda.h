@@ -84,6 +84,14 @@ int lsio_uring_cuda_get_stats(const lsio_uring_cuda* self, lsio_uring_cuda_stats
 /* Text of the last construction error on this thread. */
 const char* lsio_uring_cuda_last_error(void);
 
+/* Measurement aid (stands in for crates/lsio_uring/benches/fio.ini; fio is not installed):
+ * the read ceiling of the storage under `paths` with no GPU work at all -- n_threads threads,
+ * each with a private ring, issue `block_bytes` READ_FIXED reads at queue depth `queue_depth`
+ * into a registered pinned buffer, striding over the files, until every file has been read
+ * once. *gib_per_s receives aggregate GiB/s. */
+int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads,
+                            uint32_t queue_depth, uint32_t o_direct, double* gib_per_s);
+
 /* Drop: finishes in-flight work, joins every thread, disconnects the channel.  Chunks already
  * received stay valid until dropped. */
 void lsio_uring_cuda_free(lsio_uring_cuda* self);

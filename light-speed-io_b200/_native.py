@@ -158,3 +158,25 @@ for _name, _res, _args in [
 ]:
     getattr(lib, _name).restype = _res
     getattr(lib, _name).argtypes = _args
+
+# ---- include/lsio_threadpool.h ---------------------------------------------------------------
+TASK_FN = ctypes.CFUNCTYPE(ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64)
+lib.lsio_threadpool_new.restype = ctypes.c_void_p
+lib.lsio_threadpool_new.argtypes = [ctypes.c_size_t, TASK_FN, ctypes.c_void_p]
+lib.lsio_threadpool_push.restype = None
+lib.lsio_threadpool_push.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+lib.lsio_threadpool_n_parks.restype = ctypes.c_uint64
+lib.lsio_threadpool_n_parks.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+lib.lsio_threadpool_free.restype = None
+lib.lsio_threadpool_free.argtypes = [ctypes.c_void_p]
+
+# ---- bulk / measurement entry points -----------------------------------------------------------
+lib.lsio_cuda_fill_pattern.restype = ctypes.c_int
+lib.lsio_cuda_fill_pattern.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+lib.lsio_completion_recv_batch.restype = ctypes.c_int
+lib.lsio_completion_recv_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(COutput), ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+lib.lsio_aligned_bytes_drop_many.restype = None
+lib.lsio_aligned_bytes_drop_many.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+lib.lsio_probe_read_ceiling.restype = ctypes.c_int
+lib.lsio_probe_read_ceiling.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]

@@ -147,5 +147,8 @@ int64_t lsio_aligned_bytes_copy_to_host(const lsio_aligned_bytes* self, void* ds
     return (int64_t)n;
 }
 void lsio_aligned_bytes_drop(lsio_aligned_bytes* self) { delete self; }
+void lsio_aligned_bytes_drop_many(lsio_aligned_bytes* const* views, size_t n) {
+    for (size_t i = 0; i < n; i++) delete views[i];
+}
 
 }  // extern "C"

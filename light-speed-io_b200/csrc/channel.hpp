@@ -43,6 +43,24 @@ class Channel {
         not_full_.notify_one();
         return RecvStatus::Ok;
     }
+    // First item as recv(); then whatever else is queued, up to max.
+    RecvStatus recv_batch(T* out, size_t max, int timeout_ms, size_t* n_out) {
+        *n_out = 0;
+        if (!max) return RecvStatus::Timeout;
+        std::unique_lock<std::mutex> lk(mu_);
+        auto ready = [&] { return !q_.empty() || senders_ == 0; };
+        if (timeout_ms < 0) not_empty_.wait(lk, ready);
+        else if (!not_empty_.wait_for(lk, std::chrono::milliseconds(timeout_ms), ready)) return RecvStatus::Timeout;
+        if (q_.empty()) return RecvStatus::Disconnected;
+        size_t n = 0;
+        while (n < max && !q_.empty()) {
+            out[n++] = std::move(q_.front());
+            q_.pop_front();
+        }
+        *n_out = n;
+        not_full_.notify_all();
+        return RecvStatus::Ok;
+    }
     size_t len() {
         std::lock_guard<std::mutex> lk(mu_);
         return q_.size();

@@ -137,10 +137,41 @@ __global__ void __launch_bounds__(256) verify_kernel(const Piece* __restrict__ p
     }
 }
 
+__global__ void __launch_bounds__(256) fill_kernel(uint8_t* __restrict__ dst, uint64_t len, uint64_t file_id, uint64_t file_off) {
+    // one 8-byte file word per thread-iteration
+    const uint64_t w0 = file_off >> 3, w1 = (file_off + len + 7) >> 3;
+    for (uint64_t w = w0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = pattern_word(file_id, w);
+        const int64_t rel = (int64_t)(w << 3) - (int64_t)file_off;
+        if (rel >= 0 && (uint64_t)rel + 8 <= len && (((uint64_t)dst + (uint64_t)rel) & 7) == 0) {
+            *(uint64_t*)(dst + rel) = v;
+        } else {
+            for (int b = 0; b < 8; b++) {
+                const int64_t r = rel + b;
+                if (r >= 0 && (uint64_t)r < len) dst[r] = (uint8_t)(v >> (8 * b));
+            }
+        }
+    }
+}
+
 }  // namespace
 }  // namespace lsio
 
 extern "C" {
+
+int lsio_cuda_fill_pattern(int device, void* dst_dev, uint64_t len, uint64_t file_id, uint64_t file_off, void* stream) {
+    using namespace lsio;
+    if (!dst_dev && len) return -EINVAL;
+    if (!len) return 0;
+    DeviceGuard dg(device);
+    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+    const uint64_t words = (len + 15) / 8;
+    const unsigned grid = (unsigned)std::min<uint64_t>((words + 255) / 256, 148 * 16);
+    fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint8_t*)dst_dev, len, file_id, file_off);
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    LSIO_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 
 int lsio_cuda_xxh64(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n, uint64_t* out_dev, void* stream) {
     using namespace lsio;

@@ -108,5 +108,22 @@ def verify_pattern(buf, offs, lens, file_ids, file_offs, stream=None):
     return int(out.item())
 
 
+def fill_pattern(buf, file_id, file_off=0, stream=None):
+    """Fill a uint8 CUDA tensor with the synthetic content byte(file_id, file_off + i)."""
+    N.check(N.lib.lsio_cuda_fill_pattern(buf.device.index, ctypes.c_void_p(buf.data_ptr()), buf.numel(), int(file_id), int(file_off),
+                                         _stream_ptr(stream)), "fill_pattern")
+
+
+def probe_read_ceiling(paths, block_bytes=1 << 20, n_threads=8, queue_depth=32, o_direct=True):
+    """GiB/s of raw READ_FIXED reads over `paths` with no GPU work (stand-in for benches/fio.ini)."""
+    import os
+
+    arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    out = ctypes.c_double(0)
+    N.check(N.lib.lsio_probe_read_ceiling(arr, len(paths), block_bytes, n_threads, queue_depth, int(o_direct), ctypes.byref(out)),
+            "probe_read_ceiling")
+    return out.value
+
+
 def launch_count():
     return int(N.lib.lsio_cuda_launch_count())

@@ -18,6 +18,9 @@ from . import _native as N
 from .aligned_bytes import AlignedBytes
 
 
+OUTPUT_DTYPE = np.dtype(N.COutput)
+
+
 class RecvTimeoutError(Exception):
     """crossbeam_channel::RecvTimeoutError::Timeout"""
 
@@ -96,6 +99,30 @@ class Receiver:
 
     def try_recv(self):
         return self._recv(0)
+
+    def recv_batch(self, max_items=1024, timeout=10.0, _buf={}):
+        """Up to `max_items` completions with one call, as a numpy record array over the C
+        `lsio_output` layout (fields: status, opcode, kind, checksums, device, crc32c, xxh64,
+        chunk.buffer, chunk.user_data, context).  The caller owns every non-NULL chunk.buffer:
+        release them with `drop_buffers(records)`.  Blocks for the first item like recv_timeout."""
+        arr = (N.COutput * max_items)()
+        n = ctypes.c_size_t(0)
+        rc = N.lib.lsio_completion_recv_batch(self._h, arr, max_items, -1 if timeout is None else max(0, int(timeout * 1000)), ctypes.byref(n))
+        if rc == N.RECV_TIMEOUT:
+            raise RecvTimeoutError()
+        if rc == N.RECV_DISCONNECTED:
+            raise Disconnected()
+        if rc != N.RECV_OK:
+            raise RuntimeError(f"lsio_completion_recv_batch: {rc}")
+        rec = np.frombuffer(arr, dtype=OUTPUT_DTYPE, count=n.value)
+        rec.flags.writeable = False
+        return rec
+
+    @staticmethod
+    def drop_buffers(records):
+        """Drop the chunk buffers of a record array from recv_batch (lsio_aligned_bytes_drop each)."""
+        ptrs = np.ascontiguousarray(records["chunk"]["buffer"], dtype=np.uint64)
+        N.lib.lsio_aligned_bytes_drop_many(ptrs.ctypes.data, len(ptrs))
 
     def __len__(self):
         return N.lib.lsio_completion_len(self._h)
