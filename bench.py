@@ -431,6 +431,7 @@ def main():
     ap.add_argument("--disk-files", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--value-only", action="store_true", help="only the device-resident kernel pass (for ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -470,6 +471,13 @@ def main():
     except (OSError, ValueError):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    if args.value_only:
+        val = run_value(args, dev, args.files, expect_crc)
+        kernel_ms = statistics.mean(val["step_ms"])
+        print(json.dumps({"value_only": True, "files": args.files, "kernel_ms": kernel_ms, "achieved_gbs": val["algo_bytes"] / kernel_ms / 1e6,
+                          "frac": val["algo_bytes"] / kernel_ms / 1e6 / hbm_peak, "crc_ok": val["crc_ok"], "mismatched_bytes": val["mismatched_bytes"]}), flush=True)
+        return 0
 
     with ClockSampler(local) as clocks:
         val = run_value(args, dev, args.files, expect_crc)

@@ -129,7 +129,7 @@ class AlignedBytes:
     def __cuda_array_interface__(self):
         if self.memory_kind != "device":
             raise AttributeError("not a device view")
-        return {"shape": (self.len(),), "typestr": "|u1", "data": (self.as_ptr(), True), "version": 3, "strides": None}
+        return {"shape": (self.len(),), "typestr": "|u1", "data": (self.as_ptr(), False), "version": 3, "strides": None}
 
     def to_torch(self):
         """Zero-copy uint8 torch tensor over a device view (keeps this view alive)."""

@@ -289,7 +289,10 @@ struct Worker {
     WorkerThread<Op>& wt;
     Ring ring;
     Tracker<Op> tracker;
-    std::deque<Op> stalled;
+    // Ops that could not start: reads waiting for staging space (strictly FIFO; nothing new is
+    // pulled while one waits) and plans waiting for HBM (must NOT hold back reads: it is the
+    // completion and consumption of earlier reads that frees the arena).
+    std::deque<Op> stalled_reads, stalled_plans;
     Worker(Group& grp, WorkerThread<Op>& w) : g(grp), wt(w), tracker(grp.be->cfg.sq_entries) {}
 
     // An SQE slot, flushing the SQ first if a burst of completions filled it.
@@ -402,7 +405,7 @@ struct Worker {
             Op done = tracker.remove(ud.index_of_op);
             if (r.have_fd && r.have_statx) {
                 done.kind = Op::Plan;
-                if (plan_request(g, done.req, wt) == Start::Retry) stalled.push_back(std::move(done));
+                if (plan_request(g, done.req, wt) == Start::Retry) stalled_plans.push_back(std::move(done));
             } else if (r.have_fd) {
                 close(r.fd);  // the reference leaks this fd (Appendix A)
                 r.fd = -1;
@@ -468,28 +471,33 @@ struct Worker {
             if (!running && tracker.is_empty()) break;
             unsigned started = 0;
             if (running) {
-                // top up the SQ (worker.rs:65-88), two SQEs of headroom (MAX_SQ_ENTRIES_PER_ITERATION)
-                while (true) {
-                    if (ring_ok && (tracker.is_full() || ring.sq_len() + 2 > sq || ring.sq_len() + ring.cq_len() + 2 > sq)) break;
-                    Op op;
-                    if (!stalled.empty()) {
-                        op = std::move(stalled.front());
-                        stalled.pop_front();
-                    } else if (auto t = wt.find_task()) {
-                        op = std::move(*t);
-                    } else {
-                        break;
-                    }
+                auto room = [&] { return !ring_ok || !(tracker.is_full() || ring.sq_len() + 2 > sq || ring.sq_len() + ring.cq_len() + 2 > sq); };
+                // 1. reads that waited for staging space, in order
+                while (!stalled_reads.empty() && room()) {
+                    const Start s = start(stalled_reads.front());
+                    if (s == Start::Retry) break;
+                    stalled_reads.pop_front();
+                    if (s == Start::Started) started++;
+                }
+                // 2. plans that waited for HBM, each once
+                for (size_t n = stalled_plans.size(); n-- > 0;) {
+                    Op op = std::move(stalled_plans.front());
+                    stalled_plans.pop_front();
+                    if (start(op) == Start::Retry) stalled_plans.push_back(std::move(op));
+                    else started++;
+                }
+                // 3. top up the SQ with new tasks (worker.rs:65-88), two SQEs of headroom (MAX_SQ_ENTRIES_PER_ITERATION)
+                while (stalled_reads.empty() && room()) {
+                    auto t = wt.find_task();
+                    if (!t) break;
+                    Op op = std::move(*t);
                     if (!ring_ok) {
                         send_error(be, rc, 0, *op.req, -1, "io_uring unavailable");
                         continue;
                     }
                     const Start s = start(op);
-                    if (s == Start::Retry) {
-                        stalled.push_front(std::move(op));
-                        break;
-                    }
-                    if (s == Start::Started) started++;
+                    if (s == Start::Retry) (op.kind == Op::Read ? stalled_reads : stalled_plans).push_back(std::move(op));
+                    else if (s == Start::Started) started++;
                 }
             }
             if (ring_ok && ring.unsubmitted()) ring.submit();  // one enter per batch (reference: per op, worker.rs:79)
@@ -501,7 +509,7 @@ struct Worker {
             }
             if (ring_ok && ring.unsubmitted()) ring.submit();
             if (got || started) continue;
-            if (tracker.is_empty() && stalled.empty()) {
+            if (tracker.is_empty() && stalled_reads.empty() && stalled_plans.empty()) {
                 if (running) wt.park();  // worker.rs:93-99
                 continue;
             }
@@ -811,6 +819,11 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
 int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {
     if (!cfgp || !out) return -EINVAL;
     lsio_uring_cuda_config cfg = *cfgp;
+    // small rings: keep a read (and a coalesced copy) to a quarter of the ring so the log keeps moving
+    if (cfg.staging_bytes >= (4ull << 20)) {
+        cfg.max_read_bytes = std::min<uint64_t>(cfg.max_read_bytes, cfg.staging_bytes / 4 / kAlign * kAlign);
+        cfg.min_copy_bytes = std::min<uint64_t>(cfg.min_copy_bytes, cfg.staging_bytes / 4);
+    }
     if (cfg.n_worker_threads == 0 || cfg.n_devices == 0 || cfg.n_devices > LSIO_MAX_DEVICES || cfg.sq_entries < 4 ||
         (cfg.sq_entries & (cfg.sq_entries - 1)) || cfg.staging_bytes < (4ull << 20) || cfg.arena_bytes < (1ull << 20) || cfg.max_read_bytes < kAlign ||
         cfg.max_read_bytes > (1ull << 31) - kAlign || cfg.max_read_bytes > cfg.staging_bytes / 4) {

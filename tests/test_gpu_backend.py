@@ -1,0 +1,242 @@
+"""GPU parity tests of the drop-in backend through the C ABI (-m gpu): IoUringCuda vs the
+oracle (pread ground truth + CRC), restating crates/lsio_uring/tests/integration_test.rs and
+covering what the reference leaves untested."""
+import os
+import random
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+KIB, MIB = 1024, 1024 * 1024
+
+
+def _drain(rx, n, timeout=20.0):
+    return [rx.recv_timeout(timeout) for _ in range(n)]
+
+
+def _check_chunks(oracle, items, fn_of, ranges_of):
+    for c in items:
+        assert c.is_ok(), c
+        fn, (s, e) = fn_of(c.user_data), ranges_of(c.user_data)
+        want = oracle.pread_range(fn, s, e)
+        got = c.buffer.as_slice()
+        assert np.array_equal(got, want), (c.user_data, s, e, len(got), len(want))
+        assert c.crc32c == oracle.crc32c(want), (c.user_data, s, e)
+        assert c.buffer.memory_kind == "device" and c.device == 0
+
+
+@pytest.mark.parametrize("o_direct", [1, 0])
+def test_get_ranges(lsio, oracle, cuda_dev, data_dir, o_direct):
+    """integration_test.rs::test_get_ranges against the CUDA backend."""
+    N_WORKER_THREADS, FILE_SIZE, CHUNK_SIZE = 4, MIB, 4 * KIB
+    N_CHUNKS = FILE_SIZE // CHUNK_SIZE
+    period = int(CHUNK_SIZE * 1.5)
+    unit = bytes(random.randrange(32, 127) for _ in range(period))
+    file_contents = (unit * (FILE_SIZE // period + 1))[:FILE_SIZE]
+    filename = os.path.join(data_dir, f"lsio_uring_tempfile_{random.getrandbits(32)}")
+    with open(filename, "wb") as f:
+        f.write(file_contents)
+        f.flush()
+        os.fsync(f.fileno())
+    uring = lsio.IoUringCuda(N_WORKER_THREADS, o_direct=o_direct, arena_bytes=256 << 20, staging_bytes=32 << 20)
+    uring.get_ranges(filename, [(i * CHUNK_SIZE, (i + 1) * CHUNK_SIZE) for i in range(N_CHUNKS)], range(N_CHUNKS))
+    vec = [None] * N_CHUNKS
+    for i in range(N_CHUNKS):
+        c = uring.completion().recv_timeout(0.5 * 10)
+        assert c.is_ok(), f"Error reading chunk {i}! {c}"
+        vec[c.user_data] = c.buffer
+    completion = uring.completion().clone()
+    uring.drop()
+    with pytest.raises(lsio.Disconnected):
+        completion.recv()  # integration_test.rs:92-96
+    completion.drop()
+    assembled = b"".join(b.as_slice().tobytes() for b in vec)  # chunks outlive the backend
+    assert assembled == file_contents
+
+
+def test_unaligned_negative_eof_and_split_ranges(lsio, oracle, cuda_dev, data_dir):
+    size = MIB + 1000  # unaligned EOF
+    fn = os.path.join(data_dir, "f")
+    oracle.write_file(fn, 7, size)
+    rng = np.random.default_rng(3)
+    ranges = [(0, -1), (-100, -1), (size - 5, size), (0, 1), (511, 513), (-size, 1), (5, MIB), (513, MIB + 999), (size - 1, size),
+              (-1, -1), (1024, 2048), (MIB, -1)]
+    for _ in range(300):
+        n = int(rng.integers(1, 65536))
+        s = int(rng.integers(0, size - n))
+        ranges.append((s, s + n))
+    # max_read_bytes = 128 KiB: long ranges are read as several segments whose CRCs are combined
+    with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, max_read_bytes=128 << 10) as u:
+        u.get_ranges(fn, ranges, range(len(ranges)))
+        items = _drain(u.completion(), len(ranges))
+        assert sorted(c.user_data for c in items) == list(range(len(ranges)))  # exactly one chunk per range
+        _check_chunks(oracle, items, lambda ud: fn, lambda ud: ranges[ud])
+        st = u.stats()
+        assert st["reads"] > len(ranges) and st["errors"] == 0
+
+
+@pytest.mark.parametrize("pack_align", [1, 16, 512])
+def test_many_files_many_ops_per_thread(lsio, oracle, cuda_dev, data_dir, pack_align):
+    """Multiple files in flight, > 64 ops per worker, back-pressure on a tiny completion channel."""
+    n_files, size = 24, 300_000 + 77
+    fns = []
+    for i in range(n_files):
+        fn = os.path.join(data_dir, f"f{i}")
+        oracle.write_file(fn, 100 + i, size)
+        fns.append(fn)
+    rng = np.random.default_rng(4)
+    per_file = 40
+    all_ranges = {}
+    with lsio.IoUringCuda(2, arena_bytes=512 << 20, staging_bytes=16 << 20, completion_bound=8, pack_align=pack_align, sq_entries=16) as u:
+        for i, fn in enumerate(fns):
+            rs = []
+            for k in range(per_file):
+                n = int(rng.integers(1, 30000))
+                s = int(rng.integers(0, size - n))
+                rs.append((s, s + n))
+                all_ranges[(i << 32) | k] = rs[-1]
+            u.get_ranges(fn, rs, [(i << 32) | k for k in range(per_file)])
+        time.sleep(0.3)  # let the 8-slot channel fill: producers must block, not drop
+        assert len(u.completion()) <= 8
+        items = _drain(u.completion(), n_files * per_file)
+        assert len({c.user_data for c in items}) == n_files * per_file
+        _check_chunks(oracle, items, lambda ud: fns[ud >> 32], lambda ud: all_ranges[ud])
+        if pack_align > 1:
+            assert all(c.buffer.as_ptr() % pack_align == 0 for c in items)
+
+
+def test_errors_are_in_band(lsio, oracle, cuda_dev, data_dir):
+    fn = os.path.join(data_dir, "f")
+    size = 10_000
+    oracle.write_file(fn, 1, size)
+    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20) as u:
+        rx = u.completion()
+        # missing file: openat and statx both fail => two Err items, no chunk (as the reference)
+        u.get_ranges("/definitely/missing/lsio", [(0, 10), (10, 20)], [1, 2])
+        errs = _drain(rx, 2)
+        assert sorted((e.status, e.opcode) for e in errs) == [(-2, 18), (-2, 21)]
+        assert all("/definitely/missing/lsio" in e.context for e in errs)
+        # bad ranges become Err items (the reference asserts/panics: sqe.rs:71,81,88), good ones still arrive
+        u.get_ranges(fn, [(0, size + 1), (10, 10), (-size - 5, 10), (4096, 8192), (0, -size - 2)], [10, 11, 12, 13, 14])
+        items = _drain(rx, 5)
+        ok = [c for c in items if c.is_ok()]
+        bad = [c for c in items if not c.is_ok()]
+        assert [c.user_data for c in ok] == [13]
+        assert sorted(e.user_data for e in bad) == [10, 11, 12, 14] and all(e.status == -22 for e in bad)
+        _check_chunks(oracle, ok, lambda ud: fn, lambda ud: (4096, 8192))
+        with pytest.raises(lsio.RecvTimeoutError):
+            rx.recv_timeout(0.2)
+        # argument errors (the reference panics on a length mismatch, get_ranges.rs:28)
+        with pytest.raises(ValueError):
+            u.get_ranges(fn, [(0, 1), (1, 2)], [1])
+        with pytest.raises(ValueError):
+            u.get_ranges("relative/path", [(0, 1)], [1])
+        # a request larger than the arena is an error, not a hang
+        u.get_ranges(fn, [(0, -1)], [99])
+        assert _drain(rx, 1)[0].is_ok()
+
+
+def test_request_larger_than_arena_and_arena_recycling(lsio, oracle, cuda_dev, data_dir):
+    fn = os.path.join(data_dir, "big")
+    size = 6 * MIB
+    oracle.write_file(fn, 2, size)
+    with lsio.IoUringCuda(2, arena_bytes=4 << 20, staging_bytes=16 << 20) as u:
+        rx = u.completion()
+        u.get_ranges(fn, [(0, -1)], [1])
+        e = rx.recv_timeout(10)
+        assert not e.is_ok() and e.status == -12  # ENOMEM
+        # 3 MiB requests against a 4 MiB arena: each waits for the previous chunks to be dropped
+        for k in range(4):
+            u.get_ranges(fn, [(k * MIB, k * MIB + 3 * MIB // 2), (k * MIB + 3 * MIB // 2, k * MIB + 3 * MIB)], [2 * k, 2 * k + 1])
+        seen = 0
+        while seen < 8:
+            c = rx.recv_timeout(10)
+            assert c.is_ok()
+            k, half = divmod(c.user_data, 2)
+            s = k * MIB + half * (3 * MIB // 2)
+            assert np.array_equal(c.buffer.as_slice(), oracle.pattern(2, s, 3 * MIB // 2))
+            c.buffer.drop()
+            seen += 1
+        assert u.stats()["arena_stalls"] > 0
+
+
+def test_reference_bench_pattern_and_bulk_receive(lsio, oracle, cuda_dev, data_dir):
+    """lsio_bench's own data (`i as u8`, main.rs:102) and chunking (filesize / blocksize blocks),
+    received with the bulk API; every CRC is the Appendix C value for that block."""
+    fsize, bs = 1_000_000, 262_144
+    n_chunks = fsize // bs
+    fns = []
+    for i in range(6):
+        fn = os.path.join(data_dir, f"lsio_bench_{i}")
+        oracle.write_file(fn, i, fsize, ref_pattern=True)
+        fns.append(fn)
+    st = np.arange(n_chunks, dtype=np.int64) * bs
+    with lsio.IoUringCuda(4, arena_bytes=128 << 20, staging_bytes=16 << 20) as u:
+        for i, fn in enumerate(fns):
+            u.get_ranges_arrays(fn, st, st + bs, (np.uint64(i) << np.uint64(32)) | np.arange(n_chunks, dtype=np.uint64))
+        got = 0
+        while got < len(fns) * n_chunks:
+            rec = u.completion().recv_batch(64, 10.0)
+            assert (rec["status"] == 0).all()
+            assert (rec["crc32c"] == 0x1CA1B1D2).all()  # crc32c of one 256 KiB `i as u8` block
+            lsio.Receiver.drop_buffers(rec)
+            got += len(rec)
+
+
+def test_two_device_groups_on_one_gpu(lsio, oracle, cuda_dev, data_dir):
+    """Sharding plumbing: two worker groups (here both on GPU 0), files routed round-robin and explicitly."""
+    fns = []
+    for i in range(6):
+        fn = os.path.join(data_dir, f"f{i}")
+        oracle.write_file(fn, 50 + i, 200_000)
+        fns.append(fn)
+    with lsio.IoUringCuda(2, devices=(0, 0), arena_bytes=64 << 20, staging_bytes=16 << 20) as u:
+        for i, fn in enumerate(fns):
+            u.get_ranges(fn, [(1, 100_001), (100_001, -1)], [2 * i, 2 * i + 1], group=None if i % 2 else i % 2)
+        items = _drain(u.completion(), 12)
+        _check_chunks(oracle, items, lambda ud: fns[ud // 2], lambda ud: (1, 100_001) if ud % 2 == 0 else (100_001, -1))
+
+
+def test_zarr_like_config3_sample(lsio, oracle, cuda_dev, data_dir):
+    """BASELINE config 3 at a size the oracle finishes in seconds: 200 files x 1,049,576 B,
+    8 ranges per file of 4-64 KiB at arbitrary offsets, plus EOF-anchored and negative ranges."""
+    n_files, size = 200, 1_049_576
+    fns = []
+    for i in range(n_files):
+        fn = os.path.join(data_dir, f"z{i}")
+        oracle.write_file(fn, 1000 + i, size)
+        fns.append(fn)
+    ranges = {}
+    with lsio.IoUringCuda(4, arena_bytes=512 << 20, staging_bytes=64 << 20) as u:
+        for i, fn in enumerate(fns):
+            rng = np.random.default_rng(0xC3 + i)
+            rs = []
+            for k in range(8):
+                n = int(rng.integers(4096, 65537))
+                s = int(rng.integers(0, size - n + 1))
+                rs.append((s, s + n))
+            if i % 100 == 0:
+                rs.append((size - 5000, size))
+                rs.append((-5000, -1))
+            for k, r in enumerate(rs):
+                ranges[(i << 32) | k] = r
+            u.get_ranges(fn, rs, [(i << 32) | k for k in range(len(rs))])
+        items = _drain(u.completion(), len(ranges), 30.0)
+        _check_chunks(oracle, items, lambda ud: fns[ud >> 32], lambda ud: ranges[ud])
+        # the bytes are also provable on the device without a D2H copy
+        ptrs = np.array([c.buffer.as_ptr() for c in items], dtype=np.uint64)
+        lens = np.array([c.buffer.len() for c in items], dtype=np.uint64)
+        ids = np.array([1000 + (c.user_data >> 32) for c in items], dtype=np.uint64)
+        offs = np.array([oracle.resolve_range(size, *ranges[c.user_data])[1].start_off for c in items], dtype=np.uint64)
+        import torch
+
+        anchor = torch.empty(1, dtype=torch.uint8, device=cuda_dev)
+        assert lsio.cuda_ops.verify_pattern(anchor, ptrs - np.uint64(anchor.data_ptr()), lens, ids, offs) == 0
+
+
+def test_smoke_entry(cuda_dev):
+    import __graft_entry__ as g
+
+    g.smoke()
