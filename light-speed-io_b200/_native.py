@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblsio_b200.so")
+LIB_PATH = os.environ.get("LSIO_B200_LIB") or os.path.join(_HERE, "liblsio_b200.so")  # env override: kernel A/B builds
 
 
 class NativeLibraryMissing(ImportError):
