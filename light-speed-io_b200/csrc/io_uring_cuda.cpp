@@ -113,6 +113,21 @@ struct Batch {
     std::vector<uint64_t> seg_seq;  // staging entry of each descriptor
 };
 
+// Second stage when LSIO_CHECKSUM_XXH64 is requested: ranges whose bytes are packed wait here for
+// one xxh64_chunks launch (arrays are mapped pinned memory: no copies in either direction).
+struct XxhBatch {
+    static constexpr size_t kMax = 8192;
+    uint64_t* ptrs = nullptr;  // [kMax] ptrs | [kMax] lens | [kMax] out, mapped pinned
+    uint64_t* dev = nullptr;   // device alias of ptrs
+    cudaEvent_t done = nullptr;
+    struct Item {
+        std::shared_ptr<Request> req;
+        uint32_t range;
+        uint32_t crc;
+    };
+    std::vector<Item> items;
+};
+
 struct Stats {
     std::atomic<uint64_t> requests{0}, ranges{0}, reads{0}, short_reads{0}, read_bytes{0}, h2d_copies{0}, h2d_bytes{0}, pack_launches{0},
         kernel_launches{0}, payload_bytes{0}, chunks_ok{0}, errors{0}, staging_stalls{0}, arena_stalls{0};
@@ -131,6 +146,9 @@ struct Group {
     cudaStream_t s_copy = nullptr, s_pack = nullptr;
     std::vector<Batch> batches;
     std::deque<Batch*> free_batches, inflight;
+    std::vector<XxhBatch> xxh_batches;
+    std::deque<XxhBatch*> xxh_free, xxh_inflight;
+    std::vector<XxhBatch::Item> xxh_pending;
     std::unique_ptr<ThreadPool<Op>> pool;
     std::thread device_thread;
     std::atomic<bool> stop_device{false};
@@ -520,15 +538,19 @@ struct Worker {
 };
 
 // ---- device thread -----------------------------------------------------------------------------
-static void emit_range(Group& g, Request& r, uint32_t range_idx) {
-    Backend* be = g.be;
-    RangePlan& p = r.ranges[range_idx];
-    if (p.failed.load(std::memory_order_relaxed)) return;  // its errors were already sent; no Chunk (get_range.rs:63)
+static uint32_t range_crc(const Request& r, const RangePlan& p) {
     uint32_t crc = 0;
     for (uint32_t s = 0; s < p.nsegs; s++) {
         const SegPlan& sp = r.segs[p.first_seg + s];
         crc = s == 0 ? sp.crc : gf2::crc32c_combine(crc, sp.crc, sp.payload_len);
     }
+    return crc;
+}
+
+static void send_chunk(Group& g, const std::shared_ptr<Request>& rp, uint32_t range_idx, uint32_t crc, bool have_xxh, uint64_t xxh) {
+    Backend* be = g.be;
+    Request& r = *rp;
+    RangePlan& p = r.ranges[range_idx];
     lsio_output o;
     memset(&o, 0, sizeof o);
     o.status = 0;
@@ -537,6 +559,10 @@ static void emit_range(Group& g, Request& r, uint32_t range_idx) {
     if (be->cfg.checksum & LSIO_CHECKSUM_CRC32C) {
         o.checksums |= LSIO_CHECKSUM_CRC32C;
         o.crc32c = crc;
+    }
+    if (have_xxh) {
+        o.checksums |= LSIO_CHECKSUM_XXH64;
+        o.xxh64 = xxh;
     }
     auto* view = new lsio_aligned_bytes();
     view->buf = r.buffer;
@@ -548,6 +574,36 @@ static void emit_range(Group& g, Request& r, uint32_t range_idx) {
     send_output(be, o);
 }
 
+// All segments of a range are packed: emit its chunk, or queue it for the XXH64 stage.
+static void emit_range(Group& g, const std::shared_ptr<Request>& rp, uint32_t range_idx) {
+    RangePlan& p = rp->ranges[range_idx];
+    if (p.failed.load(std::memory_order_relaxed)) return;  // its errors were already sent; no Chunk (get_range.rs:63)
+    const uint32_t crc = (g.be->cfg.checksum & LSIO_CHECKSUM_CRC32C) ? range_crc(*rp, p) : 0;
+    if (g.be->cfg.checksum & LSIO_CHECKSUM_XXH64) g.xxh_pending.push_back(XxhBatch::Item{rp, range_idx, crc});
+    else send_chunk(g, rp, range_idx, crc, false, 0);
+}
+
+static int flush_xxh(Group& g) {
+    while (!g.xxh_pending.empty() && !g.xxh_free.empty()) {
+        XxhBatch* xb = g.xxh_free.front();
+        g.xxh_free.pop_front();
+        const size_t n = std::min(g.xxh_pending.size(), XxhBatch::kMax);
+        xb->items.assign(std::make_move_iterator(g.xxh_pending.begin()), std::make_move_iterator(g.xxh_pending.begin() + n));
+        g.xxh_pending.erase(g.xxh_pending.begin(), g.xxh_pending.begin() + n);
+        for (size_t i = 0; i < n; i++) {
+            const RangePlan& p = xb->items[i].req->ranges[xb->items[i].range];
+            xb->ptrs[i] = (uint64_t)(uintptr_t)(xb->items[i].req->buffer->buf + p.dst_off);
+            xb->ptrs[XxhBatch::kMax + i] = p.len;
+        }
+        int rc = xxh64_launch_async(xb->dev, xb->dev + XxhBatch::kMax, n, xb->dev + 2 * XxhBatch::kMax, g.s_pack);
+        if (rc) return rc;
+        g.be->stats.kernel_launches++;
+        LSIO_CUDA_TRY(cudaEventRecord(xb->done, g.s_pack));
+        g.xxh_inflight.push_back(xb);
+    }
+    return 0;
+}
+
 static void retire_batch(Group& g, Batch& b) {
     for (uint32_t i = 0; i < b.counts.nsegs; i++) {
         StageEntry& e = g.log.at(b.seg_seq[i]);
@@ -555,7 +611,7 @@ static void retire_batch(Group& g, Batch& b) {
         SegPlan& sp = r.segs[e.seg];
         sp.crc = b.crc_host[i];
         RangePlan& p = r.ranges[sp.range];
-        if (p.segs_left.fetch_sub(1, std::memory_order_acq_rel) == 1) emit_range(g, r, sp.range);
+        if (p.segs_left.fetch_sub(1, std::memory_order_acq_rel) == 1) emit_range(g, e.req, sp.range);
     }
     // failed reads carry no descriptor but still count towards their range
     for (uint64_t s = b.seq_begin; s < b.seq_end; s++) {
@@ -648,6 +704,24 @@ static void device_main(Group& g) {
             g.free_batches.push_back(b);
             progressed = true;
         }
+        // 1b. XXH64 stage: finished launches emit their chunks; packed ranges waiting for one are launched
+        while (!g.xxh_inflight.empty()) {
+            XxhBatch* xb = g.xxh_inflight.front();
+            cudaError_t q = cudaEventQuery(xb->done);
+            if (q == cudaErrorNotReady) break;
+            g.xxh_inflight.pop_front();
+            for (size_t i = 0; i < xb->items.size(); i++) {
+                if (q == cudaSuccess) send_chunk(g, xb->items[i].req, xb->items[i].range, xb->items[i].crc, true, xb->ptrs[2 * XxhBatch::kMax + i]);
+                else send_error(be, (int)q, 0, *xb->items[i].req, (int)xb->items[i].range, "CUDA error in the xxh64 stage");
+            }
+            xb->items.clear();
+            g.xxh_free.push_back(xb);
+            progressed = true;
+        }
+        if (!g.xxh_pending.empty() && !g.xxh_free.empty()) {
+            if (flush_xxh(g)) fprintf(stderr, "lsio_b200: xxh64 launch failed: %s\n", last_error_text().c_str());
+            progressed = true;
+        }
         // 2. extend the copy frontier over landed reads
         const uint64_t avail = g.log.alloc_seq();
         if (g.copy_seq < avail && !g.free_batches.empty()) {
@@ -693,10 +767,10 @@ static void device_main(Group& g) {
             continue;
         }
         if (g.stop_device.load(std::memory_order_acquire) && g.workers_alive.load(std::memory_order_acquire) == 0 && g.inflight.empty() &&
-            g.copy_seq == g.log.alloc_seq())
+            g.xxh_inflight.empty() && g.xxh_pending.empty() && g.copy_seq == g.log.alloc_seq())
             break;
         // 3. wait: spin briefly while work is in flight, sleep when idle
-        if (g.log.empty() && g.inflight.empty()) std::this_thread::sleep_for(std::chrono::microseconds(100));
+        if (g.log.empty() && g.inflight.empty() && g.xxh_inflight.empty()) std::this_thread::sleep_for(std::chrono::microseconds(100));
         else if (++idle_spins > 200) std::this_thread::sleep_for(std::chrono::microseconds(20));
         else
             for (int i = 0; i < 50; i++) __builtin_ia32_pause();
@@ -739,6 +813,11 @@ static void free_group_cuda(Group& g) {
         if (b.done) cudaEventDestroy(b.done);
     }
     g.batches.clear();
+    for (XxhBatch& x : g.xxh_batches) {
+        if (x.ptrs) cudaFreeHost(x.ptrs);
+        if (x.done) cudaEventDestroy(x.done);
+    }
+    g.xxh_batches.clear();
     if (g.s_copy) cudaStreamDestroy(g.s_copy);
     if (g.s_pack) cudaStreamDestroy(g.s_pack);
     if (g.host_ring) cudaFreeHost(g.host_ring);
@@ -779,6 +858,15 @@ static int init_group(Group& g) {
         LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
         b.seg_seq.reserve(max_segs);
         g.free_batches.push_back(&b);
+    }
+    if (cfg.checksum & LSIO_CHECKSUM_XXH64) {
+        g.xxh_batches.resize(4);
+        for (XxhBatch& x : g.xxh_batches) {
+            LSIO_CUDA_TRY(cudaHostAlloc((void**)&x.ptrs, 3 * XxhBatch::kMax * sizeof(uint64_t), cudaHostAllocPortable | cudaHostAllocMapped));
+            LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&x.dev, x.ptrs, 0));
+            LSIO_CUDA_TRY(cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
+            g.xxh_free.push_back(&x);
+        }
     }
     return 0;
 }

@@ -157,6 +157,17 @@ __global__ void __launch_bounds__(256) fill_kernel(uint8_t* __restrict__ dst, ui
 }  // namespace
 }  // namespace lsio
 
+namespace lsio {
+// Asynchronous launch for the pipeline: ptrs/lens/out are device-accessible (mapped pinned) arrays.
+int xxh64_launch_async(const uint64_t* ptrs_dev, const uint64_t* lens_dev, size_t n, uint64_t* out_dev, cudaStream_t st) {
+    if (!n) return 0;
+    xxh64_kernel<<<(unsigned)((4 * (uint64_t)n + 255) / 256), 256, 0, st>>>(ptrs_dev, lens_dev, n, out_dev);
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    LSIO_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+}  // namespace lsio
+
 extern "C" {
 
 int lsio_cuda_fill_pattern(int device, void* dst_dev, uint64_t len, uint64_t file_id, uint64_t file_off, void* stream) {

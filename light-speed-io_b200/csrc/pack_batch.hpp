@@ -38,4 +38,7 @@ int pack_prepare_device(int device);
 int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, const PackBatchCounts& c, uint32_t flags,
                       uint32_t* crc_out, cudaStream_t stream, unsigned* launches);
 
+// misc_kernels.cu: XXH64 of n spans, arrays device-accessible, asynchronous on `stream`.
+int xxh64_launch_async(const uint64_t* ptrs_dev, const uint64_t* lens_dev, size_t n, uint64_t* out_dev, cudaStream_t stream);
+
 }  // namespace lsio

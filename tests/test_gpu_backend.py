@@ -240,3 +240,29 @@ def test_smoke_entry(cuda_dev):
     import __graft_entry__ as g
 
     g.smoke()
+
+
+@pytest.mark.parametrize("checksum", [0, 2, 3])
+def test_checksum_selection_including_xxh64(lsio, oracle, cuda_dev, data_dir, checksum):
+    """checksum bits: 1 = CRC-32C fused into the pack kernel, 2 = XXH64 second stage (xxh64_chunks)."""
+    size = 700_001
+    fn = os.path.join(data_dir, "x")
+    oracle.write_file(fn, 21, size)
+    rng = np.random.default_rng(8)
+    ranges = [(0, -1), (3, 35), (1, 2), (size - 31, size)]
+    for _ in range(120):
+        n = int(rng.integers(1, 200_000))
+        s = int(rng.integers(0, size - n))
+        ranges.append((s, s + n))
+    with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, checksum=checksum, max_read_bytes=64 << 10) as u:
+        u.get_ranges(fn, ranges, range(len(ranges)))
+        items = _drain(u.completion(), len(ranges))
+        for c in items:
+            assert c.is_ok(), c
+            want = oracle.pread_range(fn, *ranges[c.user_data])
+            assert np.array_equal(c.buffer.as_slice(), want)
+            assert (c.crc32c is not None) == bool(checksum & 1) and (c.xxh64 is not None) == bool(checksum & 2)
+            if checksum & 1:
+                assert c.crc32c == oracle.crc32c(want)
+            if checksum & 2:
+                assert c.xxh64 == oracle.xxh64(want), ranges[c.user_data]
