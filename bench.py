@@ -331,6 +331,168 @@ def verify_full_landing(dev, paths, file_ids, workers, staging_mib):
     return int(mism), int(lens.sum())
 
 
+# ---- the other BASELINE.json configs (parity-test cases with numbers; not the headline line) ---------------
+def make_pattern_files(directory, prefix, n_files, size, device_index, id_base):
+    """n_files files of `size` bytes, content byte(id_base + i, off); generated on the GPU."""
+    import torch
+
+    from lsio_b200 import cuda_ops
+
+    os.makedirs(directory, exist_ok=True)
+    paths = [os.path.join(directory, f"{prefix}_{i}") for i in range(n_files)]
+    if all(os.path.exists(p) and os.path.getsize(p) == size for p in paths):
+        return paths
+    dev = torch.device(f"cuda:{device_index}")
+    group = max(1, min(n_files, (1 << 30) // size))
+    dbuf = torch.empty(group * size, dtype=torch.uint8, device=dev)
+    hbuf = torch.empty(group * size, dtype=torch.uint8, pin_memory=True)
+    for g0 in range(0, n_files, group):
+        g1 = min(n_files, g0 + group)
+        for i in range(g0, g1):
+            cuda_ops.fill_pattern(dbuf[(i - g0) * size:(i - g0 + 1) * size], id_base + i, 0)
+        hbuf[: (g1 - g0) * size].copy_(dbuf[: (g1 - g0) * size])
+        torch.cuda.synchronize(dev)
+        harr = hbuf.numpy()
+
+        def write(ids):
+            for i in ids:
+                with open(paths[i], "wb") as f:
+                    f.write(memoryview(harr[(i - g0) * size:(i - g0 + 1) * size]))
+
+        ids = list(range(g0, g1))
+        ths = [threading.Thread(target=write, args=(ids[k::16],)) for k in range(16)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    return paths
+
+
+def config_workload(name, directory, device_index, args):
+    """Returns (paths, file_ids, ranges_per_file [(starts, ends)], sizes, description)."""
+    from numpy.random import MT19937, Generator
+
+    if name == "C3":  # Zarr-like random reads (SURVEY 8d)
+        n_files, size = args.c3_files, 1_049_576
+        paths = make_pattern_files(directory, "c3", n_files, size, device_index, 100_000)
+        per = []
+        for i in range(n_files):
+            rng = Generator(MT19937(0xC3 + i))
+            ln = rng.integers(4096, 65537, size=8)
+            st = (rng.random(8) * (size - ln + 1)).astype(np.int64)
+            s, e = st, st + ln
+            if i % 100 == 0:  # one range ending exactly at EOF and one written as negative -len..-1
+                s = np.concatenate([s, [size - 5000, -7000]])
+                e = np.concatenate([e, [size, -1]])
+            per.append((s.astype(np.int64), e.astype(np.int64)))
+        return paths, [100_000 + i for i in range(n_files)], per, size, f"C3: {n_files} files x {size} B, 8 ranges/file of 4-64 KiB at arbitrary offsets (+EOF/negative ranges)"
+    if name == "C4":  # 1 MiB ranges over the C1 file set
+        paths, _ = make_files(directory, args.files, device_index)
+        k = FILE_SIZE // (1 << 20)
+        st = np.arange(k, dtype=np.int64) << 20
+        return paths, list(range(args.files)), [(st, st + (1 << 20))] * args.files, FILE_SIZE, f"C4: {args.files} files x {FILE_SIZE} B, {k} ranges of 1 MiB per file"
+    if name == "C5":  # large streaming scan, 4 MiB ranges
+        n_files, size = args.c5_files, 1 << 30
+        paths = make_pattern_files(directory, "c5", n_files, size, device_index, 200_000)
+        st = np.arange(size >> 22, dtype=np.int64) << 22
+        return paths, [200_000 + i for i in range(n_files)], [(st, st + (1 << 22))] * n_files, size, f"C5: {n_files} files x 1 GiB, 256 ranges of 4 MiB per file, {args.c5_loops} loops"
+    raise ValueError(name)
+
+
+def resolve(size, s, e):
+    so = np.where(s >= 0, s, size + s)
+    eo = np.where(e >= 0, e, size + e + 1)
+    return so, eo
+
+
+def run_config(args, dev, rank):
+    """One BASELINE config end to end through the C ABI: an untimed verification pass (every landed
+    byte checked on the device against the pattern, fused CRCs cross-checked by the crc-only kernel
+    over the landed chunks), then timed passes."""
+    import torch
+
+    import lsio_b200 as L
+    from lsio_b200 import cuda_ops
+    from lsio_b200.io_uring_cuda import Receiver
+
+    directory, source = pick_data_dir(args, 0)
+    directory = directory + "_" + args.config.lower()
+    paths, ids, per, size, desc = config_workload(args.config, directory, dev.index, args)
+    n_ranges = sum(len(p[0]) for p in per)
+    lens_by_file = []
+    for (s, e) in per:
+        so, eo = resolve(size, s, e)
+        lens_by_file.append((so, eo - so))
+    payload = int(sum(int(l.sum()) for _, l in lens_by_file))
+    base = np.cumsum([0] + [len(p[0]) for p in per])  # user_data = global range index
+    starts_all = np.concatenate([so for so, _ in lens_by_file]).astype(np.uint64)
+    lens_all = np.concatenate([l for _, l in lens_by_file]).astype(np.uint64)
+    fid_all = np.concatenate([np.full(len(p[0]), fid, dtype=np.uint64) for p, fid in zip(per, ids)])
+    keep_resident = payload < (60 << 30)
+    arena = (payload + (4 << 30)) if keep_resident else (8 << 30)
+
+    def one_pass(u, keep):
+        rx = u.completion()
+        t0 = time.perf_counter()
+        for i, p in enumerate(paths):
+            s, e = per[i]
+            u.get_ranges_arrays(p, s, e, np.arange(base[i], base[i + 1], dtype=np.uint64))
+        got, recs = 0, []
+        while got < n_ranges:
+            rec = rx.recv_batch(8192, 120.0)
+            got += len(rec)
+            if keep:
+                recs.append(rec.copy())
+            else:
+                assert (rec["status"] == 0).all()
+                Receiver.drop_buffers(rec)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, (np.concatenate(recs) if keep else None)
+
+    result = {"config": desc, "source": source, "ranges": n_ranges, "payload_bytes": payload}
+    with L.IoUringCuda(args.workers, devices=(dev.index,), arena_bytes=arena, staging_bytes=args.staging_mib << 20,
+                       min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries) as u:
+        if keep_resident:  # verification pass
+            _, rec = one_pass(u, True)
+            assert (rec["status"] == 0).all(), rec[rec["status"] != 0][:3]
+            ud = rec["chunk"]["user_data"].astype(np.int64)
+            views = [L.AlignedBytes(int(h)) for h in rec["chunk"]["buffer"]]
+            ptrs = np.array([v.as_ptr() for v in views], dtype=np.uint64)
+            vlen = np.array([v.len() for v in views], dtype=np.uint64)
+            assert np.array_equal(vlen, lens_all[ud]), "chunk lengths differ from end_off - start_off"
+            anchor = torch.empty(1, dtype=torch.uint8, device=dev)
+            rel = ptrs - np.uint64(anchor.data_ptr())
+            mism = cuda_ops.verify_pattern(anchor, rel, vlen, fid_all[ud], starts_all[ud])
+            crc2 = cuda_ops.pack_strip_crc32c(anchor, None, rel, rel, vlen, store=False).cpu().numpy().view(np.uint32)
+            result["verify"] = {"mismatched_bytes": int(mism), "crc_fused_equals_crc_of_landed_bytes": bool(np.array_equal(crc2, rec["crc32c"])),
+                                "chunks": len(views)}
+            for v in views:
+                v.drop()
+        secs = []
+        loops = args.c5_loops if args.config == "C5" else 1
+        for _ in range(max(1, args.warmup - 2)):
+            one_pass(u, False)
+        for _ in range(args.steps):
+            t = 0.0
+            for _ in range(loops):
+                t += one_pass(u, False)[0]
+            secs.append(t)
+        st = u.stats()
+    result["gib_s"] = payload * loops * len(secs) / sum(secs) / GIB
+    result["secs_per_step"] = secs
+    result["bytes_per_step"] = payload * loops
+    result["pipeline"] = {k: st[k] for k in ("reads", "read_bytes", "short_reads", "h2d_copies", "h2d_bytes", "pack_launches", "staging_stalls", "arena_stalls")}
+    result["read_amplification"] = st["read_bytes"] / max(1, st["payload_bytes"])
+    if rank == 0:
+        result["source_read_ceiling_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 2000)], min(1 << 20, size // 512 * 512), max(8, args.workers), 32, True)
+        if not args.no_cpu_baseline:  # the CPU port on the same files (the oracle's only use here)
+            from oracle import oracle
+
+            dt, okb, errs = oracle.bench_read_ranges(paths, per, 8, sqpoll=True)
+            result["cpu_baseline"] = {"value": okb / dt / GIB, "unit": "GiB/s", "kind": "port", "cores": 16, "errors": errs,
+                                      "sample": "one pass over the whole config, 8 workers + SQPOLL, C driver (oracle/lsio_uring_ref.c)"}
+        print(json.dumps(result), flush=True)
+    return 0
+
+
 def pcie_h2d_ceiling(dev):
     import torch
 
@@ -432,6 +594,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--value-only", action="store_true", help="only the device-resident kernel pass (for ncu captures)")
+    ap.add_argument("--e2e-only", action="store_true", help="only the end-to-end pass (pipeline tuning sweeps)")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"], help="C2 is the contract line; the others print an informational line")
+    ap.add_argument("--c3-files", type=int, default=10_000)
+    ap.add_argument("--c5-files", type=int, default=40)
+    ap.add_argument("--c5-loops", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -449,6 +616,9 @@ def main():
     dev = torch.device(f"cuda:{local}")
     dist_init("nccl")
     n_gpus = max(world, 1)
+
+    if args.config != "C2":
+        return run_config(args, dev, rank)
 
     need = args.files * FILE_SIZE
     directory, source = pick_data_dir(args, need)
@@ -479,6 +649,13 @@ def main():
                           "frac": val["algo_bytes"] / kernel_ms / 1e6 / hbm_peak, "crc_ok": val["crc_ok"], "mismatched_bytes": val["mismatched_bytes"]}), flush=True)
         return 0
 
+    if args.e2e_only:
+        e2e = run_e2e(args, dev, my_paths, my_ids, expect_crc, args.steps, args.warmup, args.workers)
+        print(json.dumps({"e2e_only": True, "gib_s": e2e["bytes"] / sum(e2e["secs"]) / GIB, "bad": e2e["bad"], "workers": args.workers,
+                          "staging_mib": args.staging_mib, "min_copy_mib": args.min_copy_mib, "sq_entries": args.sq_entries,
+                          "stalls": [e2e["stats"]["staging_stalls"], e2e["stats"]["arena_stalls"]], "copies": e2e["stats"]["h2d_copies"]}), flush=True)
+        return 0
+
     with ClockSampler(local) as clocks:
         val = run_value(args, dev, args.files, expect_crc)
         e2e = run_e2e(args, dev, my_paths, my_ids, expect_crc, args.steps, args.warmup, args.workers)
@@ -488,7 +665,7 @@ def main():
     ceil = {}
     if rank == 0:
         ceil["pcie_h2d_gib_s"] = pcie_h2d_ceiling(dev)
-        ceil["source_read_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 1 << 20, max(8, args.workers), 32, True)
+        ceil["source_read_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 1 << 20, min(os.cpu_count() or 8, max(8, args.workers) * n_gpus), 32, True)
     full = None
     if not args.no_verify:
         mism, landed = verify_full_landing(dev, my_paths, my_ids, args.workers, args.staging_mib)

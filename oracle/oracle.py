@@ -85,6 +85,11 @@ L.lsio_ref_bench_read_files.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.
                                         ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
 
 
+L.lsio_ref_bench_read_ranges.restype = ctypes.c_double
+L.lsio_ref_bench_read_ranges.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+
+
 def _buf(b):
     if isinstance(b, np.ndarray):
         return b.ctypes.data, b.nbytes
@@ -264,4 +269,16 @@ def bench_read_files(paths, starts, ends, n_worker_threads, sqpoll=True, mode=0)
     b, e = ctypes.c_uint64(), ctypes.c_uint64()
     secs = L.lsio_ref_bench_read_files(arr, len(paths), st.ctypes.data, en.ctypes.data, len(st), n_worker_threads, int(sqpoll), mode,
                                        ctypes.byref(b), ctypes.byref(e))
+    return secs, b.value, e.value
+
+
+def bench_read_ranges(paths, per_file_ranges, n_worker_threads, sqpoll=True, mode=0):
+    """As bench_read_files for arbitrary per-file (starts, ends) arrays. Returns (seconds, bytes, errors)."""
+    arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    st = np.ascontiguousarray(np.concatenate([r[0] for r in per_file_ranges]), dtype=np.int64)
+    en = np.ascontiguousarray(np.concatenate([r[1] for r in per_file_ranges]), dtype=np.int64)
+    cnt = np.array([len(r[0]) for r in per_file_ranges], dtype=np.uint64)
+    b, e = ctypes.c_uint64(), ctypes.c_uint64()
+    secs = L.lsio_ref_bench_read_ranges(arr, len(paths), st.ctypes.data, en.ctypes.data, cnt.ctypes.data, n_worker_threads, int(sqpoll), mode,
+                                        ctypes.byref(b), ctypes.byref(e))
     return secs, b.value, e.value
