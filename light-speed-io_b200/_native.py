@@ -136,7 +136,7 @@ class CConfig(ctypes.Structure):
                 ("checksum", ctypes.c_uint32), ("pack_align", ctypes.c_uint32), ("pin_threads", ctypes.c_uint32),
                 ("o_direct", ctypes.c_uint32), ("staging_bytes", ctypes.c_uint64), ("arena_bytes", ctypes.c_uint64),
                 ("max_read_bytes", ctypes.c_uint64), ("min_copy_bytes", ctypes.c_uint64), ("flush_us", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32)]
+                ("merge_ranges", ctypes.c_uint32), ("merge_gap_bytes", ctypes.c_uint64)]
 
 
 class CStats(ctypes.Structure):

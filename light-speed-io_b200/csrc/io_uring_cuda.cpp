@@ -52,20 +52,26 @@ constexpr uint64_t kAlign = 512;  // crates/lsio_uring/src/sqe.rs:12
 
 struct Group;
 
-// One read = one segment of one range.
+// One read serves one or more segments; a segment is the part of one range that one read carries.
+// (The reference issues exactly one read per range; merging adjacent ranges into one read is its
+// stated plan: lsio_aligned_bytes/README.md:43-57, README.md:78.)
+struct ReadPlan {
+    uint64_t file_off = 0;   // 512-aligned
+    uint32_t read_len = 0;   // multiple of 512
+    uint32_t needed = 0;     // bytes that must land: the furthest payload byte of any of its segments
+    uint32_t first_seg = 0, nsegs = 0;  // its segments are consecutive in Request::segs
+};
 struct SegPlan {
     uint32_t range = 0;
-    uint64_t file_off = 0;     // 512-aligned
-    uint32_t read_len = 0;     // multiple of 512
-    uint32_t head = 0;         // padding bytes before the payload in the slot
-    uint64_t payload_len = 0;  // bytes of the range this read carries
+    uint32_t head = 0;         // offset of the payload inside the read's slot (padding / other ranges before it)
+    uint64_t payload_len = 0;  // bytes of the range this segment carries
     uint64_t dst_off = 0;      // where they go in the request buffer
     uint32_t crc = 0;
 };
 struct RangePlan {
     int64_t start_off = 0, end_off = 0;
     uint64_t dst_off = 0, len = 0;
-    uint32_t first_seg = 0, nsegs = 0;
+    std::vector<uint32_t> seg_ids;  // this range's segments in file order (for the CRC combine)
     uint64_t user_data = 0;
     bool valid = false;
     std::atomic<uint32_t> segs_left{0};
@@ -85,6 +91,7 @@ struct Request {
     uint64_t total_bytes = 0;
     std::shared_ptr<InnerBuffer> buffer;  // the request's HBM buffer
     std::unique_ptr<RangePlan[]> ranges;
+    std::vector<ReadPlan> reads;
     std::vector<SegPlan> segs;
     std::atomic<uint32_t> reads_left{0};  // Arc<OpenFile> strong count, get_range.rs:78
     ~Request() {
@@ -96,7 +103,7 @@ struct Request {
 struct Op {
     enum Kind : uint8_t { GetRanges, Plan, Read, Close } kind = GetRanges;
     std::shared_ptr<Request> req;
-    uint32_t seg = 0;
+    uint32_t read = 0;  // index into req->reads
     StageEntry* entry = nullptr;
     uint32_t done = 0;  // bytes of this read that have landed (short-read continuation)
 };
@@ -110,7 +117,11 @@ struct Batch {
     uint32_t* crc_dev = nullptr;   // device alias of crc_host
     cudaEvent_t copied = nullptr, done = nullptr;
     uint64_t seq_begin = 0, seq_end = 0;
-    std::vector<uint64_t> seg_seq;  // staging entry of each descriptor
+    struct DescRef {
+        uint64_t seq;  // staging entry (holds the request alive until the batch retires)
+        uint32_t seg;
+    };
+    std::vector<DescRef> desc;  // segment of each descriptor
 };
 
 // Second stage when LSIO_CHECKSUM_XXH64 is requested: ranges whose bytes are packed wait here for
@@ -266,36 +277,56 @@ static Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerTh
     buf->release = [arena = g.arena, block](InnerBuffer&) { arena->release(block); };
     r.buffer = std::move(buf);
 
-    // split every range into reads of at most max_read_bytes (reference: one read per range,
-    // panics above 2 GiB, get_range.rs:23-30)
+    // Read plan: sort the ranges' padded spans, merge spans that touch / overlap / sit within
+    // merge_gap_bytes of each other into runs, cut every run into reads of at most max_read_bytes
+    // (reference: one read per range, panics above 2 GiB, get_range.rs:23-30).
     const uint64_t max_read = std::max<uint64_t>(kAlign, cfg.max_read_bytes / kAlign * kAlign);
-    for (size_t i = 0; i < n; i++) {
-        RangePlan& p = r.ranges[i];
-        if (!p.valid) continue;
-        const uint64_t aligned_start = (uint64_t)p.start_off / kAlign * kAlign;                  // sqe.rs:83
-        const uint64_t aligned_end = ((uint64_t)p.end_off + kAlign - 1) / kAlign * kAlign;      // padded length
-        p.first_seg = (uint32_t)r.segs.size();
-        for (uint64_t fo = aligned_start; fo < aligned_end; fo += max_read) {
-            SegPlan sp;
-            sp.range = (uint32_t)i;
-            sp.file_off = fo;
-            sp.read_len = (uint32_t)std::min<uint64_t>(max_read, aligned_end - fo);
-            const uint64_t lo = std::max<uint64_t>(fo, (uint64_t)p.start_off), hi = std::min<uint64_t>(fo + sp.read_len, (uint64_t)p.end_off);
-            sp.head = (uint32_t)(lo - fo);  // sqe.rs:116: view starts at start_off - aligned_start
-            sp.payload_len = hi - lo;
-            sp.dst_off = p.dst_off + (lo - (uint64_t)p.start_off);
-            r.segs.push_back(sp);
+    std::vector<uint32_t> order;
+    for (size_t i = 0; i < n; i++)
+        if (r.ranges[i].valid) order.push_back((uint32_t)i);
+    auto span_lo = [&](uint32_t i) { return (uint64_t)r.ranges[i].start_off / kAlign * kAlign; };                   // sqe.rs:83
+    auto span_hi = [&](uint32_t i) { return ((uint64_t)r.ranges[i].end_off + kAlign - 1) / kAlign * kAlign; };     // padded length
+    if (cfg.merge_ranges) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return span_lo(a) < span_lo(b); });
+    for (size_t k = 0; k < order.size();) {
+        uint64_t run_lo = span_lo(order[k]), run_hi = span_hi(order[k]);
+        size_t k_end = k + 1;
+        if (cfg.merge_ranges)
+            while (k_end < order.size() && k_end - k < 1024 && span_lo(order[k_end]) <= run_hi + cfg.merge_gap_bytes) {  // <= 1024 segments per read: a read must fit one batch
+                run_hi = std::max(run_hi, span_hi(order[k_end]));
+                k_end++;
+            }
+        for (uint64_t fo = run_lo; fo < run_hi; fo += max_read) {
+            ReadPlan rd;
+            rd.file_off = fo;
+            rd.read_len = (uint32_t)std::min<uint64_t>(max_read, run_hi - fo);
+            rd.first_seg = (uint32_t)r.segs.size();
+            for (size_t j = k; j < k_end; j++) {
+                RangePlan& p = r.ranges[order[j]];
+                const uint64_t lo = std::max<uint64_t>(fo, (uint64_t)p.start_off), hi = std::min<uint64_t>(fo + rd.read_len, (uint64_t)p.end_off);
+                if (lo >= hi) continue;
+                SegPlan sp;
+                sp.range = order[j];
+                sp.head = (uint32_t)(lo - fo);  // sqe.rs:116: the view starts at start_off - aligned_start
+                sp.payload_len = hi - lo;
+                sp.dst_off = p.dst_off + (lo - (uint64_t)p.start_off);
+                p.seg_ids.push_back((uint32_t)r.segs.size());
+                rd.needed = std::max<uint32_t>(rd.needed, (uint32_t)(hi - fo));
+                r.segs.push_back(sp);
+            }
+            rd.nsegs = (uint32_t)r.segs.size() - rd.first_seg;
+            if (rd.nsegs) r.reads.push_back(rd);  // a read that carries no payload (pure gap) is skipped
         }
-        p.nsegs = (uint32_t)r.segs.size() - p.first_seg;
-        p.segs_left.store(p.nsegs, std::memory_order_relaxed);
+        k = k_end;
     }
-    r.reads_left.store((uint32_t)r.segs.size(), std::memory_order_release);
+    for (size_t i = 0; i < n; i++)
+        if (r.ranges[i].valid) r.ranges[i].segs_left.store((uint32_t)r.ranges[i].seg_ids.size(), std::memory_order_relaxed);
+    r.reads_left.store((uint32_t)r.reads.size(), std::memory_order_release);
     // get_ranges.rs:39-45: one read op per segment onto THIS worker's deque; peers steal them.
-    for (uint32_t s = 0; s < r.segs.size(); s++) {
+    for (uint32_t s = 0; s < r.reads.size(); s++) {
         Op op;
         op.kind = Op::Read;
         op.req = rp;
-        op.seg = s;
+        op.read = s;
         wt.push(std::move(op));
     }
     return Start::Finished;
@@ -324,7 +355,7 @@ struct Worker {
     }
 
     void push_read_sqe(size_t idx, Op& op) {
-        const SegPlan& sp = op.req->segs[op.seg];
+        const ReadPlan& sp = op.req->reads[op.read];
         const uint64_t phys = op.entry->log_off % g.log.capacity() + op.done;
         io_uring_sqe* e = must_get_sqe();
         e->opcode = IORING_OP_READ_FIXED;  // north star: READ_FIXED into the registered ring (reference: Read, sqe.rs:95)
@@ -363,8 +394,8 @@ struct Worker {
         case Op::Plan:
             return plan_request(g, op.req, wt);
         case Op::Read: {  // get_range.rs:43-51 + sqe.rs:59-122
-            const SegPlan& sp = op.req->segs[op.seg];
-            StageEntry* ent = g.log.alloc(sp.read_len, op.req, op.seg);
+            const ReadPlan& sp = op.req->reads[op.read];
+            StageEntry* ent = g.log.alloc(sp.read_len, op.req, op.read);
             if (!ent) {
                 be->stats.staging_stalls++;
                 return Start::Retry;
@@ -431,24 +462,28 @@ struct Worker {
             return;
         }
         case Op::Read: {  // get_range.rs:53-91
-            const SegPlan& sp = r.segs[op->seg];
-            RangePlan& rp = r.ranges[sp.range];
-            if (cqe.res < 0) {
-                send_error(be, cqe.res, IORING_OP_READ_FIXED, r, (int)sp.range, "read failed");
-                rp.failed.store(true, std::memory_order_relaxed);
+            const ReadPlan& rd = r.reads[op->read];
+            auto fail = [&](int status, const char* what) {
+                // one Err per range that this CQE was carrying (reference: one Err per failed CQE = per range)
+                uint32_t last = UINT32_MAX;
+                for (uint32_t k = 0; k < rd.nsegs; k++) {
+                    const uint32_t range = r.segs[rd.first_seg + k].range;
+                    if (range == last) continue;
+                    last = range;
+                    if (!r.ranges[range].failed.exchange(true, std::memory_order_relaxed)) send_error(be, status, IORING_OP_READ_FIXED, r, (int)range, what);
+                }
                 op->entry->state.store(kStageFailed, std::memory_order_release);
                 finish_read_accounting(ud.index_of_op, *op);
+            };
+            if (cqe.res < 0) {
+                fail(cqe.res, "read failed");
                 return;
             }
             op->done += (uint32_t)cqe.res;
             be->stats.read_bytes += (uint64_t)cqe.res;
-            const uint64_t needed = sp.head + sp.payload_len;
-            if (op->done < needed) {  // the reference does not check (get_range.rs:66-68, issue #100)
+            if (op->done < rd.needed) {  // the reference does not check (get_range.rs:66-68, issue #100)
                 if (cqe.res == 0 || (op->done % kAlign) != 0) {
-                    send_error(be, -EIO, IORING_OP_READ_FIXED, r, (int)sp.range, "short read (unexpected end of file)");
-                    rp.failed.store(true, std::memory_order_relaxed);
-                    op->entry->state.store(kStageFailed, std::memory_order_release);
-                    finish_read_accounting(ud.index_of_op, *op);
+                    fail(-EIO, "short read (unexpected end of file)");
                     return;
                 }
                 be->stats.short_reads++;
@@ -540,8 +575,8 @@ struct Worker {
 // ---- device thread -----------------------------------------------------------------------------
 static uint32_t range_crc(const Request& r, const RangePlan& p) {
     uint32_t crc = 0;
-    for (uint32_t s = 0; s < p.nsegs; s++) {
-        const SegPlan& sp = r.segs[p.first_seg + s];
+    for (size_t s = 0; s < p.seg_ids.size(); s++) {
+        const SegPlan& sp = r.segs[p.seg_ids[s]];
         crc = s == 0 ? sp.crc : gf2::crc32c_combine(crc, sp.crc, sp.payload_len);
     }
     return crc;
@@ -605,21 +640,19 @@ static int flush_xxh(Group& g) {
 }
 
 static void retire_batch(Group& g, Batch& b) {
-    for (uint32_t i = 0; i < b.counts.nsegs; i++) {
-        StageEntry& e = g.log.at(b.seg_seq[i]);
-        Request& r = *e.req;
-        SegPlan& sp = r.segs[e.seg];
-        sp.crc = b.crc_host[i];
-        RangePlan& p = r.ranges[sp.range];
-        if (p.segs_left.fetch_sub(1, std::memory_order_acq_rel) == 1) emit_range(g, e.req, sp.range);
-    }
-    // failed reads carry no descriptor but still count towards their range
+    // failed reads carry no descriptor but their segments still count towards their ranges
     for (uint64_t s = b.seq_begin; s < b.seq_end; s++) {
         StageEntry& e = g.log.at(s);
-        if (e.state.load(std::memory_order_relaxed) == kStageFailed) {
-            RangePlan& p = e.req->ranges[e.req->segs[e.seg].range];
-            p.segs_left.fetch_sub(1, std::memory_order_acq_rel);
-        }
+        if (e.state.load(std::memory_order_relaxed) != kStageFailed) continue;
+        const ReadPlan& rd = e.req->reads[e.seg];
+        for (uint32_t k = 0; k < rd.nsegs; k++) e.req->ranges[e.req->segs[rd.first_seg + k].range].segs_left.fetch_sub(1, std::memory_order_acq_rel);
+    }
+    for (uint32_t i = 0; i < b.counts.nsegs; i++) {
+        const std::shared_ptr<Request>& rp = g.log.at(b.desc[i].seq).req;
+        SegPlan& sp = rp->segs[b.desc[i].seg];
+        sp.crc = b.crc_host[i];
+        RangePlan& p = rp->ranges[sp.range];
+        if (p.segs_left.fetch_sub(1, std::memory_order_acq_rel) == 1) emit_range(g, rp, sp.range);
     }
     g.log.retire_through(b.seq_end);
 }
@@ -629,7 +662,7 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
     Batch* b = g.free_batches.front();
     g.free_batches.pop_front();
     b->counts = PackBatchCounts();
-    b->seg_seq.clear();
+    b->desc.clear();
     b->seq_begin = seq_begin;
     b->seq_end = seq_end;
     const uint64_t cap = g.log.capacity();
@@ -642,13 +675,16 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
     for (uint64_t s = seq_begin; s < seq_end; s++) {
         StageEntry& e = g.log.at(s);
         if (e.state.load(std::memory_order_acquire) != kStageLanded) continue;
-        const SegPlan& sp = e.req->segs[e.seg];
-        lsio_cuda_segment seg;
-        seg.src = (uint64_t)(uintptr_t)(g.dev_ring + e.log_off % cap + sp.head);
-        seg.dst = (uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off);
-        seg.len = sp.payload_len;
-        pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store);  // sized by the caller's limits
-        b->seg_seq.push_back(s);
+        const ReadPlan& rd = e.req->reads[e.seg];
+        for (uint32_t k = 0; k < rd.nsegs; k++) {
+            const SegPlan& sp = e.req->segs[rd.first_seg + k];
+            lsio_cuda_segment seg;
+            seg.src = (uint64_t)(uintptr_t)(g.dev_ring + e.log_off % cap + sp.head);
+            seg.dst = (uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off);
+            seg.len = sp.payload_len;
+            pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store);  // sized by the caller's limits
+            b->desc.push_back(Batch::DescRef{s, rd.first_seg + k});
+        }
         landed_bytes += e.len;
     }
     if (landed_bytes) {
@@ -694,9 +730,9 @@ static void device_main(Group& g) {
                 cuda_fail(q, "pack batch", __FILE__, __LINE__);
                 fprintf(stderr, "lsio_b200: %s\n", last_error_text().c_str());
                 for (uint32_t i = 0; i < b->counts.nsegs; i++) {
-                    StageEntry& e = g.log.at(b->seg_seq[i]);
-                    RangePlan& p = e.req->ranges[e.req->segs[e.seg].range];
-                    if (!p.failed.exchange(true)) send_error(be, (int)q, 0, *e.req, (int)e.req->segs[e.seg].range, "CUDA error in the H2D/pack stage");
+                    Request& rq = *g.log.at(b->desc[i].seq).req;
+                    const uint32_t range = rq.segs[b->desc[i].seg].range;
+                    if (!rq.ranges[range].failed.exchange(true)) send_error(be, (int)q, 0, rq, (int)range, "CUDA error in the H2D/pack stage");
                 }
             }
             g.inflight.pop_front();
@@ -738,16 +774,21 @@ static void device_main(Group& g) {
                     break;
                 }
                 size_t t = 0;
+                size_t ns = 0;
                 if (st == kStageLanded) {
-                    const SegPlan& sp = e.req->segs[e.seg];
-                    t = pack_tile_count((uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off), sp.payload_len);
+                    const ReadPlan& rd = e.req->reads[e.seg];
+                    for (uint32_t k = 0; k < rd.nsegs; k++) {
+                        const SegPlan& sp = e.req->segs[rd.first_seg + k];
+                        t += pack_tile_count((uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off), sp.payload_len);
+                    }
+                    ns = rd.nsegs;
                     if (!oldest) oldest = e.landed_ns;
                 }
-                if (nsegs + 1 > max_segs || ntiles + t > max_tiles || (bytes && bytes + e.len > max_batch_bytes)) {
+                if (nsegs + ns > max_segs || ntiles + t > max_tiles || (bytes && bytes + e.len > max_batch_bytes)) {
                     hit_limit = true;
                     break;
                 }
-                nsegs++;
+                nsegs += ns;
                 ntiles += t;
                 bytes = e.log_off + e.len - g.log.at(g.copy_seq).log_off;
             }
@@ -856,7 +897,7 @@ static int init_group(Group& g) {
         LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&b.crc_dev, b.crc_host, 0));
         LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
         LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
-        b.seg_seq.reserve(max_segs);
+        b.desc.reserve(max_segs);
         g.free_batches.push_back(&b);
     }
     if (cfg.checksum & LSIO_CHECKSUM_XXH64) {
@@ -902,6 +943,8 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->max_read_bytes = 8ull << 20;
     cfg->min_copy_bytes = 8ull << 20;
     cfg->flush_us = 200;
+    cfg->merge_ranges = 1;
+    cfg->merge_gap_bytes = 0;
 }
 
 int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {
@@ -914,7 +957,7 @@ int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uri
     }
     if (cfg.n_worker_threads == 0 || cfg.n_devices == 0 || cfg.n_devices > LSIO_MAX_DEVICES || cfg.sq_entries < 4 ||
         (cfg.sq_entries & (cfg.sq_entries - 1)) || cfg.staging_bytes < (4ull << 20) || cfg.arena_bytes < (1ull << 20) || cfg.max_read_bytes < kAlign ||
-        cfg.max_read_bytes > (1ull << 31) - kAlign || cfg.max_read_bytes > cfg.staging_bytes / 4) {
+        cfg.max_read_bytes > (1ull << 30) || cfg.max_read_bytes > cfg.staging_bytes / 4) {
         set_error("invalid lsio_uring_cuda_config");
         return -EINVAL;
     }

@@ -68,13 +68,16 @@ def test_unaligned_negative_eof_and_split_ranges(lsio, oracle, cuda_dev, data_di
         s = int(rng.integers(0, size - n))
         ranges.append((s, s + n))
     # max_read_bytes = 128 KiB: long ranges are read as several segments whose CRCs are combined
-    with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, max_read_bytes=128 << 10) as u:
-        u.get_ranges(fn, ranges, range(len(ranges)))
-        items = _drain(u.completion(), len(ranges))
-        assert sorted(c.user_data for c in items) == list(range(len(ranges)))  # exactly one chunk per range
-        _check_chunks(oracle, items, lambda ud: fn, lambda ud: ranges[ud])
-        st = u.stats()
-        assert st["reads"] > len(ranges) and st["errors"] == 0
+    for merge in (0, 1):
+        with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, max_read_bytes=128 << 10, merge_ranges=merge) as u:
+            u.get_ranges(fn, ranges, range(len(ranges)))
+            items = _drain(u.completion(), len(ranges))
+            assert sorted(c.user_data for c in items) == list(range(len(ranges)))  # exactly one chunk per range
+            _check_chunks(oracle, items, lambda ud: fn, lambda ud: ranges[ud])
+            st = u.stats()
+            assert st["errors"] == 0
+            if not merge:
+                assert st["reads"] > len(ranges)  # one read per range, long ones split (reference: one read per range)
 
 
 @pytest.mark.parametrize("pack_align", [1, 16, 512])
@@ -306,3 +309,30 @@ def test_drop_with_work_in_flight_and_concurrent_submitters(lsio, oracle, cuda_d
                 seen += 1
         assert seen <= 16
         rx.drop()
+
+
+@pytest.mark.parametrize("merge,gap", [(1, 0), (0, 0), (1, 4096)])
+def test_read_planner_merges_adjacent_overlapping_and_duplicate_ranges(lsio, oracle, cuda_dev, data_dir, merge, gap):
+    """SURVEY 8f rank 1 (planned in the reference: lsio_aligned_bytes/README.md:43-57): ranges whose
+    padded spans touch or overlap share one read; every range still gets exactly one chunk with its own
+    bytes and CRC, whatever the merge setting."""
+    size = 3 * MIB + 333
+    fn = os.path.join(data_dir, "m")
+    oracle.write_file(fn, 31, size)
+    bs = 4096
+    ranges = [(i * bs, (i + 1) * bs) for i in range(256)]            # 256 adjacent blocks: one 1 MiB run
+    ranges += [(MIB + 10, MIB + 5000), (MIB + 4000, MIB + 9000), (MIB + 10, MIB + 5000)]  # overlapping + duplicate
+    ranges += [(2 * MIB + 100, 2 * MIB + 200), (2 * MIB + 3000, 2 * MIB + 3100)]          # 2.8 KiB apart: merged only with a gap
+    ranges += [(5, 2 * MIB + 777)]                                     # one long range over everything before it
+    ranges = [ranges[i] for i in np.random.default_rng(5).permutation(len(ranges))]  # submission order must not matter
+    with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, merge_ranges=merge, merge_gap_bytes=gap, max_read_bytes=512 << 10) as u:
+        u.get_ranges(fn, ranges, range(len(ranges)))
+        items = _drain(u.completion(), len(ranges))
+        assert sorted(c.user_data for c in items) == list(range(len(ranges)))
+        _check_chunks(oracle, items, lambda ud: fn, lambda ud: ranges[ud])
+        st = u.stats()
+        if merge:
+            assert st["reads"] < 40, st      # everything lies in one run up to 2 MiB+..., cut into 512 KiB reads
+            assert st["read_bytes"] < 2.5 * size
+        else:
+            assert st["reads"] >= len(ranges)
