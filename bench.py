@@ -242,28 +242,11 @@ def run_value(args, dev, n_files, expect_crc):
 
 # ---- the end-to-end pass through the C ABI (`e2e`) ----------------------------------------------------
 def e2e_pass(u, paths, file_ids, expect_crc, starts, ends, ud_lo):
-    import torch
-
-    from lsio_b200.io_uring_cuda import Receiver
-
-    rx = u.completion()
-    total = len(paths) * N_CHUNKS
-    t0 = time.perf_counter()
-    for p, fid in zip(paths, file_ids):
-        u.get_ranges_arrays(p, starts, ends, (np.uint64(fid) << np.uint64(32)) | ud_lo)
-    got = ok_n = bad = 0
-    while got < total:
-        rec = rx.recv_batch(4096, 60.0)
-        ok = rec["status"] == 0
-        ud = rec["chunk"]["user_data"]
-        fi, ci = (ud >> np.uint64(32)).astype(np.int64), (ud & np.uint64(0xFFFFFFFF)).astype(np.int64)
-        good = ok & (rec["crc32c"] == expect_crc[fi % len(expect_crc), ci % N_CHUNKS])
-        ok_n += int(good.sum())
-        bad += int((~good).sum())
-        Receiver.drop_buffers(rec)
-        got += len(rec)
-    torch.cuda.synchronize()
-    return time.perf_counter() - t0, ok_n * BLOCK, bad
+    """One pass of lsio_bench::read_files over the backend's C ABI (native driver, csrc/lsio_bench.cpp):
+    submit every file, receive one chunk per range, check its device CRC against the table made at
+    generation time, drop it; ends with a device synchronise."""
+    secs, nbytes, ok, bad = u.bench_read_files(paths, file_ids, BLOCK, N_CHUNKS, expect_crc)
+    return secs, nbytes, bad + (len(paths) * N_CHUNKS - ok - bad)
 
 
 def run_e2e(args, dev, paths, file_ids, expect_crc, steps, warmup, workers, o_direct=True):

@@ -1,0 +1,38 @@
+/*
+ * lsio_bench.h -- C ABI of the workload driver: the B200 build's `lsio_bench::read_files`
+ * (crates/lsio_bench/src/main.rs:124-190): submit one get_ranges per file, then drain one
+ * completion per range, wall-clock from before the first submit to the last completion
+ * (plus, here, a device synchronise so every byte is resident in HBM).  Unlike the reference
+ * (which only counts completions) every chunk can be checked against an expected
+ * CRC-32C table, and payload bytes are counted from the ranges actually delivered.
+ */
+#ifndef LSIO_BENCH_H
+#define LSIO_BENCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "lsio_uring_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsio_bench_result {
+    double seconds;        /* first get_ranges -> last chunk received, checked and device-synchronised */
+    uint64_t chunks_ok;    /* Ok chunks whose CRC matched (or all Ok chunks when no table is given) */
+    uint64_t chunks_bad;   /* Err items + CRC mismatches */
+    uint64_t payload_bytes;/* sum of the lengths of the Ok chunks */
+} lsio_bench_result;
+
+/* paths[i] is read as n_chunks ranges [k*blocksize, (k+1)*blocksize) (main.rs:137-145) with
+ * user_data = file_ids[i] << 32 | k.  expected_crc32c may be NULL; otherwise it is indexed
+ * [file_ids[i] * crc_stride + k].  Chunks are dropped on receipt, as lsio_bench does. */
+int lsio_bench_read_files(lsio_uring_cuda* backend, const char* const* paths, const uint32_t* file_ids, size_t n_files,
+                          uint64_t blocksize, uint32_t n_chunks, const uint32_t* expected_crc32c, size_t crc_stride,
+                          lsio_bench_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -180,3 +180,13 @@ lib.lsio_aligned_bytes_drop_many.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 lib.lsio_probe_read_ceiling.restype = ctypes.c_int
 lib.lsio_probe_read_ceiling.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
                                         ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
+
+
+# ---- include/lsio_bench.h -------------------------------------------------------------------------
+class CBenchResult(ctypes.Structure):
+    _fields_ = [("seconds", ctypes.c_double), ("chunks_ok", ctypes.c_uint64), ("chunks_bad", ctypes.c_uint64), ("payload_bytes", ctypes.c_uint64)]
+
+
+lib.lsio_bench_read_files.restype = ctypes.c_int
+lib.lsio_bench_read_files.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64,
+                                      ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(CBenchResult)]

@@ -198,6 +198,19 @@ class IoUringCuda:
     def completion(self):
         return self._rx
 
+    def bench_read_files(self, paths, file_ids, blocksize, n_chunks, expected_crc32c=None):
+        """lsio_bench::read_files (crates/lsio_bench/src/main.rs:124-190) run natively over this backend:
+        returns (seconds, payload_bytes, chunks_ok, chunks_bad)."""
+        arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(os.fspath(p)) for p in paths])
+        ids = np.ascontiguousarray(file_ids, dtype=np.uint32)
+        crc = None if expected_crc32c is None else np.ascontiguousarray(expected_crc32c, dtype=np.uint32)
+        res = N.CBenchResult()
+        rc = N.lib.lsio_bench_read_files(self._h, arr, ids.ctypes.data, len(paths), blocksize, n_chunks,
+                                         None if crc is None else crc.ctypes.data, 0 if crc is None else crc.shape[1], ctypes.byref(res))
+        if rc:
+            raise RuntimeError(f"lsio_bench_read_files failed: rc={rc}")
+        return res.seconds, res.payload_bytes, res.chunks_ok, res.chunks_bad
+
     def stats(self):
         s = N.CStats()
         N.lib.lsio_uring_cuda_get_stats(self._h, ctypes.byref(s))

@@ -336,3 +336,63 @@ def test_read_planner_merges_adjacent_overlapping_and_duplicate_ranges(lsio, ora
             assert st["read_bytes"] < 2.5 * size
         else:
             assert st["reads"] >= len(ranges)
+
+
+def test_native_bench_driver(lsio, oracle, cuda_dev, data_dir):
+    """lsio_bench::read_files restated natively (include/lsio_bench.h): counts delivered bytes
+    (not filesize * n_files) and checks every chunk's CRC."""
+    fsize, bs = 1_000_000, 262_144
+    n_chunks = fsize // bs
+    fns, table = [], np.zeros((4, n_chunks), dtype=np.uint32)
+    for i in range(4):
+        fn = os.path.join(data_dir, f"lsio_bench_{i}")
+        oracle.write_file(fn, 40 + i, fsize)
+        fns.append(fn)
+        for k in range(n_chunks):
+            table[i, k] = oracle.crc32c(oracle.pattern(40 + i, k * bs, bs))
+    with lsio.IoUringCuda(4, arena_bytes=64 << 20, staging_bytes=16 << 20) as u:
+        secs, nbytes, ok, bad = u.bench_read_files(fns, range(4), bs, n_chunks, table)
+        assert (nbytes, ok, bad) == (4 * n_chunks * bs, 4 * n_chunks, 0) and secs > 0
+        table[2, 1] ^= 1  # a wrong expectation must be noticed
+        _, nbytes, ok, bad = u.bench_read_files(fns, range(4), bs, n_chunks, table)
+        assert (ok, bad) == (4 * n_chunks - 1, 1)
+
+
+def test_range_larger_than_two_gib(lsio, oracle, cuda_dev):
+    """The reference panics above 2,147,479,552 B (get_range.rs:23-30); here the read is split and the
+    segment CRCs are combined.  A sparse tmpfs file keeps it cheap: 2.5 GiB of zeros + a marker."""
+    import torch
+
+    if not os.path.isdir("/dev/shm"):
+        pytest.skip("needs tmpfs")
+    size = (5 << 29) + 123
+    fn = f"/dev/shm/lsio_big_{os.getpid()}"
+    try:
+        with open(fn, "wb") as f:
+            f.truncate(size)
+            f.seek(size - 100)
+            f.write(b"\x5a" * 100)
+        with lsio.IoUringCuda(4, arena_bytes=3 << 30, staging_bytes=256 << 20) as u:
+            u.get_ranges(fn, [(1, -1)], [7])
+            c = u.completion().recv_timeout(120)
+            assert c.is_ok() and c.user_data == 7 and c.buffer.len() == size - 1
+            t = c.buffer.to_torch()
+            assert int(torch.count_nonzero(t[:-100])) == 0 and bool((t[-100:] == 0x5A).all())
+            # crc32c(zeros(n) + 0x5a*100) from crc32c of a small zero block by repeated combining
+            z = oracle.crc32c(bytes(1 << 20))
+            n, acc, blk, blen = size - 1 - 100, 0, z, 1 << 20
+            want, first, k = 0, True, n // (1 << 20)
+            while k:  # binary decomposition of the zero run
+                if k & 1:
+                    want = blk if first else oracle.crc32c_combine(want, blk, blen)
+                    first = False
+                blk = oracle.crc32c_combine(blk, blk, blen)
+                blen *= 2
+                k >>= 1
+            tail = bytes(n % (1 << 20)) + b"\x5a" * 100
+            want = oracle.crc32c_combine(want, oracle.crc32c(tail), len(tail))
+            assert c.crc32c == want
+            assert u.stats()["reads"] >= size // (8 << 20)
+    finally:
+        if os.path.exists(fn):
+            os.unlink(fn)
