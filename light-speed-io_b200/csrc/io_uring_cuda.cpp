@@ -682,7 +682,13 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
             seg.src = (uint64_t)(uintptr_t)(g.dev_ring + e.log_off % cap + sp.head);
             seg.dst = (uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off);
             seg.len = sp.payload_len;
-            pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store);  // sized by the caller's limits
+            if (!pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store)) {
+                // cannot happen: device_main sizes every run with the same tile arithmetic
+                RangePlan& p = e.req->ranges[sp.range];
+                if (!p.failed.exchange(true)) send_error(be, -EOVERFLOW, 0, *e.req, (int)sp.range, "internal: pack batch overflow");
+                p.segs_left.fetch_sub(1, std::memory_order_acq_rel);
+                continue;
+            }
             b->desc.push_back(Batch::DescRef{s, rd.first_seg + k});
         }
         landed_bytes += e.len;

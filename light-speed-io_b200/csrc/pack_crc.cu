@@ -59,6 +59,12 @@ constexpr int kWarps = kThreads / 32;
 #ifndef LSIO_TILE_MAP
 #define LSIO_TILE_MAP 0  // 0: tile i -> CTA i % grid (interleaved); 1: each CTA owns a contiguous run of tiles
 #endif
+#ifndef LSIO_PREFETCH_ROWS
+#define LSIO_PREFETCH_ROWS 0   // rows of 512 B to prefetch into L2 ahead of the load stream (0 = off)
+#endif
+#ifndef LSIO_LD_L2_256
+#define LSIO_LD_L2_256 0       // 1: ld...L2::256B prefetch-size hint on the streaming loads
+#endif
 #ifndef LSIO_ST_HINT
 #define LSIO_ST_HINT 1   // 1: st.global.L1::no_allocate, 0: plain st.global, 2: st.global.cs
 #endif
@@ -139,11 +145,16 @@ struct Params {
 // ---- device helpers ----------------------------------------------------------------------
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 r;
+#if LSIO_LD_L2_256
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+#endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 ld_cached(const uint4* p) { return __ldg(p); }
 __device__ __forceinline__ void st_vec(uint4* p, const uint4& v) {
 #if LSIO_ST_HINT == 1
@@ -257,10 +268,26 @@ __device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, c
     int vr = vend - kTileVecs;
     // skip rows that lie wholly before the segment (leading zeros: free)
     if (vr < 0) vr += ((-vr) >> 5) << 5;
+    constexpr int kPf = LSIO_PREFETCH_ROWS;
+    const int pf_end = min(vend, g.nvec);  // prefetch only source vectors of this tile
+    if (kPf > 0) {  // prologue: fill the L2 prefetch window
+#pragma unroll 1
+        for (int r = kUnroll; r < kPf; r++) {
+            const int v = vr + 32 * r + lane;
+            if (v < pf_end) prefetch_l2(g.sbase + v);
+        }
+    }
     for (; vr < vend;) {
         // interior rows: every vector lies wholly inside the segment and past the init bytes
         const bool interior4 = vr >= 2 && vr + 32 * kUnroll <= min(vend, g.nvec - 1);
         if (interior4) {
+            if (kPf > 0) {
+#pragma unroll
+                for (int u = 0; u < kUnroll; u++) {
+                    const int v = vr + 32 * (kPf + u) + lane;
+                    if (v < pf_end) prefetch_l2(g.sbase + v);
+                }
+            }
             uint4 d[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) d[u] = fetch<WS, false>(g, vr + 32 * u + lane, bs);
