@@ -255,7 +255,7 @@ def run_e2e(args, dev, paths, file_ids, expect_crc, steps, warmup, workers, o_di
     starts, ends = chunk_ranges()
     ud_lo = np.arange(N_CHUNKS, dtype=np.uint64)
     u = L.IoUringCuda(workers, devices=(dev.index,), arena_bytes=8 << 30, staging_bytes=args.staging_mib << 20, o_direct=int(o_direct),
-                      min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries)
+                      min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges)
     try:
         for _ in range(warmup):
             e2e_pass(u, paths, file_ids, expect_crc, starts, ends, ud_lo)
@@ -432,7 +432,8 @@ def run_config(args, dev, rank):
 
     result = {"config": desc, "source": source, "ranges": n_ranges, "payload_bytes": payload}
     with L.IoUringCuda(args.workers, devices=(dev.index,), arena_bytes=arena, staging_bytes=args.staging_mib << 20,
-                       min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries) as u:
+                       min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, statx_via_ring=args.statx_via_ring,
+                       max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges) as u:
         if keep_resident:  # verification pass
             _, rec = one_pass(u, True)
             assert (rec["status"] == 0).all(), rec[rec["status"] != 0][:3]
@@ -451,13 +452,20 @@ def run_config(args, dev, rank):
                 v.drop()
         secs = []
         loops = args.c5_loops if args.config == "C5" else 1
+        expect = None
+        if keep_resident:  # the fused CRCs of the verified pass, indexed by user_data, are the expectation of the timed passes
+            expect = np.zeros(n_ranges, dtype=np.uint32)
+            expect[ud] = rec["crc32c"]
+
+        def native_pass():  # timed passes run the native driver (csrc/lsio_bench.cpp): no Python in the loop
+            t, nb, ok, bad = u.bench_read_ranges(paths, per, expect)
+            assert bad == 0 and ok == n_ranges and nb == payload, (ok, bad, nb)
+            return t
+
         for _ in range(max(1, args.warmup - 2)):
-            one_pass(u, False)
+            native_pass()
         for _ in range(args.steps):
-            t = 0.0
-            for _ in range(loops):
-                t += one_pass(u, False)[0]
-            secs.append(t)
+            secs.append(sum(native_pass() for _ in range(loops)))
         st = u.stats()
     result["gib_s"] = payload * loops * len(secs) / sum(secs) / GIB
     result["secs_per_step"] = secs
@@ -572,6 +580,9 @@ def main():
     ap.add_argument("--staging-mib", type=int, default=1024)
     ap.add_argument("--min-copy-mib", type=int, default=8)
     ap.add_argument("--sq-entries", type=int, default=64)
+    ap.add_argument("--max-read-kib", type=int, default=1024, help="reads (merged or split) are cut at this size")
+    ap.add_argument("--merge-ranges", type=int, default=1)
+    ap.add_argument("--statx-via-ring", type=int, default=0, help="1 = the reference's openat+statx SQE pair per file")
     ap.add_argument("--disk-dir", default="/tmp/lsio_bench_disk", help="secondary e2e leg on a disk-backed directory ('' disables)")
     ap.add_argument("--disk-files", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -32,6 +32,12 @@ int lsio_bench_read_files(lsio_uring_cuda* backend, const char* const* paths, co
                           uint64_t blocksize, uint32_t n_chunks, const uint32_t* expected_crc32c, size_t crc_stride,
                           lsio_bench_result* out);
 
+/* Same driver for arbitrary per-file range lists (BASELINE configs C3-C5): file i owns counts[i]
+ * consecutive entries of starts[]/ends[] (reference range semantics, negative = from the end);
+ * user_data = global index of the range.  expected_crc32c (optional) is indexed by that index. */
+int lsio_bench_read_ranges(lsio_uring_cuda* backend, const char* const* paths, size_t n_files, const int64_t* starts,
+                           const int64_t* ends, const uint64_t* counts, const uint32_t* expected_crc32c, lsio_bench_result* out);
+
 #ifdef __cplusplus
 }
 #endif

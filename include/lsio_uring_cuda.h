@@ -46,11 +46,17 @@ typedef struct lsio_uring_cuda_config {
     uint32_t o_direct;          /* 1 = O_RDONLY|O_DIRECT as the reference (sqe.rs:25); 0 = buffered          */
     uint64_t staging_bytes;     /* pinned + io_uring-registered staging ring per device                      */
     uint64_t arena_bytes;       /* HBM arena per device that request buffers are carved from                 */
-    uint64_t max_read_bytes;    /* reads longer than this are split, <= 1 GiB (reference: panics > 2 GiB)    */
+    uint64_t max_read_bytes;    /* reads (merged or not) are cut at this size; default 1 MiB, <= 1 GiB        */
     uint64_t min_copy_bytes;    /* H2D copies are coalesced up to at least this many bytes                   */
     uint32_t flush_us;          /* ...or until the oldest landed read has waited this long                   */
     uint32_t merge_ranges;      /* 1 = ranges of one request whose padded spans touch/overlap share one read    */
     uint64_t merge_gap_bytes;   /* ...also when separated by at most this many bytes (the gap is read and dropped) */
+    uint32_t statx_via_ring;    /* 1 = the reference's two unlinked SQEs per file, openat + statx (get_ranges.rs:49-65):
+                                   a missing file yields two Err items; the kernel always runs statx on an io-wq
+                                   worker.  0 (default) = openat SQE, then fstat() on the new fd when it completes
+                                   (never blocks, no second SQE): a missing file yields one Err item, as the
+                                   reference's own doc comment promises (lsio_io lib.rs:30-35) */
+    uint32_t reserved2;
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {

@@ -136,7 +136,8 @@ class CConfig(ctypes.Structure):
                 ("checksum", ctypes.c_uint32), ("pack_align", ctypes.c_uint32), ("pin_threads", ctypes.c_uint32),
                 ("o_direct", ctypes.c_uint32), ("staging_bytes", ctypes.c_uint64), ("arena_bytes", ctypes.c_uint64),
                 ("max_read_bytes", ctypes.c_uint64), ("min_copy_bytes", ctypes.c_uint64), ("flush_us", ctypes.c_uint32),
-                ("merge_ranges", ctypes.c_uint32), ("merge_gap_bytes", ctypes.c_uint64)]
+                ("merge_ranges", ctypes.c_uint32), ("merge_gap_bytes", ctypes.c_uint64),
+                ("statx_via_ring", ctypes.c_uint32), ("reserved2", ctypes.c_uint32)]
 
 
 class CStats(ctypes.Structure):
@@ -190,3 +191,6 @@ class CBenchResult(ctypes.Structure):
 lib.lsio_bench_read_files.restype = ctypes.c_int
 lib.lsio_bench_read_files.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64,
                                       ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(CBenchResult)]
+lib.lsio_bench_read_ranges.restype = ctypes.c_int
+lib.lsio_bench_read_ranges.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(CBenchResult)]

@@ -32,6 +32,16 @@ class Channel {
         q_.push_back(std::move(v));
         not_empty_.notify_one();
     }
+    // Sends n items with as few lock round trips and wake-ups as the bound allows (order kept).
+    void send_many(T* items, size_t n) {
+        size_t i = 0;
+        while (i < n) {
+            std::unique_lock<std::mutex> lk(mu_);
+            not_full_.wait(lk, [&] { return q_.size() < bound_; });
+            while (i < n && q_.size() < bound_) q_.push_back(std::move(items[i++]));
+            not_empty_.notify_all();
+        }
+    }
     RecvStatus recv(T* out, int timeout_ms) {
         std::unique_lock<std::mutex> lk(mu_);
         auto ready = [&] { return !q_.empty() || senders_ == 0; };

@@ -50,7 +50,6 @@ extern "C" int lsio_bench_read_files(lsio_uring_cuda* backend, const char* const
             views[i] = o.status == 0 ? o.chunk.buffer : nullptr;
             if (o.status != 0) {
                 r.chunks_bad++;
-                if (o.opcode != 0 && o.chunk.user_data == 0 && n_chunks) got += 0;  // request-level error: counted below
                 continue;
             }
             bool ok = true;
@@ -69,6 +68,63 @@ extern "C" int lsio_bench_read_files(lsio_uring_cuda* backend, const char* const
         got += n;
     }
     cudaDeviceSynchronize();  // chunks are emitted only after their pack event; this closes the timed region on the device too
+    r.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    lsio_completion_drop(rx);
+    *out = r;
+    return status;
+}
+
+extern "C" int lsio_bench_read_ranges(lsio_uring_cuda* backend, const char* const* paths, size_t n_files, const int64_t* starts,
+                                      const int64_t* ends, const uint64_t* counts, const uint32_t* expected_crc32c, lsio_bench_result* out) {
+    if (!backend || !paths || !starts || !ends || !counts || !out) return -22;
+    uint64_t total = 0, max_n = 0;
+    for (size_t i = 0; i < n_files; i++) {
+        total += counts[i];
+        if (counts[i] > max_n) max_n = counts[i];
+    }
+    std::vector<uint64_t> ud(max_n ? max_n : 1);
+    lsio_completion* rx = lsio_uring_cuda_completion(backend);
+    if (!rx) return -22;
+    const size_t kBatch = 2048;
+    std::vector<lsio_output> rec(kBatch);
+    std::vector<lsio_aligned_bytes*> views(kBatch);
+    lsio_bench_result r{};
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t off = 0;
+    for (size_t i = 0; i < n_files; i++) {
+        for (uint64_t k = 0; k < counts[i]; k++) ud[k] = off + k;
+        int rc = lsio_uring_cuda_get_ranges(backend, paths[i], starts + off, ends + off, counts[i], ud.data(), counts[i]);
+        if (rc) {
+            lsio_completion_drop(rx);
+            return rc;
+        }
+        off += counts[i];
+    }
+    uint64_t got = 0;
+    int status = 0;
+    while (got < total) {
+        size_t n = 0;
+        int rc = lsio_completion_recv_batch(rx, rec.data(), kBatch, 20000, &n);
+        if (rc != LSIO_RECV_OK) {
+            status = rc == LSIO_RECV_TIMEOUT ? -110 : -32;
+            break;
+        }
+        for (size_t i = 0; i < n; i++) {
+            const lsio_output& o = rec[i];
+            views[i] = o.status == 0 ? o.chunk.buffer : nullptr;
+            bool ok = o.status == 0;
+            if (ok && expected_crc32c) ok = (o.checksums & LSIO_CHECKSUM_CRC32C) && o.crc32c == expected_crc32c[o.chunk.user_data];
+            if (ok) {
+                r.chunks_ok++;
+                r.payload_bytes += lsio_aligned_bytes_len(o.chunk.buffer);
+            } else {
+                r.chunks_bad++;
+            }
+        }
+        lsio_aligned_bytes_drop_many(views.data(), n);
+        got += n;
+    }
+    cudaDeviceSynchronize();
     r.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     lsio_completion_drop(rx);
     *out = r;

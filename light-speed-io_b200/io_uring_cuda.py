@@ -211,6 +211,21 @@ class IoUringCuda:
             raise RuntimeError(f"lsio_bench_read_files failed: rc={rc}")
         return res.seconds, res.payload_bytes, res.chunks_ok, res.chunks_bad
 
+    def bench_read_ranges(self, paths, per_file_ranges, expected_crc32c=None):
+        """Native driver for arbitrary per-file (starts, ends) arrays; user_data = global range index.
+        Returns (seconds, payload_bytes, chunks_ok, chunks_bad)."""
+        arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(os.fspath(p)) for p in paths])
+        st = np.ascontiguousarray(np.concatenate([r[0] for r in per_file_ranges]), dtype=np.int64)
+        en = np.ascontiguousarray(np.concatenate([r[1] for r in per_file_ranges]), dtype=np.int64)
+        cnt = np.array([len(r[0]) for r in per_file_ranges], dtype=np.uint64)
+        crc = None if expected_crc32c is None else np.ascontiguousarray(expected_crc32c, dtype=np.uint32)
+        res = N.CBenchResult()
+        rc = N.lib.lsio_bench_read_ranges(self._h, arr, len(paths), st.ctypes.data, en.ctypes.data, cnt.ctypes.data,
+                                          None if crc is None else crc.ctypes.data, ctypes.byref(res))
+        if rc:
+            raise RuntimeError(f"lsio_bench_read_ranges failed: rc={rc}")
+        return res.seconds, res.payload_bytes, res.chunks_ok, res.chunks_bad
+
     def stats(self):
         s = N.CStats()
         N.lib.lsio_uring_cuda_get_stats(self._h, ctypes.byref(s))
