@@ -99,6 +99,10 @@ const char* lsio_uring_cuda_last_error(void);
 int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads,
                             uint32_t queue_depth, uint32_t o_direct, double* gib_per_s);
 
+/* Test aid: host-logic self tests of the shipped components (tracker, user_data, channel, staging
+ * log, arena, GF(2) combine), no GPU needed; see csrc/selftest.cpp. 0 = pass. */
+int lsio_uring_cuda_selftest(int which);
+
 /* Drop: finishes in-flight work, joins every thread, disconnects the channel.  Chunks already
  * received stay valid until dropped. */
 void lsio_uring_cuda_free(lsio_uring_cuda* self);

@@ -194,3 +194,5 @@ lib.lsio_bench_read_files.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_c
 lib.lsio_bench_read_ranges.restype = ctypes.c_int
 lib.lsio_bench_read_ranges.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(CBenchResult)]
+lib.lsio_uring_cuda_selftest.restype = ctypes.c_int
+lib.lsio_uring_cuda_selftest.argtypes = [ctypes.c_int]

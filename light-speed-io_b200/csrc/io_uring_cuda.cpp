@@ -51,6 +51,9 @@ static inline uint64_t now_ns() {
 constexpr uint64_t kAlign = 512;  // crates/lsio_uring/src/sqe.rs:12
 
 struct Group;
+struct Request;
+using StagingLog = StagingLogT<Request>;
+using StageEntry = StageEntryT<Request>;
 
 // One read serves one or more segments; a segment is the part of one range that one read carries.
 // (The reference issues exactly one read per range; merging adjacent ranges into one read is its

@@ -19,21 +19,23 @@
 
 namespace lsio {
 
-struct Request;
-
 enum : uint32_t { kStageReading = 0, kStageLanded = 1, kStageFailed = 2 };
 
-struct StageEntry {
+// R = the request type an entry keeps alive (the backend's Request; a dummy in the self test).
+template <class R>
+struct StageEntryT {
     uint64_t log_off = 0;  // monotonically increasing logical byte offset; phys = log_off % capacity
     uint32_t len = 0;      // bytes reserved (padded read length)
     std::atomic<uint32_t> state{kStageReading};
-    std::shared_ptr<Request> req;
-    uint32_t seg = 0;      // index into req->segs
+    std::shared_ptr<R> req;
+    uint32_t seg = 0;      // index into req->reads
     uint64_t landed_ns = 0;
 };
 
-class StagingLog {
+template <class R>
+class StagingLogT {
   public:
+    using StageEntry = StageEntryT<R>;
     static constexpr uint64_t kRegBoundary = 1ull << 30;  // one io_uring registered buffer is <= 1 GiB
 
     void init(uint64_t capacity, size_t max_entries) {
@@ -43,7 +45,7 @@ class StagingLog {
     uint64_t capacity() const { return cap_; }
 
     // Reserve `len` bytes (multiple of 512).  Thread-safe.  nullptr = ring or entry table full.
-    StageEntry* alloc(uint32_t len, std::shared_ptr<Request> req, uint32_t seg) {
+    StageEntry* alloc(uint32_t len, std::shared_ptr<R> req, uint32_t seg) {
         std::lock_guard<std::mutex> lk(mu_);
         if (alloc_seq_ - retire_seq_.load(std::memory_order_acquire) >= entries_.size()) return nullptr;
         uint64_t off = alloc_off_;

@@ -27,8 +27,8 @@ def _check_chunks(oracle, items, fn_of, ranges_of):
         assert c.buffer.memory_kind == "device" and c.device == 0
 
 
-@pytest.mark.parametrize("o_direct,statx_via_ring", [(1, 0), (0, 0), (1, 1)])
-def test_get_ranges(lsio, oracle, cuda_dev, data_dir, o_direct, statx_via_ring):
+@pytest.mark.parametrize("o_direct,statx_via_ring,sqpoll", [(1, 0, 0), (0, 0, 0), (1, 1, 0), (1, 1, 1)])
+def test_get_ranges(lsio, oracle, cuda_dev, data_dir, o_direct, statx_via_ring, sqpoll):
     """integration_test.rs::test_get_ranges against the CUDA backend."""
     N_WORKER_THREADS, FILE_SIZE, CHUNK_SIZE = 4, MIB, 4 * KIB
     N_CHUNKS = FILE_SIZE // CHUNK_SIZE
@@ -40,7 +40,7 @@ def test_get_ranges(lsio, oracle, cuda_dev, data_dir, o_direct, statx_via_ring):
         f.write(file_contents)
         f.flush()
         os.fsync(f.fileno())
-    uring = lsio.IoUringCuda(N_WORKER_THREADS, o_direct=o_direct, statx_via_ring=statx_via_ring, arena_bytes=256 << 20, staging_bytes=32 << 20)
+    uring = lsio.IoUringCuda(N_WORKER_THREADS, o_direct=o_direct, statx_via_ring=statx_via_ring, sqpoll=sqpoll, arena_bytes=256 << 20, staging_bytes=32 << 20)  # (1, 1, 1) is the reference's own ring configuration
     uring.get_ranges(filename, [(i * CHUNK_SIZE, (i + 1) * CHUNK_SIZE) for i in range(N_CHUNKS)], range(N_CHUNKS))
     vec = [None] * N_CHUNKS
     for i in range(N_CHUNKS):

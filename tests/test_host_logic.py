@@ -215,3 +215,13 @@ def test_files_for_rank_is_a_partition(lsio):
     for r in range(4):
         for i in sharding.files_for_rank(100, r, 4, fn, gpu_nodes):
             assert gpu_nodes[r] == fn[i]
+
+
+# ---- the shipped C++ host components, restating the reference's unit tests (csrc/selftest.cpp) ----------
+@pytest.mark.parametrize("which,name", [(1, "tracker (tracker.rs:74-114)"), (2, "user_data (user_data.rs:47-56)"),
+                                        (3, "bounded channel: back-pressure, batch receive, disconnect"),
+                                        (4, "staging ring as a log: wrap, no-straddle, in-order retire"),
+                                        (5, "HBM arena: first fit + coalescing"), (6, "crc32c_combine / GF(2) inverse")])
+def test_native_host_components(lsio, which, name):
+    rc = lsio._native.lib.lsio_uring_cuda_selftest(which)
+    assert rc == 0, f"{name}: check {rc % 100} failed"
