@@ -51,13 +51,15 @@ def dist_env():
 
 
 def dist_init(backend):
+    import torch
     import torch.distributed as dist
 
-    rank, world, _ = dist_env()
+    rank, world, local = dist_env()
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group(backend, rank=rank, world_size=world)
+        kw = {"device_id": torch.device(f"cuda:{local}")} if backend == "nccl" else {}
+        dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, world
 
 
@@ -575,7 +577,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dir", default=None, help="directory for the synthetic files (default: /dev/shm if it has room)")
     ap.add_argument("--files", type=int, default=N_FILES)
-    ap.add_argument("--workers", type=int, default=8, help="io_uring worker threads per GPU (README config: 8)")
+    ap.add_argument("--workers", type=int, default=0, help="io_uring worker threads per GPU (0 = 8, the README config, capped by the CPUs available per rank)")
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--staging-mib", type=int, default=1024)
     ap.add_argument("--min-copy-mib", type=int, default=8)
@@ -605,6 +607,8 @@ def main():
     from lsio_b200 import cuda_ops, sharding
 
     rank, world, local = dist_env()
+    if args.workers <= 0:  # leave a core each for the device thread, the consumer and the interpreter
+        args.workers = max(2, min(8, (os.cpu_count() or 8) // max(world, 1) - 3))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -737,6 +741,10 @@ def main():
                 pass
         print(json.dumps(line), flush=True)
     barrier()
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
     return 0
 
 

@@ -169,6 +169,7 @@ struct Group {
     std::atomic<bool> stop_device{false};
     std::atomic<uint32_t> workers_alive{0};
     uint64_t copy_seq = 0;  // device thread: next staging entry to copy
+    Batch* last_flush_batch = nullptr;  // the batch flush_run() was filling when it failed
     std::string init_error;
 };
 
@@ -687,6 +688,7 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
     Backend* be = g.be;
     Batch* b = g.free_batches.front();
     g.free_batches.pop_front();
+    g.last_flush_batch = b;
     b->counts = PackBatchCounts();
     b->desc.clear();
     b->seq_begin = seq_begin;
@@ -830,7 +832,26 @@ static void device_main(Group& g) {
                 const bool timed_out = oldest && now_ns() - oldest > (uint64_t)cfg.flush_us * 1000;
                 if (hit_limit || bytes >= cfg.min_copy_bytes || timed_out || draining || (!oldest)) {
                     int rc = flush_run(g, g.copy_seq, s);
-                    if (rc) fprintf(stderr, "lsio_b200: flush failed: %s\n", last_error_text().c_str());
+                    if (rc) {
+                        // A CUDA call failed while enqueueing: report every range of the run in-band and
+                        // retire it, so that callers see errors instead of a hang.
+                        fprintf(stderr, "lsio_b200: flush failed: %s\n", last_error_text().c_str());
+                        Batch* b = g.last_flush_batch;  // popped from the free list by flush_run, never reached `inflight`
+                        for (uint64_t q = g.copy_seq; q < s; q++) {
+                            StageEntry& e = g.log.at(q);
+                            if (e.state.load(std::memory_order_acquire) != kStageLanded) continue;
+                            const ReadPlan& rd = e.req->reads[e.seg];
+                            for (uint32_t k = 0; k < rd.nsegs; k++) {
+                                const uint32_t range = e.req->segs[rd.first_seg + k].range;
+                                if (!e.req->ranges[range].failed.exchange(true)) send_error(be, rc, 0, *e.req, (int)range, "CUDA error while enqueueing the H2D/pack stage");
+                            }
+                        }
+                        cudaStreamSynchronize(g.s_copy);
+                        cudaStreamSynchronize(g.s_pack);
+                        cudaGetLastError();
+                        retire_batch(g, *b);  // its ranges are marked failed: nothing is emitted, the slots are freed
+                        g.free_batches.push_back(b);
+                    }
                     g.copy_seq = s;
                     progressed = true;
                 }
