@@ -56,7 +56,8 @@ typedef struct lsio_uring_cuda_config {
                                    worker.  0 (default) = openat SQE, then fstat() on the new fd when it completes
                                    (never blocks, no second SQE): a missing file yields one Err item, as the
                                    reference's own doc comment promises (lsio_io lib.rs:30-35) */
-    uint32_t reserved2;
+    uint32_t zero_copy;         /* 1 = no H2D memcpy: the pack kernel reads the mapped pinned ring over PCIe and writes
+                                   HBM once (fuses H2D + strip + checksum); 0 (default) = cudaMemcpyAsync + device ring */
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {

@@ -156,6 +156,7 @@ struct Group {
     std::shared_ptr<DeviceArena> arena;
     uint8_t* host_ring = nullptr;
     uint8_t* dev_ring = nullptr;
+    uint8_t* host_ring_dev = nullptr;  // device alias of the mapped pinned ring (zero_copy mode)
     StagingLog log;
     cudaStream_t s_copy = nullptr, s_pack = nullptr;
     std::vector<Batch> batches;
@@ -707,7 +708,7 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
         for (uint32_t k = 0; k < rd.nsegs; k++) {
             const SegPlan& sp = e.req->segs[rd.first_seg + k];
             lsio_cuda_segment seg;
-            seg.src = (uint64_t)(uintptr_t)(g.dev_ring + e.log_off % cap + sp.head);
+            seg.src = (uint64_t)(uintptr_t)((be->cfg.zero_copy ? g.host_ring_dev : g.dev_ring) + e.log_off % cap + sp.head);
             seg.dst = (uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off);
             seg.len = sp.payload_len;
             if (!pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store)) {
@@ -722,11 +723,13 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
         landed_bytes += e.len;
     }
     if (landed_bytes) {
-        LSIO_CUDA_TRY(cudaMemcpyAsync(g.dev_ring + phys, g.host_ring + phys, bytes, cudaMemcpyHostToDevice, g.s_copy));
-        LSIO_CUDA_TRY(cudaEventRecord(b->copied, g.s_copy));
-        be->stats.h2d_copies++;
-        be->stats.h2d_bytes += bytes;
-        LSIO_CUDA_TRY(cudaStreamWaitEvent(g.s_pack, b->copied, 0));
+        if (!be->cfg.zero_copy) {
+            LSIO_CUDA_TRY(cudaMemcpyAsync(g.dev_ring + phys, g.host_ring + phys, bytes, cudaMemcpyHostToDevice, g.s_copy));
+            LSIO_CUDA_TRY(cudaEventRecord(b->copied, g.s_copy));
+            be->stats.h2d_copies++;
+            be->stats.h2d_bytes += bytes;
+            LSIO_CUDA_TRY(cudaStreamWaitEvent(g.s_pack, b->copied, 0));
+        }
         LSIO_CUDA_TRY(cudaMemcpyAsync(b->dev_desc, b->host_desc, b->lay.upload_bytes, cudaMemcpyHostToDevice, g.s_pack));
         unsigned launches = 0;
         int rc = pack_batch_launch(g.device, b->lay, b->dev_desc, b->counts, flags, b->crc_dev, g.s_pack, &launches);
@@ -930,8 +933,9 @@ static int init_group(Group& g) {
     if (cfg.pin_threads) g.cpus = numa_cpus_of_device(g.device);
     const uint64_t ring_bytes = cfg.staging_bytes / 4096 * 4096;
     // pinned (page-locked, DMA-able) and later registered with every worker's io_uring
-    LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.host_ring, ring_bytes, cudaHostAllocPortable));
-    LSIO_CUDA_TRY(cudaMalloc((void**)&g.dev_ring, ring_bytes));
+    LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.host_ring, ring_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&g.host_ring_dev, g.host_ring, 0));
+    if (!cfg.zero_copy) LSIO_CUDA_TRY(cudaMalloc((void**)&g.dev_ring, ring_bytes));
     g.log.init(ring_bytes, 1 << 16);
     uint8_t* arena_base = nullptr;
     LSIO_CUDA_TRY(cudaMalloc((void**)&arena_base, cfg.arena_bytes));
@@ -1003,6 +1007,7 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->merge_ranges = 1;
     cfg->merge_gap_bytes = 0;
     cfg->statx_via_ring = 0;
+    cfg->zero_copy = 0;
 }
 
 int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {

@@ -317,8 +317,8 @@ def test_drop_with_work_in_flight_and_concurrent_submitters(lsio, oracle, cuda_d
         rx.drop()
 
 
-@pytest.mark.parametrize("merge,gap", [(1, 0), (0, 0), (1, 4096)])
-def test_read_planner_merges_adjacent_overlapping_and_duplicate_ranges(lsio, oracle, cuda_dev, data_dir, merge, gap):
+@pytest.mark.parametrize("merge,gap,zero_copy", [(1, 0, 0), (0, 0, 0), (1, 4096, 0), (1, 0, 1)])
+def test_read_planner_merges_adjacent_overlapping_and_duplicate_ranges(lsio, oracle, cuda_dev, data_dir, merge, gap, zero_copy):
     """SURVEY 8f rank 1 (planned in the reference: lsio_aligned_bytes/README.md:43-57): ranges whose
     padded spans touch or overlap share one read; every range still gets exactly one chunk with its own
     bytes and CRC, whatever the merge setting."""
@@ -331,7 +331,7 @@ def test_read_planner_merges_adjacent_overlapping_and_duplicate_ranges(lsio, ora
     ranges += [(2 * MIB + 100, 2 * MIB + 200), (2 * MIB + 3000, 2 * MIB + 3100)]          # 2.8 KiB apart: merged only with a gap
     ranges += [(5, 2 * MIB + 777)]                                     # one long range over everything before it
     ranges = [ranges[i] for i in np.random.default_rng(5).permutation(len(ranges))]  # submission order must not matter
-    with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, merge_ranges=merge, merge_gap_bytes=gap, max_read_bytes=512 << 10) as u:
+    with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, merge_ranges=merge, merge_gap_bytes=gap, max_read_bytes=512 << 10, zero_copy=zero_copy) as u:
         u.get_ranges(fn, ranges, range(len(ranges)))
         items = _drain(u.completion(), len(ranges))
         assert sorted(c.user_data for c in items) == list(range(len(ranges)))
