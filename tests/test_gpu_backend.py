@@ -402,3 +402,15 @@ def test_range_larger_than_two_gib(lsio, oracle, cuda_dev):
     finally:
         if os.path.exists(fn):
             os.unlink(fn)
+
+
+def test_lsio_bench_cli(lsio, cuda_dev, data_dir, capsys):
+    """The reference's CLI (crates/lsio_bench/src/main.rs) with the same flags, on its own data pattern."""
+    from lsio_b200 import lsio_bench
+
+    rc = lsio_bench.main(["--directory", data_dir, "--nrfiles", "3", "--filesize", "1000000", "--blocksize", "262144", "-w", "2"])
+    out = capsys.readouterr().out
+    assert rc == 0
+    assert "3 files x 3 chunks per file = 9 total chunks" in out
+    assert f"Delivered into HBM: {9 * 262144} bytes in 9 chunks (0 bad)" in out
+    assert "Total bandwidth = " in out
