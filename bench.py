@@ -610,8 +610,8 @@ def main():
 
     rank, world, local = dist_env()
     cpus_per_rank = (os.cpu_count() or 8) // max(world, 1)
-    if args.workers <= 0:  # leave a core each for the device thread, the consumer and the interpreter
-        args.workers = max(2, min(8, cpus_per_rank - 3))
+    if args.workers <= 0:  # leave cores for the consumer and the (mostly sleeping) device thread
+        args.workers = max(2, min(8, cpus_per_rank - 2))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
