@@ -414,3 +414,18 @@ def test_lsio_bench_cli(lsio, cuda_dev, data_dir, capsys):
     assert "3 files x 3 chunks per file = 9 total chunks" in out
     assert f"Delivered into HBM: {9 * 262144} bytes in 9 chunks (0 bad)" in out
     assert "Total bandwidth = " in out
+
+
+def test_plain_c_consumer_of_the_abi(lsio, cuda_dev, data_dir, tmp_path):
+    """integration_test.rs restated in C (tests/c/integration_test.c), linked against liblsio_b200.so: the
+    boundary is a plain C ABI, usable with no Python and no C++ on the caller's side."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(lsio._native.LIB_PATH)
+    exe = str(tmp_path / "integration_test")
+    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Werror", f"-I{root}/include", f"{root}/tests/c/integration_test.c", f"-L{libdir}", "-llsio_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    p = subprocess.run([exe, data_dir], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "256 chunks of 4096 bytes landed in HBM and match the file" in p.stdout
