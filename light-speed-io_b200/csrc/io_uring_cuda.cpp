@@ -952,6 +952,7 @@ static int init_group(Group& g) {
         b.lay = pack_batch_layout(max_segs, max_tiles);
         LSIO_CUDA_TRY(cudaHostAlloc((void**)&b.host_desc, b.lay.upload_bytes, cudaHostAllocPortable));
         LSIO_CUDA_TRY(cudaMalloc((void**)&b.dev_desc, b.lay.total_bytes));
+        LSIO_CUDA_TRY(cudaMemset(b.dev_desc, 0, b.lay.total_bytes));  // the kernel's tile-scheduler words start at zero
         LSIO_CUDA_TRY(cudaHostAlloc((void**)&b.crc_host, max_segs * 4, cudaHostAllocPortable | cudaHostAllocMapped));
         LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&b.crc_dev, b.crc_host, 0));
         LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));

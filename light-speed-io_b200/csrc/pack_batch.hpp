@@ -12,11 +12,11 @@
 namespace lsio {
 
 // Memory layout of one batch's descriptor block (same offsets on host and device):
-//   Seg[max_segs] | uint2 tiles[max_tiles] | u32 multi[max_segs] || u32 partials[max_tiles]
+//   Seg[max_segs] | uint2 tiles[max_tiles] | u32 multi[max_segs] || u32 partials[max_tiles] | u32 sched[2]
 // Only the part before `||` (upload_bytes) is written by the host and copied to the device.
 struct PackBatchLayout {
     size_t max_segs = 0, max_tiles = 0;
-    size_t off_tiles = 0, off_multi = 0, off_partials = 0;
+    size_t off_tiles = 0, off_multi = 0, off_partials = 0, off_sched = 0;  // sched: 2 words, must be zero before the first launch
     size_t upload_bytes = 0, total_bytes = 0;
 };
 PackBatchLayout pack_batch_layout(size_t max_segs, size_t max_tiles);

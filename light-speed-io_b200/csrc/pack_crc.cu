@@ -32,7 +32,8 @@
 //    ~14 % of HBM bandwidth when measured.
 //  * init/xorout: the 0xFFFFFFFF init is folded in by complementing the first 4 bytes of the
 //    message; xorout is a final NOT.  Segments shorter than 4 bytes take a scalar path.
-//  * Grid: one 1024-thread CTA per SM (persistent), tiles dealt round-robin to warps.
+//  * Grid: one 1024-thread CTA per SM (persistent); warps take tiles IN ORDER from a global counter
+//    (dynamic tile scheduler), which keeps the concurrently touched window dense.
 #include "common.hpp"
 #include "gf2.hpp"
 #include "lsio_cuda.h"
@@ -55,9 +56,6 @@ constexpr int kWarps = kThreads / 32;
 #endif
 #ifndef LSIO_UNROLL_SHIFTED
 #define LSIO_UNROLL_SHIFTED 2  // ... when every vector needs two source loads (measured: 2 beats 4, registers)
-#endif
-#ifndef LSIO_TILE_MAP
-#define LSIO_TILE_MAP 0  // 0: tile i -> CTA i % grid (interleaved); 1: each CTA owns a contiguous run of tiles
 #endif
 #ifndef LSIO_PREFETCH_ROWS
 #define LSIO_PREFETCH_ROWS 0   // rows of 512 B to prefetch into L2 ahead of the load stream (0 = off)
@@ -140,6 +138,7 @@ struct Params {
     uint32_t nmulti;
     uint32_t* crc_out;   // one per segment
     const uint32_t* tables;
+    uint32_t* sched;     // [0] next tile, [1] warps finished: the dynamic tile scheduler (zero between launches)
 };
 
 // ---- device helpers ----------------------------------------------------------------------
@@ -363,7 +362,7 @@ __device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, c
 template <bool kStore, bool kCrc>
 __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
     extern __shared__ __align__(16) uint32_t sh[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (kCrc) {
         // replicate the 4 KiB G table into the lane-private layout; copy the small tables
         for (int i = tid; i < 1024 * 32; i += kThreads) sh[kSmG + i] = __ldg(p.tables + kG + (i >> 5));
@@ -372,15 +371,15 @@ __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
     }
     const char* ltb = (const char*)(sh + kSmG) + lane * 4;
 
-#if LSIO_TILE_MAP == 0
-    // tile i -> CTA (i % grid), warp ((i / grid) % kWarps): neighbours in memory run on different SMs
-    for (uint32_t t = blockIdx.x + (uint32_t)warp * gridDim.x; t < p.ntiles; t += gridDim.x * kWarps) {
-#else
-    // each CTA streams one contiguous run of tiles; its warps take consecutive tiles
-    const uint32_t per_cta = (p.ntiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t t_end = min(p.ntiles, (blockIdx.x + 1) * per_cta);
-    for (uint32_t t = blockIdx.x * per_cta + warp; t < t_end; t += kWarps) {
-#endif
+    // Dynamic tile scheduler: every warp takes the NEXT tile from a global counter, like the hardware
+    // block scheduler would.  Measured on a plain copy (tools/copy_pattern_bench4.cu): static striding lets
+    // warps drift apart until the concurrently touched window spans hundreds of MB (94 % of the HBM copy
+    // peak); taking tiles in order keeps a dense sliding window (101 %).
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(p.sched, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= p.ntiles) break;
         const uint2 te = __ldg(p.tiles + t);
         const Seg s = *(p.segs + te.x);  // 32 B, warp-uniform broadcast
         const uint64_t dst = kStore ? s.dst : s.src;  // crc-only: checksum in place
@@ -420,6 +419,14 @@ __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
         const int z = (int)(a1 - (dst + s.len));
         const uint32_t crc = ~warp_mul(part, sh + kSmF + z * 32, lane);
         if (lane == 0) p.crc_out[te.x] = crc;
+    }
+    // the last warp to run dry re-arms the scheduler for the next launch of this batch / plan
+    if (lane == 0) {
+        const uint32_t done = atomicAdd(p.sched + 1, 1u);
+        if (done == gridDim.x * kWarps - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+        }
     }
 }
 
@@ -507,7 +514,8 @@ PackBatchLayout pack_batch_layout(size_t max_segs, size_t max_tiles) {
     l.off_multi = l.off_tiles + up(max_tiles * sizeof(uint2));
     l.upload_bytes = l.off_multi + up(max_segs * 4);
     l.off_partials = l.upload_bytes;
-    l.total_bytes = l.off_partials + up(max_tiles * 4);
+    l.off_sched = l.off_partials + up(max_tiles * 4);
+    l.total_bytes = l.off_sched + 256;
     return l;
 }
 
@@ -539,7 +547,7 @@ int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, c
     if (rc) return rc;
     char* base = (char*)dev_block;
     Params p{(const Seg*)base, (const uint2*)(base + lay.off_tiles), c.ntiles, (uint32_t*)(base + lay.off_partials),
-             (const uint32_t*)(base + lay.off_multi), c.nmulti, crc_out, tables};
+             (const uint32_t*)(base + lay.off_multi), c.nmulti, crc_out, tables, (uint32_t*)(base + lay.off_sched)};
     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms, c.ntiles);
     if (store && crc) pack_kernel<true, true><<<grid, kThreads, kSmBytes, st>>>(p);
     else if (crc) pack_kernel<false, true><<<grid, kThreads, kSmBytes, st>>>(p);
@@ -591,6 +599,7 @@ int lsio_cuda_pack_plan_create(int device, const lsio_cuda_segment* segs, size_t
     std::vector<char> host(plan->lay.upload_bytes);
     for (size_t i = 0; i < n; i++) pack_batch_append(plan->lay, host.data(), &plan->counts, segs[i], store);
     cudaError_t e = cudaMalloc(&plan->dev_block, plan->lay.total_bytes);
+    if (e == cudaSuccess) e = cudaMemset(plan->dev_block, 0, plan->lay.total_bytes);  // scheduler words start at zero
     if (e == cudaSuccess) e = cudaMemcpy(plan->dev_block, host.data(), plan->lay.upload_bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         if (plan->dev_block) cudaFree(plan->dev_block);
