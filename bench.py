@@ -256,8 +256,9 @@ def run_e2e(args, dev, paths, file_ids, expect_crc, steps, warmup, workers, o_di
 
     starts, ends = chunk_ranges()
     ud_lo = np.arange(N_CHUNKS, dtype=np.uint64)
-    u = L.IoUringCuda(workers, devices=(dev.index,), arena_bytes=8 << 30, staging_bytes=args.staging_mib << 20, o_direct=int(o_direct),
-                      min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us)
+    u = L.IoUringCuda(workers, devices=(dev.index,), arena_bytes=args.arena_gib << 30, staging_bytes=args.staging_mib << 20, o_direct=int(o_direct),
+                      min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
+                      staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots)
     try:
         for _ in range(warmup):
             e2e_pass(u, paths, file_ids, expect_crc, starts, ends, ud_lo)
@@ -435,7 +436,8 @@ def run_config(args, dev, rank):
     result = {"config": desc, "source": source, "ranges": n_ranges, "payload_bytes": payload}
     with L.IoUringCuda(args.workers, devices=(dev.index,), arena_bytes=arena, staging_bytes=args.staging_mib << 20,
                        min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, statx_via_ring=args.statx_via_ring,
-                       max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us) as u:
+                       max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
+                       staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots) as u:
         if keep_resident:  # verification pass
             _, rec = one_pass(u, True)
             assert (rec["status"] == 0).all(), rec[rec["status"] != 0][:3]
@@ -580,11 +582,14 @@ def main():
     ap.add_argument("--workers", type=int, default=0, help="io_uring worker threads per GPU (0 = 8, the README config, capped by the CPUs available per rank)")
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--staging-mib", type=int, default=1024)
+    ap.add_argument("--arena-gib", type=int, default=8)
     ap.add_argument("--min-copy-mib", type=int, default=8)
     ap.add_argument("--sq-entries", type=int, default=64)
-    ap.add_argument("--max-read-kib", type=int, default=1024, help="reads (merged or split) are cut at this size")
+    ap.add_argument("--max-read-kib", type=int, default=2048, help="reads (merged or split) are cut at this size")
     ap.add_argument("--merge-ranges", type=int, default=1)
     ap.add_argument("--poll-sleep-us", type=int, default=50, help="device-thread poll interval in microseconds (0 = spin)")
+    ap.add_argument("--staging-mode", type=int, default=1, help="1 = per-worker cache-sized pinned slots (default), 0 = one big pinned ring")
+    ap.add_argument("--host-slots", type=int, default=4, help="staging mode 1: pinned slots per worker")
     ap.add_argument("--zero-copy", type=int, default=0, help="1 = the pack kernel reads the pinned ring over PCIe (no H2D memcpy)")
     ap.add_argument("--statx-via-ring", type=int, default=0, help="1 = the reference's openat+statx SQE pair per file")
     ap.add_argument("--disk-dir", default="/tmp/lsio_bench_disk", help="secondary e2e leg on a disk-backed directory ('' disables)")

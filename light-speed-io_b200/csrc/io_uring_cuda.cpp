@@ -109,6 +109,8 @@ struct Op {
     uint32_t read = 0;  // index into req->reads
     StageEntry* entry = nullptr;
     uint32_t done = 0;  // bytes of this read that have landed (short-read continuation)
+    int slot = -1;      // staging_mode 1: the worker's host slot (extent) this read lands in
+    uint32_t ref = 0;   // index of this read in entry->reads
 };
 
 struct Batch {
@@ -121,7 +123,8 @@ struct Batch {
     cudaEvent_t copied = nullptr, done = nullptr;
     uint64_t seq_begin = 0, seq_end = 0;
     struct DescRef {
-        uint64_t seq;  // staging entry (holds the request alive until the batch retires)
+        uint64_t seq;  // staging extent (holds the request alive until the batch retires)
+        uint32_t ref;  // read inside the extent
         uint32_t seg;
     };
     std::vector<DescRef> desc;  // segment of each descriptor
@@ -142,6 +145,14 @@ struct XxhBatch {
     std::vector<Item> items;
 };
 
+// staging_mode 1: the private staging window of one io worker.
+struct WorkerSlots {
+    uint8_t* base = nullptr;  // host_slots_per_worker slots of slot_bytes, inside Group::slot_block
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<uint8_t> busy;  // 0 free, 1 read in flight, 2 H2D copy in flight (touched by the owning worker only)
+};
+
 struct Stats {
     std::atomic<uint64_t> requests{0}, ranges{0}, reads{0}, short_reads{0}, read_bytes{0}, h2d_copies{0}, h2d_bytes{0}, pack_launches{0},
         kernel_launches{0}, payload_bytes{0}, chunks_ok{0}, errors{0}, staging_stalls{0}, arena_stalls{0};
@@ -157,6 +168,9 @@ struct Group {
     uint8_t* host_ring = nullptr;
     uint8_t* dev_ring = nullptr;
     uint8_t* host_ring_dev = nullptr;  // device alias of the mapped pinned ring (zero_copy mode)
+    uint8_t* slot_block = nullptr;     // staging_mode 1: all workers' slots, one pinned allocation
+    uint64_t slot_bytes = 0;
+    std::vector<WorkerSlots> wslots;
     StagingLog log;
     cudaStream_t s_copy = nullptr, s_pack = nullptr;
     std::vector<Batch> batches;
@@ -348,7 +362,77 @@ struct Worker {
     // pulled while one waits) and plans waiting for HBM (must NOT hold back reads: it is the
     // completion and consumption of earlier reads that frees the arena).
     std::deque<Op> stalled_reads, stalled_plans;
-    Worker(Group& grp, WorkerThread<Op>& w) : g(grp), wt(w), tracker(grp.be->cfg.sq_entries) {}
+    WorkerSlots* slots = nullptr;  // staging_mode 1
+    Worker(Group& grp, WorkerThread<Op>& w) : g(grp), wt(w), tracker(grp.be->cfg.sq_entries) {
+        if (grp.be->cfg.staging_mode == 1) {
+            slots = &grp.wslots[w.id()];
+            extents.resize(slots->busy.size());
+        }
+    }
+
+    // staging_mode 1: per-slot extent bookkeeping (this worker only)
+    struct Extent {
+        StageEntry* entry = nullptr;
+        uint32_t pending = 0;  // reads submitted but not yet landed/failed
+        bool closed = false;   // no more reads will be added
+    };
+    std::vector<Extent> extents;  // one per slot
+    int cur = -1;                 // slot of the extent being filled, or -1
+
+    // The extent's reads have all landed (or failed) and nothing more will be added: copy it to the device log
+    // with ONE cudaMemcpyAsync while it is still in this core's cache, then publish it to the device thread.
+    void finish_extent(int slot) {
+        Extent& x = extents[slot];
+        StageEntry* ent = x.entry;
+        Backend* be = g.be;
+        bool any = false;
+        for (auto& r : ent->reads) any |= r.state == kStageLanded;
+        if (any) {
+            const uint64_t phys = ent->log_off % g.log.capacity();
+            cudaError_t ce = cudaMemcpyAsync(g.dev_ring + phys, slots->base + (uint64_t)slot * g.slot_bytes, ent->used, cudaMemcpyHostToDevice, slots->stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(slots->ev[slot], slots->stream);
+            if (ce != cudaSuccess) {
+                cudaGetLastError();
+                for (auto& r : ent->reads) {
+                    if (r.state != kStageLanded) continue;
+                    r.state = kStageFailed;
+                    const ReadPlan& rd = r.req->reads[r.read];
+                    for (uint32_t k = 0; k < rd.nsegs; k++) {
+                        const uint32_t range = r.req->segs[rd.first_seg + k].range;
+                        if (!r.req->ranges[range].failed.exchange(true)) send_error(be, (int)ce, 0, *r.req, (int)range, "cudaMemcpyAsync (H2D) failed");
+                    }
+                }
+                slots->busy[slot] = 0;
+            } else {
+                slots->busy[slot] = 2;
+                ent->copy_event = slots->ev[slot];
+                ent->owner = (uint32_t)wt.id();
+                be->stats.h2d_copies++;
+                be->stats.h2d_bytes += ent->used;
+            }
+        } else {
+            slots->busy[slot] = 0;
+        }
+        x.entry = nullptr;
+        ent->landed_ns = now_ns();
+        ent->state.store(kStageLanded, std::memory_order_release);
+    }
+    void close_current_extent() {
+        if (cur < 0) return;
+        const int slot = cur;
+        cur = -1;
+        extents[slot].closed = true;
+        if (extents[slot].pending == 0) finish_extent(slot);
+    }
+
+    // staging_mode 1: a free slot of this worker, recycling slots whose H2D copy has finished; -1 if none
+    int acquire_slot() {
+        for (size_t i = 0; i < slots->busy.size(); i++)
+            if (slots->busy[i] == 2 && cudaEventQuery(slots->ev[i]) != cudaErrorNotReady) slots->busy[i] = 0;
+        for (size_t i = 0; i < slots->busy.size(); i++)
+            if (slots->busy[i] == 0) return (int)i;
+        return -1;
+    }
 
     // An SQE slot, flushing the SQ first if a burst of completions filled it.
     io_uring_sqe* must_get_sqe() {
@@ -362,14 +446,19 @@ struct Worker {
 
     void push_read_sqe(size_t idx, Op& op) {
         const ReadPlan& sp = op.req->reads[op.read];
-        const uint64_t phys = op.entry->log_off % g.log.capacity() + op.done;
         io_uring_sqe* e = must_get_sqe();
-        e->opcode = IORING_OP_READ_FIXED;  // north star: READ_FIXED into the registered ring (reference: Read, sqe.rs:95)
+        e->opcode = IORING_OP_READ_FIXED;  // north star: READ_FIXED into registered pinned memory (reference: Read, sqe.rs:95)
         e->fd = op.req->fd;
-        e->addr = (uint64_t)(uintptr_t)(g.host_ring + phys);
+        if (slots) {
+            e->addr = (uint64_t)(uintptr_t)(slots->base + (uint64_t)op.slot * g.slot_bytes + op.entry->reads[op.ref].off + op.done);
+            e->buf_index = 0;
+        } else {
+            const uint64_t phys = op.entry->log_off % g.log.capacity() + op.done;
+            e->addr = (uint64_t)(uintptr_t)(g.host_ring + phys);
+            e->buf_index = (uint16_t)(phys / StagingLog::kRegBoundary);
+        }
         e->len = sp.read_len - op.done;
         e->off = sp.file_off + op.done;
-        e->buf_index = (uint16_t)(phys / StagingLog::kRegBoundary);
         e->user_data = UringUserData::pack((uint32_t)idx, IORING_OP_READ_FIXED);
     }
 
@@ -403,13 +492,44 @@ struct Worker {
             return plan_request(g, op.req, wt);
         case Op::Read: {  // get_range.rs:43-51 + sqe.rs:59-122
             const ReadPlan& sp = op.req->reads[op.read];
-            StageEntry* ent = g.log.alloc(sp.read_len, op.req, op.read);
-            if (!ent) {
-                be->stats.staging_stalls++;
-                return Start::Retry;
+            StageEntry* ent;
+            uint32_t off = 0;
+            int slot = -1;
+            if (slots) {
+                // pack this read behind the previous ones of the current extent, or open a new extent
+                if (cur >= 0 && extents[cur].entry->used + sp.read_len > g.slot_bytes) close_current_extent();
+                if (cur < 0) {
+                    const int free_slot = acquire_slot();
+                    if (free_slot < 0) {  // all of this worker's slots are still being read or copied
+                        be->stats.staging_stalls++;
+                        return Start::Retry;
+                    }
+                    StageEntry* fresh = g.log.alloc((uint32_t)g.slot_bytes);
+                    if (!fresh) {
+                        be->stats.staging_stalls++;
+                        return Start::Retry;
+                    }
+                    slots->busy[free_slot] = 1;
+                    extents[free_slot] = Extent{fresh, 0, false};
+                    cur = free_slot;
+                }
+                slot = cur;
+                ent = extents[cur].entry;
+                off = ent->used;
+                ent->used += sp.read_len;
+                extents[cur].pending++;
+            } else {
+                ent = g.log.alloc(sp.read_len);
+                if (!ent) {
+                    be->stats.staging_stalls++;
+                    return Start::Retry;
+                }
             }
+            op.ref = (uint32_t)ent->reads.size();
+            ent->reads.push_back(ReadRefT<Request>{op.req, op.read, off, kStageReading});
             op.entry = ent;
             op.done = 0;
+            op.slot = slot;
             auto idx = tracker.get_next_index();
             push_read_sqe(*idx, op);
             tracker.put(*idx, std::move(op));
@@ -420,6 +540,20 @@ struct Worker {
             break;
         }
         return Start::Finished;
+    }
+
+    // A read has landed or failed: record it in its extent and publish the extent when it is complete.
+    void read_done(Op& op, uint32_t state) {
+        StageEntry* ent = op.entry;
+        ent->reads[op.ref].state = state;
+        if (slots) {
+            Extent& x = extents[op.slot];
+            x.pending--;
+            if (x.closed && x.pending == 0) finish_extent(op.slot);
+        } else {
+            ent->landed_ns = now_ns();
+            ent->state.store(kStageLanded, std::memory_order_release);  // staging_mode 0: one read per extent
+        }
     }
 
     void finish_read_accounting(size_t idx, Op& op) {
@@ -492,7 +626,7 @@ struct Worker {
                     last = range;
                     if (!r.ranges[range].failed.exchange(true, std::memory_order_relaxed)) send_error(be, status, IORING_OP_READ_FIXED, r, (int)range, what);
                 }
-                op->entry->state.store(kStageFailed, std::memory_order_release);
+                read_done(*op, kStageFailed);
                 finish_read_accounting(ud.index_of_op, *op);
             };
             if (cqe.res < 0) {
@@ -510,8 +644,7 @@ struct Worker {
                 push_read_sqe(ud.index_of_op, *op);  // read the remainder into the same slot
                 return;
             }
-            op->entry->landed_ns = now_ns();
-            op->entry->state.store(kStageLanded, std::memory_order_release);
+            read_done(*op, kStageLanded);
             finish_read_accounting(ud.index_of_op, *op);
             return;
         }
@@ -529,8 +662,13 @@ struct Worker {
         int rc = ring.init(cfg.sq_entries, cfg.sqpoll ? 1000 : 0);
         if (rc == 0) {
             std::vector<iovec> iov;
-            for (uint64_t o = 0; o < g.log.capacity(); o += StagingLog::kRegBoundary)
-                iov.push_back(iovec{g.host_ring + o, (size_t)std::min<uint64_t>(StagingLog::kRegBoundary, g.log.capacity() - o)});
+            if (slots) {
+                cudaSetDevice(g.device);  // this worker issues its own H2D copies
+                iov.push_back(iovec{slots->base, (size_t)(g.slot_bytes * slots->busy.size())});
+            } else {
+                for (uint64_t o = 0; o < g.log.capacity(); o += StagingLog::kRegBoundary)
+                    iov.push_back(iovec{g.host_ring + o, (size_t)std::min<uint64_t>(StagingLog::kRegBoundary, g.log.capacity() - o)});
+            }
             rc = ring.register_buffers(iov.data(), (unsigned)iov.size());
         }
         if (rc != 0) {
@@ -560,9 +698,13 @@ struct Worker {
                     else started++;
                 }
                 // 3. top up the SQ with new tasks (worker.rs:65-88), two SQEs of headroom (MAX_SQ_ENTRIES_PER_ITERATION)
+                bool ran_dry = false;
                 while (stalled_reads.empty() && room()) {
                     auto t = wt.find_task();
-                    if (!t) break;
+                    if (!t) {
+                        ran_dry = true;
+                        break;
+                    }
                     Op op = std::move(*t);
                     if (!ring_ok) {
                         send_error(be, rc, 0, *op.req, -1, "io_uring unavailable");
@@ -572,6 +714,10 @@ struct Worker {
                     if (s == Start::Retry) (op.kind == Op::Read ? stalled_reads : stalled_plans).push_back(std::move(op));
                     else if (s == Start::Started) started++;
                 }
+                // nothing more to add right now: let the partly filled extent go (bounds latency, ends a workload)
+                if (slots && ran_dry && stalled_reads.empty()) close_current_extent();
+            } else if (slots) {
+                close_current_extent();
             }
             if (ring_ok && ring.unsubmitted()) ring.submit();  // one enter per batch (reference: per op, worker.rs:79)
             bool got = false;
@@ -670,12 +816,14 @@ static void retire_batch(Group& g, Batch& b) {
     // failed reads carry no descriptor but their segments still count towards their ranges
     for (uint64_t s = b.seq_begin; s < b.seq_end; s++) {
         StageEntry& e = g.log.at(s);
-        if (e.state.load(std::memory_order_relaxed) != kStageFailed) continue;
-        const ReadPlan& rd = e.req->reads[e.seg];
-        for (uint32_t k = 0; k < rd.nsegs; k++) e.req->ranges[e.req->segs[rd.first_seg + k].range].segs_left.fetch_sub(1, std::memory_order_acq_rel);
+        for (auto& ref : e.reads) {
+            if (ref.state != kStageFailed) continue;
+            const ReadPlan& rd = ref.req->reads[ref.read];
+            for (uint32_t k = 0; k < rd.nsegs; k++) ref.req->ranges[ref.req->segs[rd.first_seg + k].range].segs_left.fetch_sub(1, std::memory_order_acq_rel);
+        }
     }
     for (uint32_t i = 0; i < b.counts.nsegs; i++) {
-        const std::shared_ptr<Request>& rp = g.log.at(b.desc[i].seq).req;
+        const std::shared_ptr<Request>& rp = g.log.at(b.desc[i].seq).reads[b.desc[i].ref].req;
         SegPlan& sp = rp->segs[b.desc[i].seg];
         sp.crc = b.crc_host[i];
         RangePlan& p = rp->ranges[sp.range];
@@ -701,29 +849,40 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
     const bool store = true;
     const uint32_t flags = LSIO_CUDA_PACK_STORE | ((be->cfg.checksum & LSIO_CHECKSUM_CRC32C) ? LSIO_CUDA_PACK_CRC32C : 0);
     uint64_t landed_bytes = 0;
+    cudaEvent_t last_copy[64] = {};  // staging_mode 1: the last H2D copy of every worker in this run
     for (uint64_t s = seq_begin; s < seq_end; s++) {
         StageEntry& e = g.log.at(s);
-        if (e.state.load(std::memory_order_acquire) != kStageLanded) continue;
-        const ReadPlan& rd = e.req->reads[e.seg];
-        for (uint32_t k = 0; k < rd.nsegs; k++) {
-            const SegPlan& sp = e.req->segs[rd.first_seg + k];
-            lsio_cuda_segment seg;
-            seg.src = (uint64_t)(uintptr_t)((be->cfg.zero_copy ? g.host_ring_dev : g.dev_ring) + e.log_off % cap + sp.head);
-            seg.dst = (uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off);
-            seg.len = sp.payload_len;
-            if (!pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store)) {
-                // cannot happen: device_main sizes every run with the same tile arithmetic
-                RangePlan& p = e.req->ranges[sp.range];
-                if (!p.failed.exchange(true)) send_error(be, -EOVERFLOW, 0, *e.req, (int)sp.range, "internal: pack batch overflow");
-                p.segs_left.fetch_sub(1, std::memory_order_acq_rel);
-                continue;
+        for (uint32_t ri = 0; ri < e.reads.size(); ri++) {
+            auto& ref = e.reads[ri];
+            if (ref.state != kStageLanded) continue;
+            const ReadPlan& rd = ref.req->reads[ref.read];
+            for (uint32_t k = 0; k < rd.nsegs; k++) {
+                const SegPlan& sp = ref.req->segs[rd.first_seg + k];
+                lsio_cuda_segment seg;
+                seg.src = (uint64_t)(uintptr_t)((be->cfg.zero_copy ? g.host_ring_dev : g.dev_ring) + e.log_off % cap + ref.off + sp.head);
+                seg.dst = (uint64_t)(uintptr_t)(ref.req->buffer->buf + sp.dst_off);
+                seg.len = sp.payload_len;
+                if (!pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store)) {
+                    // cannot happen: device_main sizes every run with the same tile arithmetic
+                    RangePlan& p = ref.req->ranges[sp.range];
+                    if (!p.failed.exchange(true)) send_error(be, -EOVERFLOW, 0, *ref.req, (int)sp.range, "internal: pack batch overflow");
+                    p.segs_left.fetch_sub(1, std::memory_order_acq_rel);
+                    continue;
+                }
+                b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k});
             }
-            b->desc.push_back(Batch::DescRef{s, rd.first_seg + k});
+            landed_bytes += rd.read_len;
         }
-        landed_bytes += e.len;
+        if (e.copy_event && e.owner < 64) last_copy[e.owner] = (cudaEvent_t)e.copy_event;
+    }
+    if (landed_bytes && be->cfg.staging_mode == 1) {
+        // the extents of this run were copied by their workers: the pack stream waits for the LAST copy of
+        // every worker in the run (copies of one worker complete in order on its stream)
+        for (cudaEvent_t ev : last_copy)
+            if (ev) LSIO_CUDA_TRY(cudaStreamWaitEvent(g.s_pack, ev, 0));
     }
     if (landed_bytes) {
-        if (!be->cfg.zero_copy) {
+        if (!be->cfg.zero_copy && be->cfg.staging_mode == 0) {
             LSIO_CUDA_TRY(cudaMemcpyAsync(g.dev_ring + phys, g.host_ring + phys, bytes, cudaMemcpyHostToDevice, g.s_copy));
             LSIO_CUDA_TRY(cudaEventRecord(b->copied, g.s_copy));
             be->stats.h2d_copies++;
@@ -767,7 +926,7 @@ static void device_main(Group& g) {
                 cuda_fail(q, "pack batch", __FILE__, __LINE__);
                 fprintf(stderr, "lsio_b200: %s\n", last_error_text().c_str());
                 for (uint32_t i = 0; i < b->counts.nsegs; i++) {
-                    Request& rq = *g.log.at(b->desc[i].seq).req;
+                    Request& rq = *g.log.at(b->desc[i].seq).reads[b->desc[i].ref].req;
                     const uint32_t range = rq.segs[b->desc[i].seg].range;
                     if (!rq.ranges[range].failed.exchange(true)) send_error(be, (int)q, 0, rq, (int)range, "CUDA error in the H2D/pack stage");
                 }
@@ -813,13 +972,14 @@ static void device_main(Group& g) {
                 }
                 size_t t = 0;
                 size_t ns = 0;
-                if (st == kStageLanded) {
-                    const ReadPlan& rd = e.req->reads[e.seg];
+                for (auto& ref : e.reads) {
+                    if (ref.state != kStageLanded) continue;
+                    const ReadPlan& rd = ref.req->reads[ref.read];
                     for (uint32_t k = 0; k < rd.nsegs; k++) {
-                        const SegPlan& sp = e.req->segs[rd.first_seg + k];
-                        t += pack_tile_count((uint64_t)(uintptr_t)(e.req->buffer->buf + sp.dst_off), sp.payload_len);
+                        const SegPlan& sp = ref.req->segs[rd.first_seg + k];
+                        t += pack_tile_count((uint64_t)(uintptr_t)(ref.req->buffer->buf + sp.dst_off), sp.payload_len);
                     }
-                    ns = rd.nsegs;
+                    ns += rd.nsegs;
                     if (!oldest) oldest = e.landed_ns;
                 }
                 if (nsegs + ns > max_segs || ntiles + t > max_tiles || (bytes && bytes + e.len > max_batch_bytes)) {
@@ -842,11 +1002,13 @@ static void device_main(Group& g) {
                         Batch* b = g.last_flush_batch;  // popped from the free list by flush_run, never reached `inflight`
                         for (uint64_t q = g.copy_seq; q < s; q++) {
                             StageEntry& e = g.log.at(q);
-                            if (e.state.load(std::memory_order_acquire) != kStageLanded) continue;
-                            const ReadPlan& rd = e.req->reads[e.seg];
-                            for (uint32_t k = 0; k < rd.nsegs; k++) {
-                                const uint32_t range = e.req->segs[rd.first_seg + k].range;
-                                if (!e.req->ranges[range].failed.exchange(true)) send_error(be, rc, 0, *e.req, (int)range, "CUDA error while enqueueing the H2D/pack stage");
+                            for (auto& ref : e.reads) {
+                                if (ref.state != kStageLanded) continue;
+                                const ReadPlan& rd = ref.req->reads[ref.read];
+                                for (uint32_t k = 0; k < rd.nsegs; k++) {
+                                    const uint32_t range = ref.req->segs[rd.first_seg + k].range;
+                                    if (!ref.req->ranges[range].failed.exchange(true)) send_error(be, rc, 0, *ref.req, (int)range, "CUDA error while enqueueing the H2D/pack stage");
+                                }
                             }
                         }
                         cudaStreamSynchronize(g.s_copy);
@@ -919,6 +1081,14 @@ static void free_group_cuda(Group& g) {
     g.xxh_batches.clear();
     if (g.s_copy) cudaStreamDestroy(g.s_copy);
     if (g.s_pack) cudaStreamDestroy(g.s_pack);
+    for (WorkerSlots& ws : g.wslots) {
+        for (auto ev : ws.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (ws.stream) cudaStreamDestroy(ws.stream);
+    }
+    g.wslots.clear();
+    if (g.slot_block) cudaFreeHost(g.slot_block);
+    g.slot_block = nullptr;
     if (g.host_ring) cudaFreeHost(g.host_ring);
     if (g.dev_ring) cudaFree(g.dev_ring);
     g.s_copy = g.s_pack = nullptr;
@@ -933,10 +1103,27 @@ static int init_group(Group& g) {
     if (rc) return rc;
     if (cfg.pin_threads) g.cpus = numa_cpus_of_device(g.device);
     const uint64_t ring_bytes = cfg.staging_bytes / 4096 * 4096;
-    // pinned (page-locked, DMA-able) and later registered with every worker's io_uring
-    LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.host_ring, ring_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
-    LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&g.host_ring_dev, g.host_ring, 0));
-    if (!cfg.zero_copy) LSIO_CUDA_TRY(cudaMalloc((void**)&g.dev_ring, ring_bytes));
+    if (cfg.staging_mode == 1) {
+        // per-worker cache-sized windows of pinned slots; the ordered log lives on the device only
+        g.slot_bytes = (cfg.max_read_bytes + 4095) / 4096 * 4096;
+        const uint64_t per_worker = g.slot_bytes * cfg.host_slots_per_worker;
+        LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.slot_block, per_worker * cfg.n_worker_threads, cudaHostAllocPortable));
+        g.wslots.resize(cfg.n_worker_threads);
+        for (uint32_t w = 0; w < cfg.n_worker_threads; w++) {
+            WorkerSlots& ws = g.wslots[w];
+            ws.base = g.slot_block + per_worker * w;
+            LSIO_CUDA_TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+            ws.ev.resize(cfg.host_slots_per_worker);
+            ws.busy.assign(cfg.host_slots_per_worker, 0);
+            for (auto& ev : ws.ev) LSIO_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        }
+        LSIO_CUDA_TRY(cudaMalloc((void**)&g.dev_ring, ring_bytes));
+    } else {
+        // pinned (page-locked, DMA-able) and later registered with every worker's io_uring
+        LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.host_ring, ring_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+        LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&g.host_ring_dev, g.host_ring, 0));
+        if (!cfg.zero_copy) LSIO_CUDA_TRY(cudaMalloc((void**)&g.dev_ring, ring_bytes));
+    }
     g.log.init(ring_bytes, 1 << 16);
     uint8_t* arena_base = nullptr;
     LSIO_CUDA_TRY(cudaMalloc((void**)&arena_base, cfg.arena_bytes));
@@ -1003,13 +1190,15 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     // Reads (merged or split) are cut at 1 MiB: measured on this pool, tmpfs-sourced C2 runs at 33 GiB/s with
     // reads <= 1 MiB, 32 at 2 MiB and 26 at >= 4 MiB -- the per-core L2 is 2 MiB and the H2D DMA is served from
     // cache while the freshly copied slot is still resident (the host is memory-bandwidth bound).
-    cfg->max_read_bytes = 1ull << 20;
+    cfg->max_read_bytes = 2ull << 20;  // staging_mode 1: also the slot size; 2 MiB x 4 slots per worker measured best (42 GiB/s)
     cfg->min_copy_bytes = 8ull << 20;
     cfg->flush_us = 200;
     cfg->merge_ranges = 1;
     cfg->merge_gap_bytes = 0;
     cfg->statx_via_ring = 0;
     cfg->zero_copy = 0;
+    cfg->staging_mode = 1;
+    cfg->host_slots_per_worker = 4;
     cfg->poll_sleep_us = 50;  // measured: same throughput as spinning (33-34 GiB/s C2, 27.7 vs 28.1 C3) without burning a core per GPU
 }
 
@@ -1020,6 +1209,11 @@ int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uri
     if (cfg.staging_bytes >= (4ull << 20)) {
         cfg.max_read_bytes = std::min<uint64_t>(cfg.max_read_bytes, cfg.staging_bytes / 4 / kAlign * kAlign);
         cfg.min_copy_bytes = std::min<uint64_t>(cfg.min_copy_bytes, cfg.staging_bytes / 4);
+    }
+    if (cfg.zero_copy) cfg.staging_mode = 0;  // the kernel needs the whole pinned ring mapped
+    if (cfg.staging_mode == 1 && (cfg.host_slots_per_worker == 0 || cfg.host_slots_per_worker > 256 || cfg.n_worker_threads > 64)) {
+        set_error("staging_mode 1 needs 1..256 host_slots_per_worker and at most 64 worker threads per device");
+        return -EINVAL;
     }
     if (cfg.n_worker_threads == 0 || cfg.n_devices == 0 || cfg.n_devices > LSIO_MAX_DEVICES || cfg.sq_entries < 4 ||
         (cfg.sq_entries & (cfg.sq_entries - 1)) || cfg.staging_bytes < (4ull << 20) || cfg.arena_bytes < (1ull << 20) || cfg.max_read_bytes < kAlign ||

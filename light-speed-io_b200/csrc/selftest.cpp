@@ -120,30 +120,35 @@ extern "C" int lsio_uring_cuda_selftest(int which) {
         log.init(cap, 8);
         auto req = std::make_shared<Request>();
         std::vector<StageEntry*> e;
-        for (int i = 0; i < 3; i++) e.push_back(log.alloc(256 << 10, req, (uint32_t)i));
+        auto alloc = [&](StagingLog& l, uint32_t len, uint32_t idx) {
+            StageEntry* x = l.alloc(len);
+            if (x) x->reads.push_back(ReadRefT<DummyRequest>{req, idx, 0, kStageReading});
+            return x;
+        };
+        for (int i = 0; i < 3; i++) e.push_back(alloc(log, 256 << 10, (uint32_t)i));
         CHECK(1, e[0] && e[1] && e[2] && e[0]->log_off == 0 && e[1]->log_off == (256 << 10) && e[2]->log_off == (512 << 10));
-        CHECK(2, log.alloc(512 << 10, req, 3) == nullptr);  // only 256 KiB left before the wrap and nothing is free yet
-        StageEntry* last = log.alloc(256 << 10, req, 3);
+        CHECK(2, alloc(log, 512 << 10, 3) == nullptr);  // only 256 KiB left before the wrap and nothing is free yet
+        StageEntry* last = alloc(log, 256 << 10, 3);
         CHECK(3, last && last->log_off == (768 << 10));
-        CHECK(4, log.alloc(512, req, 4) == nullptr);  // ring full
+        CHECK(4, alloc(log, 512, 4) == nullptr);  // ring full
         CHECK(5, log.alloc_seq() == 4 && log.retire_seq() == 0 && req.use_count() == 5);
         log.retire_through(2);  // the device thread retires in order
         CHECK(6, req.use_count() == 3);
-        StageEntry* w = log.alloc(384 << 10, req, 5);
+        StageEntry* w = alloc(log, 384 << 10, 5);
         CHECK(7, w && w->log_off == cap && w->log_off % cap == 0);  // wrapped: logical offsets keep growing
-        CHECK(8, log.alloc(256 << 10, req, 6) == nullptr);  // [384K, 512K) is free but too small
+        CHECK(8, alloc(log, 256 << 10, 6) == nullptr);  // [384K, 512K) is free but too small
         log.retire_through(4);
-        StageEntry* x = log.alloc(512 << 10, req, 7);
+        StageEntry* x = alloc(log, 512 << 10, 7);
         CHECK(9, x && x->log_off == cap + (384 << 10));
         // an allocation never straddles the wrap: it skips to the start of the ring
         log.retire_through(6);
-        StageEntry* y = log.alloc(256 << 10, req, 8);
+        StageEntry* y = alloc(log, 256 << 10, 8);
         CHECK(10, y && y->log_off % cap == 0 && y->log_off == 2 * cap);
         // the entry table bounds the number of live slots too
         log.retire_through(7);
         StagingLog small;
         small.init(1 << 20, 2);
-        CHECK(11, small.alloc(512, req, 0) && small.alloc(512, req, 1) && small.alloc(512, req, 2) == nullptr);
+        CHECK(11, alloc(small, 512, 0) && alloc(small, 512, 1) && alloc(small, 512, 2) == nullptr);
         return 0;
     }
     case 5: {

@@ -21,15 +21,29 @@ namespace lsio {
 
 enum : uint32_t { kStageReading = 0, kStageLanded = 1, kStageFailed = 2 };
 
-// R = the request type an entry keeps alive (the backend's Request; a dummy in the self test).
+// One read that lands inside an extent.  R = the request type it keeps alive (the backend's Request;
+// a dummy in the self test).
+template <class R>
+struct ReadRefT {
+    std::shared_ptr<R> req;
+    uint32_t read = 0;   // index into req->reads
+    uint32_t off = 0;    // byte offset of the read's buffer inside the extent (512-aligned)
+    uint32_t state = kStageReading;  // written by the owning io worker before the extent is published
+};
+
+// A staging EXTENT: one contiguous reservation of the (device) log carrying one or more reads.
+// staging_mode 0: one read per extent, host memory at the same ring offset.  staging_mode 1: an io worker
+// packs consecutive reads into one of its cache-sized pinned slots and copies the extent with one H2D.
 template <class R>
 struct StageEntryT {
     uint64_t log_off = 0;  // monotonically increasing logical byte offset; phys = log_off % capacity
-    uint32_t len = 0;      // bytes reserved (padded read length)
-    std::atomic<uint32_t> state{kStageReading};
-    std::shared_ptr<R> req;
-    uint32_t seg = 0;      // index into req->reads
+    uint32_t len = 0;      // bytes reserved
+    std::atomic<uint32_t> state{kStageReading};  // kStageLanded once every read has landed/failed (and its copy is enqueued)
+    std::vector<ReadRefT<R>> reads;              // owned by the allocating worker until `state` is published
     uint64_t landed_ns = 0;
+    void* copy_event = nullptr;  // staging_mode 1: the cudaEvent_t recorded after this extent's H2D copy
+    uint32_t owner = 0;          // staging_mode 1: the io worker (copy stream) that issued it
+    uint32_t used = 0;           // staging_mode 1: bytes of the extent actually filled (= copied)
 };
 
 template <class R>
@@ -45,7 +59,7 @@ class StagingLogT {
     uint64_t capacity() const { return cap_; }
 
     // Reserve `len` bytes (multiple of 512).  Thread-safe.  nullptr = ring or entry table full.
-    StageEntry* alloc(uint32_t len, std::shared_ptr<R> req, uint32_t seg) {
+    StageEntry* alloc(uint32_t len) {
         std::lock_guard<std::mutex> lk(mu_);
         if (alloc_seq_ - retire_seq_.load(std::memory_order_acquire) >= entries_.size()) return nullptr;
         uint64_t off = alloc_off_;
@@ -57,8 +71,9 @@ class StagingLogT {
         e.log_off = off;
         e.len = len;
         e.state.store(kStageReading, std::memory_order_relaxed);
-        e.req = std::move(req);
-        e.seg = seg;
+        e.reads.clear();
+        e.used = 0;
+        e.copy_event = nullptr;
         alloc_off_ = off + len;
         alloc_seq_pub_.store(++alloc_seq_, std::memory_order_release);
         return &e;
@@ -75,7 +90,7 @@ class StagingLogT {
         for (; s < seq_end; s++) {
             StageEntry& e = at(s);
             free_to = e.log_off + e.len;
-            e.req.reset();
+            e.reads.clear();  // drops the requests' references
         }
         free_off_.store(free_to, std::memory_order_release);
         retire_seq_.store(seq_end, std::memory_order_release);

@@ -68,8 +68,9 @@ def test_unaligned_negative_eof_and_split_ranges(lsio, oracle, cuda_dev, data_di
         s = int(rng.integers(0, size - n))
         ranges.append((s, s + n))
     # max_read_bytes = 128 KiB: long ranges are read as several segments whose CRCs are combined
-    for merge in (0, 1):
-        with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, max_read_bytes=128 << 10, merge_ranges=merge) as u:
+    for merge, staging_mode in ((0, 1), (1, 1), (1, 0)):  # staging_mode 1: per-worker slot extents; 0: one big pinned ring
+        with lsio.IoUringCuda(3, arena_bytes=256 << 20, staging_bytes=32 << 20, max_read_bytes=128 << 10, merge_ranges=merge,
+                              staging_mode=staging_mode, host_slots_per_worker=3) as u:
             u.get_ranges(fn, ranges, range(len(ranges)))
             items = _drain(u.completion(), len(ranges))
             assert sorted(c.user_data for c in items) == list(range(len(ranges)))  # exactly one chunk per range
@@ -80,8 +81,8 @@ def test_unaligned_negative_eof_and_split_ranges(lsio, oracle, cuda_dev, data_di
                 assert st["reads"] > len(ranges)  # one read per range, long ones split (reference: one read per range)
 
 
-@pytest.mark.parametrize("pack_align", [1, 16, 512])
-def test_many_files_many_ops_per_thread(lsio, oracle, cuda_dev, data_dir, pack_align):
+@pytest.mark.parametrize("pack_align,staging_mode", [(1, 1), (16, 1), (512, 1), (1, 0)])
+def test_many_files_many_ops_per_thread(lsio, oracle, cuda_dev, data_dir, pack_align, staging_mode):
     """Multiple files in flight, > 64 ops per worker, back-pressure on a tiny completion channel."""
     n_files, size = 24, 300_000 + 77
     fns = []
@@ -92,7 +93,8 @@ def test_many_files_many_ops_per_thread(lsio, oracle, cuda_dev, data_dir, pack_a
     rng = np.random.default_rng(4)
     per_file = 40
     all_ranges = {}
-    with lsio.IoUringCuda(2, arena_bytes=512 << 20, staging_bytes=16 << 20, completion_bound=8, pack_align=pack_align, sq_entries=16) as u:
+    with lsio.IoUringCuda(2, arena_bytes=512 << 20, staging_bytes=16 << 20, completion_bound=8, pack_align=pack_align, sq_entries=16,
+                          staging_mode=staging_mode, host_slots_per_worker=2) as u:
         for i, fn in enumerate(fns):
             rs = []
             for k in range(per_file):
@@ -398,7 +400,7 @@ def test_range_larger_than_two_gib(lsio, oracle, cuda_dev):
             tail = bytes(n % (1 << 20)) + b"\x5a" * 100
             want = oracle.crc32c_combine(want, oracle.crc32c(tail), len(tail))
             assert c.crc32c == want
-            assert u.stats()["reads"] >= size // (1 << 20)
+            assert u.stats()["reads"] >= size // (2 << 20)  # split at max_read_bytes (2 MiB)
     finally:
         if os.path.exists(fn):
             os.unlink(fn)
