@@ -258,7 +258,7 @@ def run_e2e(args, dev, paths, file_ids, expect_crc, steps, warmup, workers, o_di
     ud_lo = np.arange(N_CHUNKS, dtype=np.uint64)
     u = L.IoUringCuda(workers, devices=(dev.index,), arena_bytes=args.arena_gib << 30, staging_bytes=args.staging_mib << 20, o_direct=int(o_direct),
                       min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
-                      staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots)
+                      staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib)
     try:
         for _ in range(warmup):
             e2e_pass(u, paths, file_ids, expect_crc, starts, ends, ud_lo)
@@ -437,7 +437,7 @@ def run_config(args, dev, rank):
     with L.IoUringCuda(args.workers, devices=(dev.index,), arena_bytes=arena, staging_bytes=args.staging_mib << 20,
                        min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, statx_via_ring=args.statx_via_ring,
                        max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
-                       staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots) as u:
+                       staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib) as u:
         if keep_resident:  # verification pass
             _, rec = one_pass(u, True)
             assert (rec["status"] == 0).all(), rec[rec["status"] != 0][:3]
@@ -585,11 +585,13 @@ def main():
     ap.add_argument("--arena-gib", type=int, default=8)
     ap.add_argument("--min-copy-mib", type=int, default=8)
     ap.add_argument("--sq-entries", type=int, default=64)
-    ap.add_argument("--max-read-kib", type=int, default=2048, help="reads (merged or split) are cut at this size")
+    ap.add_argument("--max-read-kib", type=int, default=512, help="reads (merged or split) are cut at this size")
     ap.add_argument("--merge-ranges", type=int, default=1)
     ap.add_argument("--poll-sleep-us", type=int, default=50, help="device-thread poll interval in microseconds (0 = spin)")
     ap.add_argument("--staging-mode", type=int, default=1, help="1 = per-worker cache-sized pinned slots (default), 0 = one big pinned ring")
     ap.add_argument("--host-slots", type=int, default=4, help="staging mode 1: pinned slots per worker")
+    ap.add_argument("--host-slot-kib", type=int, default=2048, help="staging mode 1: slot (extent, H2D copy) size")
+    ap.add_argument("--e2e-dir", default=None, help="--e2e-only: run the pass over files in this directory instead")
     ap.add_argument("--zero-copy", type=int, default=0, help="1 = the pack kernel reads the pinned ring over PCIe (no H2D memcpy)")
     ap.add_argument("--statx-via-ring", type=int, default=0, help="1 = the reference's openat+statx SQE pair per file")
     ap.add_argument("--disk-dir", default="/tmp/lsio_bench_disk", help="secondary e2e leg on a disk-backed directory ('' disables)")
@@ -656,6 +658,9 @@ def main():
         return 0
 
     if args.e2e_only:
+        if args.e2e_dir:
+            my_paths, expect_crc = make_files(args.e2e_dir, args.files, local)
+            my_ids = list(range(args.files))
         e2e = run_e2e(args, dev, my_paths, my_ids, expect_crc, args.steps, args.warmup, args.workers)
         print(json.dumps({"e2e_only": True, "gib_s": e2e["bytes"] / sum(e2e["secs"]) / GIB, "bad": e2e["bad"], "workers": args.workers,
                           "staging_mib": args.staging_mib, "min_copy_mib": args.min_copy_mib, "sq_entries": args.sq_entries,
@@ -671,7 +676,11 @@ def main():
     ceil = {}
     if rank == 0:
         ceil["pcie_h2d_gib_s"] = pcie_h2d_ceiling(dev)
-        ceil["source_read_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 1 << 20, min(os.cpu_count() or 8, max(8, args.workers) * n_gpus), 32, True)
+        nthr = min(os.cpu_count() or 8, max(8, args.workers) * n_gpus)
+        # raw READ_FIXED reads, no GPU work: into a large buffer (DRAM-bound destination) and into small per-thread
+        # buffers (cache-resident destination, what staging_mode 1 does); the ceiling is the better of the two
+        ceil["source_read_big_buffers_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 1 << 20, nthr, 32, True)
+        ceil["source_read_gib_s"] = max(ceil["source_read_big_buffers_gib_s"], cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 512 << 10, nthr, 4, True))
     full = None
     if not args.no_verify:
         mism, landed = verify_full_landing(dev, my_paths, my_ids, args.workers, args.staging_mib)
@@ -685,7 +694,7 @@ def main():
             if free > args.disk_files * FILE_SIZE + (4 << 30):
                 dpaths, dcrc = make_files(args.disk_dir, args.disk_files, local)
                 dres = run_e2e(args, dev, dpaths, list(range(args.disk_files)), dcrc, 2, 1, args.workers)
-                dceil = cuda_ops.probe_read_ceiling(dpaths, 1 << 20, 8, 32, True)
+                dceil = max(cuda_ops.probe_read_ceiling(dpaths, 1 << 20, 8, 32, True), cuda_ops.probe_read_ceiling(dpaths, 256 << 10, 8, 32, True))
                 disk = {"value": dres["bytes"] / sum(dres["secs"]) / GIB, "unit": "GiB/s", "files": args.disk_files, "bad": dres["bad"],
                         "read_ceiling_gib_s": dceil, "frac_of_ceiling": dres["bytes"] / sum(dres["secs"]) / GIB / dceil, "dir": args.disk_dir}
         except Exception as ex:  # the disk leg is informative only

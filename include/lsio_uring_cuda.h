@@ -60,15 +60,16 @@ typedef struct lsio_uring_cuda_config {
                                    n > 0 = sleep n microseconds between polls (for boxes with few CPUs per GPU) */
     uint32_t zero_copy;         /* 1 = no H2D memcpy: the pack kernel reads the mapped pinned ring over PCIe and writes
                                    HBM once (fuses H2D + strip + checksum); 0 (default) = cudaMemcpyAsync + device ring */
-    uint32_t staging_mode;      /* 1 (default) = every io worker owns `host_slots_per_worker` pinned slots of max_read_bytes
-                                   (a window that stays in its core's cache) and copies each landed read to the
+    uint32_t staging_mode;      /* 1 (default) = every io worker owns `host_slots_per_worker` pinned slots
+                                   (a window that stays in its core's cache; slots are `host_slot_kib` each) and copies each landed read to the
                                    device log itself on a private stream: the host is DRAM-bandwidth bound and a
                                    cache-resident window avoids the write-allocate/write-back traffic of a big ring
                                    (measured: tmpfs reads 69 GiB/s into <= 2 MiB/thread buffers vs 40 into a big one).
                                    0 = one `staging_bytes` pinned ring mirrored on the device, copied in coalesced
                                    runs by the device thread (needed for zero_copy) */
     uint32_t host_slots_per_worker; /* staging_mode 1: slots per worker (default 4) */
-    uint32_t reserved4;
+    uint32_t host_slot_kib;     /* staging_mode 1: slot (extent) size in KiB, >= max_read_bytes (default 2048): the
+                                   granularity of the H2D copies; several reads of max_read_bytes can be in flight in one */
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {

@@ -128,6 +128,7 @@ struct Batch {
         uint32_t seg;
     };
     std::vector<DescRef> desc;  // segment of each descriptor
+    std::vector<cudaEvent_t> copy_events;
 };
 
 // Second stage when LSIO_CHECKSUM_XXH64 is requested: ranges whose bytes are packed wait here for
@@ -849,7 +850,8 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
     const bool store = true;
     const uint32_t flags = LSIO_CUDA_PACK_STORE | ((be->cfg.checksum & LSIO_CHECKSUM_CRC32C) ? LSIO_CUDA_PACK_CRC32C : 0);
     uint64_t landed_bytes = 0;
-    cudaEvent_t last_copy[64] = {};  // staging_mode 1: the last H2D copy of every worker in this run
+    std::vector<cudaEvent_t>& copy_events = b->copy_events;  // staging_mode 1: the H2D copy of every extent in this run
+    copy_events.clear();
     for (uint64_t s = seq_begin; s < seq_end; s++) {
         StageEntry& e = g.log.at(s);
         for (uint32_t ri = 0; ri < e.reads.size(); ri++) {
@@ -873,13 +875,14 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
             }
             landed_bytes += rd.read_len;
         }
-        if (e.copy_event && e.owner < 64) last_copy[e.owner] = (cudaEvent_t)e.copy_event;
+        if (e.copy_event) copy_events.push_back((cudaEvent_t)e.copy_event);
     }
     if (landed_bytes && be->cfg.staging_mode == 1) {
-        // the extents of this run were copied by their workers: the pack stream waits for the LAST copy of
-        // every worker in the run (copies of one worker complete in order on its stream)
-        for (cudaEvent_t ev : last_copy)
-            if (ev) LSIO_CUDA_TRY(cudaStreamWaitEvent(g.s_pack, ev, 0));
+        // The extents of this run were copied by their workers: the pack stream waits for EVERY one of them.
+        // (Not just the last extent per worker in log order: with asynchronous reads an extent allocated
+        // earlier can complete -- and be copied -- after a later one of the same worker.  A slot's event is
+        // re-recorded only after its previous copy finished, so a wait never under-covers.)
+        for (cudaEvent_t ev : copy_events) LSIO_CUDA_TRY(cudaStreamWaitEvent(g.s_pack, ev, 0));
     }
     if (landed_bytes) {
         if (!be->cfg.zero_copy && be->cfg.staging_mode == 0) {
@@ -1105,7 +1108,7 @@ static int init_group(Group& g) {
     const uint64_t ring_bytes = cfg.staging_bytes / 4096 * 4096;
     if (cfg.staging_mode == 1) {
         // per-worker cache-sized windows of pinned slots; the ordered log lives on the device only
-        g.slot_bytes = (cfg.max_read_bytes + 4095) / 4096 * 4096;
+        g.slot_bytes = std::max<uint64_t>((uint64_t)cfg.host_slot_kib << 10, (cfg.max_read_bytes + 4095) / 4096 * 4096);
         const uint64_t per_worker = g.slot_bytes * cfg.host_slots_per_worker;
         LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.slot_block, per_worker * cfg.n_worker_threads, cudaHostAllocPortable));
         g.wslots.resize(cfg.n_worker_threads);
@@ -1187,10 +1190,11 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->o_direct = 1;             // sqe.rs:25
     cfg->staging_bytes = 1ull << 30;
     cfg->arena_bytes = 8ull << 30;
-    // Reads (merged or split) are cut at 1 MiB: measured on this pool, tmpfs-sourced C2 runs at 33 GiB/s with
-    // reads <= 1 MiB, 32 at 2 MiB and 26 at >= 4 MiB -- the per-core L2 is 2 MiB and the H2D DMA is served from
-    // cache while the freshly copied slot is still resident (the host is memory-bandwidth bound).
-    cfg->max_read_bytes = 2ull << 20;  // staging_mode 1: also the slot size; 2 MiB x 4 slots per worker measured best (42 GiB/s)
+    // Reads (merged or split) are cut at 512 KiB and packed into 2 MiB extents (host_slot_kib).  Measured on this
+    // pool: tmpfs-sourced C2 runs at 41.8 GiB/s for reads of 512 KiB..2 MiB, while the (virtio) disk gives 6.1 GiB/s
+    // with 256-512 KiB reads and 3.8 with 2 MiB ones (more, smaller requests in flight).  In staging_mode 0 reads of
+    // <= 1 MiB matter for another reason: the slot is handed to the H2D DMA while still in the 2 MiB per-core L2.
+    cfg->max_read_bytes = 512ull << 10;
     cfg->min_copy_bytes = 8ull << 20;
     cfg->flush_us = 200;
     cfg->merge_ranges = 1;
@@ -1199,6 +1203,7 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->zero_copy = 0;
     cfg->staging_mode = 1;
     cfg->host_slots_per_worker = 4;
+    cfg->host_slot_kib = 2048;
     cfg->poll_sleep_us = 50;  // measured: same throughput as spinning (33-34 GiB/s C2, 27.7 vs 28.1 C3) without burning a core per GPU
 }
 
