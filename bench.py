@@ -672,8 +672,9 @@ def main():
         e2e = run_e2e(args, dev, my_paths, my_ids, expect_crc, args.steps, args.warmup, args.workers)
     clk = clocks.summary()
 
-    # ceilings of the I/O roofline, measured in the same run (rank 0's view)
+    # ceilings of the I/O roofline, measured in the same run (rank 0's view) while every other rank is idle
     ceil = {}
+    barrier()
     if rank == 0:
         ceil["pcie_h2d_gib_s"] = pcie_h2d_ceiling(dev)
         nthr = min(os.cpu_count() or 8, max(8, args.workers) * n_gpus)
@@ -681,6 +682,7 @@ def main():
         # buffers (cache-resident destination, what staging_mode 1 does); the ceiling is the better of the two
         ceil["source_read_big_buffers_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 1 << 20, nthr, 32, True)
         ceil["source_read_gib_s"] = max(ceil["source_read_big_buffers_gib_s"], cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 512 << 10, nthr, 4, True))
+    barrier()
     full = None
     if not args.no_verify:
         mism, landed = verify_full_landing(dev, my_paths, my_ids, args.workers, args.staging_mib)
