@@ -5,13 +5,16 @@
 // Per device group (one group per GPU, threads pinned to that GPU's NUMA node):
 //
 //   caller ── get_ranges ─▶ injector ─▶ k io workers (work-stealing pool, private io_uring each)
-//        openat(O_DIRECT)+statx ─▶ plan: resolve ranges (sqe.rs:64-83), lay the request out in one
-//        HBM buffer (arena), split into reads ─▶ READ_FIXED into the pinned staging LOG
-//                                                         │ landed (CQE, short reads retried)
-//                                                         ▼
-//   device thread:  coalesce contiguous landed slots ─▶ ONE cudaMemcpyAsync H2D (copy stream)
-//        ─▶ pack_strip_crc32c over the batch (pack stream, after the copy's event)
-//        ─▶ event ─▶ one Chunk{device view, user_data, crc32c} per range on the bounded channel
+//        openat(O_DIRECT) [+statx] ─▶ plan: resolve ranges (sqe.rs:64-83), lay the request out in one HBM
+//        buffer (arena), merge/split into reads ─▶ READ_FIXED into the worker's own pinned slots, packed
+//        back to back as 2 MiB EXTENTS that stay in the core's cache
+//                                   │ all reads of an extent landed (CQEs, short reads retried)
+//                                   ▼
+//        the worker copies the extent with ONE cudaMemcpyAsync on its own stream into the device log
+//   device thread:  batch published extents in log order ─▶ wait on their copy events
+//        ─▶ pack_strip_crc32c over the batch (pack stream) ─▶ event
+//        ─▶ one Chunk{device view, user_data, crc32c} per range on the bounded channel
+//   (staging_mode 0: one big pinned ring instead; the device thread copies coalesced runs of landed reads)
 //
 // What is kept from the reference: submit/complete semantics, one chunk per range, unordered
 // completions, in-band errors (one per failed CQE: operation.rs:82-100), user_data packing,
