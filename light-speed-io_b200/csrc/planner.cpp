@@ -1,0 +1,149 @@
+// planner.cpp -- completion items and the request planner: the reference's range arithmetic
+// (crates/lsio_uring/src/sqe.rs:59-122) and fan-out (get_ranges.rs:39-45) re-stated for a whole request,
+// plus what the reference only plans: merging adjacent ranges and splitting long reads.
+#include "backend.hpp"
+
+namespace lsio {
+
+// ---- completion items ----------------------------------------------------------------------
+void send_output(Backend* be, lsio_output& o) {
+    if (o.status != 0) be->stats.errors++;
+    else be->stats.chunks_ok++;
+    be->out->send(o);
+}
+
+// operation.rs:82-100 maybe_send_error: one Err per failed CQE, with context.
+void send_error(Backend* be, int status, uint8_t opcode, const Request& r, int range, const char* what) {
+    lsio_output o;
+    memset(&o, 0, sizeof o);
+    o.status = status;
+    o.opcode = opcode;
+    o.device = r.grp ? r.grp->device : -1;
+    if (range >= 0) {
+        o.chunk.user_data = r.user_data[range];
+        snprintf(o.context, sizeof o.context, "%s: %s (io_uring opcode %u, result %d). path=%s range=%lld..%lld user_data=%llu", what,
+                 status < 0 ? strerror(-status) : "CUDA error", opcode, status, r.path.c_str(), (long long)r.starts[range], (long long)r.ends[range],
+                 (unsigned long long)r.user_data[range]);
+    } else {
+        snprintf(o.context, sizeof o.context, "%s: %s (io_uring opcode %u, result %d). path=%s n_ranges=%zu", what,
+                 status < 0 ? strerror(-status) : "CUDA error", opcode, status, r.path.c_str(), r.starts.size());
+    }
+    send_output(be, o);
+}
+
+// ---- planning: sqe.rs:59-122 re-stated for a whole request -----------------------------------
+Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op>& wt) {
+    Request& r = *rp;
+    Backend* be = g.be;
+    const lsio_uring_cuda_config& cfg = be->cfg;
+    const int64_t filesize = (int64_t)r.stx.stx_size;
+    const size_t n = r.starts.size();
+    if (!r.planned) {
+        r.ranges.reset(new RangePlan[n ? n : 1]);
+        uint64_t dst = 0;
+        const uint64_t pa = cfg.pack_align ? cfg.pack_align : 1;
+        for (size_t i = 0; i < n; i++) {
+            RangePlan& p = r.ranges[i];
+            p.user_data = r.user_data[i];
+            const int64_t s = r.starts[i], e = r.ends[i];
+            const int64_t start_off = s >= 0 ? s : filesize + s;  // sqe.rs:64-70
+            const int64_t end_off = e >= 0 ? e : filesize + e + 1;  // sqe.rs:73-80
+            // The reference asserts (panics) on these; here they are in-band errors (Appendix A).
+            if (start_off < 0 || end_off < 0 || end_off <= start_off || end_off > filesize) {
+                send_error(be, -EINVAL, 0, r, (int)i, "invalid byte range for this file");
+                continue;
+            }
+            p.valid = true;
+            p.start_off = start_off;
+            p.end_off = end_off;
+            p.len = (uint64_t)(end_off - start_off);
+            dst = (dst + pa - 1) / pa * pa;
+            p.dst_off = dst;
+            dst += p.len;
+        }
+        r.total_bytes = dst;
+        r.planned = true;
+        be->stats.ranges += n;
+    }
+    if (r.total_bytes == 0) {  // nothing to read
+        close(r.fd);
+        r.fd = -1;
+        return Start::Finished;
+    }
+    uint8_t* block = g.arena->alloc(r.total_bytes + 16);
+    if (!block) {
+        if (r.total_bytes + 16 > g.arena->capacity()) {
+            for (size_t i = 0; i < n; i++)
+                if (r.ranges[i].valid) send_error(be, -ENOMEM, 0, r, (int)i, "request larger than the HBM arena (arena_bytes)");
+            close(r.fd);
+            r.fd = -1;
+            return Start::Finished;
+        }
+        be->stats.arena_stalls++;
+        return Start::Retry;  // wait for the consumer to drop chunks
+    }
+    auto buf = std::make_shared<InnerBuffer>();
+    buf->buf = block;
+    buf->size = r.total_bytes;
+    buf->align = kAlign;
+    buf->kind = MemKind::Device;
+    buf->device = g.device;
+    buf->release = [arena = g.arena, block](InnerBuffer&) { arena->release(block); };
+    r.buffer = std::move(buf);
+
+    // Read plan: sort the ranges' padded spans, merge spans that touch / overlap / sit within
+    // merge_gap_bytes of each other into runs, cut every run into reads of at most max_read_bytes
+    // (reference: one read per range, panics above 2 GiB, get_range.rs:23-30).
+    const uint64_t max_read = std::max<uint64_t>(kAlign, cfg.max_read_bytes / kAlign * kAlign);
+    std::vector<uint32_t> order;
+    for (size_t i = 0; i < n; i++)
+        if (r.ranges[i].valid) order.push_back((uint32_t)i);
+    auto span_lo = [&](uint32_t i) { return (uint64_t)r.ranges[i].start_off / kAlign * kAlign; };                   // sqe.rs:83
+    auto span_hi = [&](uint32_t i) { return ((uint64_t)r.ranges[i].end_off + kAlign - 1) / kAlign * kAlign; };     // padded length
+    if (cfg.merge_ranges) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return span_lo(a) < span_lo(b); });
+    for (size_t k = 0; k < order.size();) {
+        uint64_t run_lo = span_lo(order[k]), run_hi = span_hi(order[k]);
+        size_t k_end = k + 1;
+        if (cfg.merge_ranges)
+            while (k_end < order.size() && k_end - k < 1024 && span_lo(order[k_end]) <= run_hi + cfg.merge_gap_bytes) {  // <= 1024 segments per read: a read must fit one batch
+                run_hi = std::max(run_hi, span_hi(order[k_end]));
+                k_end++;
+            }
+        for (uint64_t fo = run_lo; fo < run_hi; fo += max_read) {
+            ReadPlan rd;
+            rd.file_off = fo;
+            rd.read_len = (uint32_t)std::min<uint64_t>(max_read, run_hi - fo);
+            rd.first_seg = (uint32_t)r.segs.size();
+            for (size_t j = k; j < k_end; j++) {
+                RangePlan& p = r.ranges[order[j]];
+                const uint64_t lo = std::max<uint64_t>(fo, (uint64_t)p.start_off), hi = std::min<uint64_t>(fo + rd.read_len, (uint64_t)p.end_off);
+                if (lo >= hi) continue;
+                SegPlan sp;
+                sp.range = order[j];
+                sp.head = (uint32_t)(lo - fo);  // sqe.rs:116: the view starts at start_off - aligned_start
+                sp.payload_len = hi - lo;
+                sp.dst_off = p.dst_off + (lo - (uint64_t)p.start_off);
+                p.seg_ids.push_back((uint32_t)r.segs.size());
+                rd.needed = std::max<uint32_t>(rd.needed, (uint32_t)(hi - fo));
+                r.segs.push_back(sp);
+            }
+            rd.nsegs = (uint32_t)r.segs.size() - rd.first_seg;
+            if (rd.nsegs) r.reads.push_back(rd);  // a read that carries no payload (pure gap) is skipped
+        }
+        k = k_end;
+    }
+    for (size_t i = 0; i < n; i++)
+        if (r.ranges[i].valid) r.ranges[i].segs_left.store((uint32_t)r.ranges[i].seg_ids.size(), std::memory_order_relaxed);
+    r.reads_left.store((uint32_t)r.reads.size(), std::memory_order_release);
+    // get_ranges.rs:39-45: one read op per segment onto THIS worker's deque; peers steal them.
+    for (uint32_t s = 0; s < r.reads.size(); s++) {
+        Op op;
+        op.kind = Op::Read;
+        op.req = rp;
+        op.read = s;
+        wt.push(std::move(op));
+    }
+    return Start::Finished;
+}
+
+}  // namespace lsio

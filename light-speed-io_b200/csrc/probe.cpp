@@ -1,0 +1,76 @@
+// probe.cpp -- lsio_probe_read_ceiling: raw READ_FIXED read rate of a file set with no GPU work
+// (measurement aid; stands in for crates/lsio_uring/benches/fio.ini).
+#include "backend.hpp"
+
+using namespace lsio;
+
+extern "C" {
+
+int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads, uint32_t queue_depth,
+                            uint32_t o_direct, double* gib_per_s) {
+    if (!paths || !n_paths || !gib_per_s || !n_threads || !queue_depth || block_bytes < kAlign || block_bytes % kAlign) return -EINVAL;
+    const uint64_t slot_bytes = block_bytes * queue_depth;
+    uint8_t* pinned = nullptr;
+    LSIO_CUDA_TRY(cudaHostAlloc((void**)&pinned, slot_bytes * n_threads, cudaHostAllocPortable));
+    std::atomic<size_t> next_file{0};
+    std::atomic<uint64_t> total{0};
+    std::atomic<int> err{0};
+    const uint64_t t0 = now_ns();
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_threads; t++) {
+        th.emplace_back([&, t] {
+            Ring ring;
+            unsigned sq = 4;
+            while (sq < queue_depth) sq <<= 1;
+            int rc = ring.init(sq, 0);
+            iovec iv{pinned + (uint64_t)t * slot_bytes, (size_t)slot_bytes};
+            if (rc == 0) rc = ring.register_buffers(&iv, 1);
+            if (rc) { err.store(rc); return; }
+            uint64_t bytes = 0;
+            for (size_t f; (f = next_file.fetch_add(1)) < n_paths;) {
+                int fd = open(paths[f], O_RDONLY | (o_direct ? O_DIRECT : 0));
+                if (fd < 0) { err.store(-errno); break; }
+                struct stat st;
+                fstat(fd, &st);
+                const uint64_t nblk = ((uint64_t)st.st_size + block_bytes - 1) / block_bytes;
+                uint64_t issued = 0, done = 0;
+                std::vector<unsigned> free_slots;
+                for (unsigned i = 0; i < queue_depth; i++) free_slots.push_back(i);
+                while (done < nblk) {
+                    while (issued < nblk && !free_slots.empty()) {
+                        io_uring_sqe* e = ring.get_sqe();
+                        if (!e) break;
+                        const unsigned slot = free_slots.back();
+                        free_slots.pop_back();
+                        e->opcode = IORING_OP_READ_FIXED;
+                        e->fd = fd;
+                        e->addr = (uint64_t)(uintptr_t)(pinned + (uint64_t)t * slot_bytes + (uint64_t)slot * block_bytes);
+                        e->len = (uint32_t)block_bytes;
+                        e->off = issued * block_bytes;
+                        e->buf_index = 0;
+                        e->user_data = slot;
+                        issued++;
+                    }
+                    ring.submit(1);
+                    io_uring_cqe c;
+                    while (ring.pop_cqe(&c)) {
+                        if (c.res < 0) err.store(c.res);
+                        else bytes += (uint64_t)c.res;
+                        free_slots.push_back((unsigned)c.user_data);
+                        done++;
+                    }
+                }
+                close(fd);
+            }
+            total.fetch_add(bytes);
+        });
+    }
+    for (auto& x : th) x.join();
+    const double secs = (double)(now_ns() - t0) * 1e-9;
+    cudaFreeHost(pinned);
+    if (err.load()) return err.load();
+    *gib_per_s = (double)total.load() / secs / (double)(1ull << 30);
+    return 0;
+}
+
+}  // extern "C"
