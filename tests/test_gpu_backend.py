@@ -454,3 +454,32 @@ def test_out_of_order_completions_of_large_reads(lsio, oracle, cuda_dev, data_di
         for _ in range(3):
             secs, nbytes, ok, bad = u.bench_read_files(fns, range(n_files), bs, n_chunks, table)
             assert (ok, bad, nbytes) == (n_files * n_chunks, 0, n_files * fsize)
+
+
+def test_in_process_sharding_over_two_real_gpus(lsio, oracle, cuda_dev, data_dir):
+    """One backend, two device groups on two different GPUs: files dealt round-robin (and one routed explicitly);
+    every chunk is a view in the HBM of the GPU its file was routed to.  Skips on single-GPU boxes."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fns = []
+    for i in range(8):
+        fn = os.path.join(data_dir, f"g{i}")
+        oracle.write_file(fn, 900 + i, 3_000_000 + i)
+        fns.append(fn)
+    with lsio.IoUringCuda(3, devices=(0, 1), arena_bytes=256 << 20, staging_bytes=64 << 20) as u:
+        for i, fn in enumerate(fns):
+            u.get_ranges(fn, [(7, 1_500_000), (1_500_000, -1)], [2 * i, 2 * i + 1], group=1 if i == 0 else None)
+        items = _drain(u.completion(), 16, 30.0)
+        devices = {}
+        for c in items:
+            assert c.is_ok(), c
+            i, half = divmod(c.user_data, 2)
+            want = oracle.pread_range(fns[i], *((7, 1_500_000) if half == 0 else (1_500_000, -1)))
+            assert np.array_equal(c.buffer.as_slice(), want) and c.crc32c == oracle.crc32c(want)
+            assert c.buffer.device == c.device and c.buffer.to_torch().device.index == c.device
+            devices.setdefault(i, set()).add(c.device)
+        assert all(len(d) == 1 for d in devices.values())          # a file (request) lives on one GPU
+        assert devices[0] == {1}                                   # explicit routing
+        assert {next(iter(d)) for d in devices.values()} == {0, 1}  # both GPUs were used
