@@ -173,7 +173,6 @@ struct Group {
     std::atomic<uint32_t> workers_alive{0};
     uint64_t copy_seq = 0;  // device thread: next staging entry to copy
     Batch* last_flush_batch = nullptr;  // the batch flush_run() was filling when it failed
-    std::string init_error;
 };
 
 using OutChannel = Channel<lsio_output>;
