@@ -483,3 +483,80 @@ def test_in_process_sharding_over_two_real_gpus(lsio, oracle, cuda_dev, data_dir
         assert all(len(d) == 1 for d in devices.values())          # a file (request) lives on one GPU
         assert devices[0] == {1}                                   # explicit routing
         assert {next(iter(d)) for d in devices.values()} == {0, 1}  # both GPUs were used
+
+
+def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
+    """Randomised soak over the whole configuration space (both staging modes, tmpfs and disk, slot / read / merge /
+    checksum / alignment / queue settings, valid and invalid ranges, a consumer that sometimes lags): every chunk is
+    compared with the oracle's pread bytes and checksums; every range yields exactly one item."""
+    import shutil
+    import tempfile
+
+    rng = np.random.default_rng(2026)
+    dirs = [tempfile.mkdtemp(prefix="lsio_stress_", dir=d) for d in (("/dev/shm", "/tmp") if os.path.isdir("/dev/shm") else ("/tmp",))]
+    try:
+        files = []
+        for i in range(14):
+            size = int(rng.choice([1, 511, 4096, 70_001, 1_048_576, 3_000_003, 9_437_184 + 17]))
+            fn = os.path.join(dirs[i % len(dirs)], f"s{i}")
+            oracle.write_file(fn, 5000 + i, size)
+            files.append((fn, size))
+        for it in range(int(os.environ.get("LSIO_STRESS_ITERS", 14))):
+            cfg = dict(
+                staging_mode=int(rng.integers(0, 2)), host_slots_per_worker=int(rng.integers(1, 6)), host_slot_kib=int(rng.choice([128, 512, 2048])),
+                max_read_bytes=int(rng.choice([4096, 65536, 524288, 4 << 20])), merge_ranges=int(rng.integers(0, 2)),
+                merge_gap_bytes=int(rng.choice([0, 4096])), checksum=int(rng.integers(0, 4)), pack_align=int(rng.choice([1, 16, 512])),
+                sq_entries=int(rng.choice([8, 64])), completion_bound=int(rng.choice([4, 1024])), statx_via_ring=int(rng.integers(0, 2)),
+                o_direct=int(rng.integers(0, 2)), poll_sleep_us=int(rng.choice([0, 50])), arena_bytes=96 << 20, staging_bytes=32 << 20,
+            )
+            expect = {}
+            with lsio.IoUringCuda(int(rng.integers(1, 5)), **cfg) as u:
+                ud = 0
+                for fn, size in [files[int(k)] for k in rng.integers(0, len(files), 10)]:
+                    rs = []
+                    for _ in range(int(rng.integers(1, 40))):
+                        kind = rng.integers(0, 10)
+                        if kind == 0:
+                            r = (0, -1)
+                        elif kind == 1:
+                            r = (int(size + rng.integers(1, 100)), int(size + 200))  # invalid: beyond EOF
+                        elif kind == 2:
+                            n = int(min(size, rng.integers(1, 3000)))
+                            r = (-n, -1)
+                        else:
+                            n = int(rng.integers(1, min(size, 2_000_000) + 1))
+                            s = int(rng.integers(0, size - n + 1))
+                            r = (s, s + n)
+                        rs.append(r)
+                    ids = list(range(ud, ud + len(rs)))
+                    for k, r in zip(ids, rs):
+                        expect[k] = (fn, size, r)
+                    ud += len(rs)
+                    u.get_ranges(fn, rs, ids)
+                seen = set()
+                rx = u.completion()
+                for n_got in range(len(expect)):
+                    if n_got % 37 == 0 and it % 3 == 0:
+                        time.sleep(0.002)  # a lagging consumer: back-pressure on small channels
+                    c = rx.recv_timeout(30.0)
+                    assert c.user_data not in seen, f"duplicate item for {c.user_data} with {cfg}"
+                    seen.add(c.user_data)
+                    fn, size, (s, e) = expect[c.user_data]
+                    rc, rr = oracle.resolve_range(size, s, e)
+                    valid = rc == 0 and rr.end_off <= size and rr.end_off > rr.start_off
+                    assert c.is_ok() == valid, (cfg, (s, e), size, c)
+                    if valid:
+                        want = oracle.pread_range(fn, s, e)
+                        assert np.array_equal(c.buffer.as_slice(), want), (cfg, fn, (s, e))
+                        if cfg["checksum"] & 1:
+                            assert c.crc32c == oracle.crc32c(want), (cfg, (s, e))
+                        if cfg["checksum"] & 2:
+                            assert c.xxh64 == oracle.xxh64(want), (cfg, (s, e))
+                        if cfg["pack_align"] > 1:
+                            assert c.buffer.as_ptr() % cfg["pack_align"] == 0
+                        c.buffer.drop()
+                with pytest.raises(lsio.RecvTimeoutError):
+                    rx.recv_timeout(0.05)
+    finally:
+        for d in dirs:
+            shutil.rmtree(d, ignore_errors=True)
