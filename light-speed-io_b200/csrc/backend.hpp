@@ -79,6 +79,7 @@ struct Request {
     bool have_fd = false, have_statx = false, planned = false;
     uint8_t n_cqes_received = 0;
     uint64_t total_bytes = 0;
+    uint64_t arena_epoch_seen = 0;  // arena epoch when this request last found the arena full
     std::shared_ptr<InnerBuffer> buffer;  // the request's HBM buffer
     std::unique_ptr<RangePlan[]> ranges;
     std::vector<ReadPlan> reads;

@@ -70,6 +70,7 @@ Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op
         r.fd = -1;
         return Start::Finished;
     }
+    const uint64_t epoch_before = g.arena->epoch();
     uint8_t* block = g.arena->alloc(r.total_bytes + 16);
     if (!block) {
         if (r.total_bytes + 16 > g.arena->capacity()) {
@@ -80,6 +81,7 @@ Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op
             return Start::Finished;
         }
         be->stats.arena_stalls++;
+        r.arena_epoch_seen = epoch_before;
         return Start::Retry;  // wait for the consumer to drop chunks
     }
     auto buf = std::make_shared<InnerBuffer>();

@@ -142,6 +142,7 @@ class DeviceArena {
         uint64_t len = u->second;
         used_.erase(u);
         in_use_ -= len;
+        epoch_.fetch_add(1, std::memory_order_release);
         auto next = free_.lower_bound(off);
         if (next != free_.end() && off + len == next->first) {
             len += next->second;
@@ -160,6 +161,8 @@ class DeviceArena {
         std::lock_guard<std::mutex> lk(mu_);
         return in_use_;
     }
+    // Bumped on every release: a request that found the arena full retries only after it moved.
+    uint64_t epoch() const { return epoch_.load(std::memory_order_acquire); }
 
   private:
     int device_;
@@ -169,6 +172,7 @@ class DeviceArena {
     std::mutex mu_;
     std::map<uint64_t, uint64_t> free_, used_;
     uint64_t in_use_ = 0;
+    std::atomic<uint64_t> epoch_{0};
 };
 
 }  // namespace lsio

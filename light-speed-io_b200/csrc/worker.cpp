@@ -347,6 +347,11 @@ struct Worker {
                 for (size_t n = stalled_plans.size(); n-- > 0;) {
                     Op op = std::move(stalled_plans.front());
                     stalled_plans.pop_front();
+                    // nothing has been released since it last failed: do not even take the arena lock
+                    if (op.req->planned && op.req->arena_epoch_seen == g.arena->epoch()) {
+                        stalled_plans.push_back(std::move(op));
+                        continue;
+                    }
                     if (start(op) == Start::Retry) stalled_plans.push_back(std::move(op));
                     else started++;
                 }
