@@ -71,6 +71,37 @@ void lsio_aligned_bytes_drop(lsio_aligned_bytes* self);
 /* Drops the `buffer` of n consecutive lsio_output-like records: views[i] may be NULL. */
 void lsio_aligned_bytes_drop_many(lsio_aligned_bytes* const* views, size_t n);
 
+
+/* ---- DLPack export (the Python / PyTorch surface the reference only plans,
+ * README.md:74,85,103, planned_design.md:79 `lsio_io_python_bridge`).  Layout-compatible with
+ * DLPack's `DLManagedTensor` (dlpack.h, ABI of v0.x that torch.from_dlpack / cupy / jax consume)
+ * so a chunk in HBM becomes a framework tensor without a copy. ------------------------------------ */
+typedef struct lsio_dl_tensor {
+    void* data;
+    int32_t device_type; /* 1 = kDLCPU, 2 = kDLCUDA, 3 = kDLCUDAHost (pinned) */
+    int32_t device_id;
+    int32_t ndim;
+    uint8_t dtype_code;  /* 0 int, 1 uint, 2 float, 4 bfloat */
+    uint8_t dtype_bits;
+    uint16_t dtype_lanes;
+    int64_t* shape;
+    int64_t* strides;    /* NULL: compact row-major */
+    uint64_t byte_offset;
+} lsio_dl_tensor;
+typedef struct lsio_dl_managed_tensor {
+    lsio_dl_tensor dl_tensor;
+    void* manager_ctx;
+    void (*deleter)(struct lsio_dl_managed_tensor* self);
+} lsio_dl_managed_tensor;
+
+/* A DLManagedTensor over the view: `ndim` dimensions `shape[]` of elements (dtype_code, dtype_bits),
+ * whose byte size must equal the view's length and whose element size must divide the view's address;
+ * shape == NULL means one dimension of len / (dtype_bits / 8) elements.  The tensor holds its own
+ * share of the backing buffer (the HBM request buffer is recycled after BOTH the view and the tensor
+ * are released); the consumer calls `deleter` once.  Returns 0 or LSIO_AB_ERR_ARG. */
+int lsio_aligned_bytes_to_dlpack(const lsio_aligned_bytes* self, uint8_t dtype_code, uint8_t dtype_bits, const int64_t* shape,
+                                 int32_t ndim, lsio_dl_managed_tensor** out);
+
 #ifdef __cplusplus
 }
 #endif

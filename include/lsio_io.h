@@ -11,6 +11,9 @@
  *                                                              disconnects when the backend is dropped)
  *   trait Reader::get_ranges()              lib.rs:16-45       each backend's <backend>_get_ranges(), see
  *                                                              lsio_uring_cuda.h
+ *   TODO "group instructions" (issue #68)   lib.rs:6-8         lsio_output.group + <backend>_next_group():
+ *     planned_design.md:71-72                                  every operation of group n completes before any
+ *                                                              I/O of group n+1 starts; outputs carry their group
  */
 #ifndef LSIO_IO_H
 #define LSIO_IO_H
@@ -47,6 +50,7 @@ typedef struct lsio_output {
     uint32_t crc32c;    /* CRC-32C of the chunk's bytes as landed (computed on the device) */
     uint64_t xxh64;     /* XXH64 (seed 0) of the chunk's bytes */
     lsio_chunk chunk;   /* valid when status == 0; user_data is echoed for range errors too */
+    uint64_t group;     /* ordered group the operation was submitted in (lib.rs:6-8); 0 until next_group() is called */
     char context[256];  /* error context: path, range, user_data, like the reference's error string */
 } lsio_output;
 

@@ -97,6 +97,18 @@ int lsio_uring_cuda_get_ranges_on(lsio_uring_cuda* self, uint32_t group, const c
                                   const int64_t* range_start, const int64_t* range_end, size_t n_ranges,
                                   const uint64_t* user_data, size_t n_user_data);
 
+/* Ordered groups of operations -- planned in the reference, not built there (lsio_io lib.rs:6-8,
+ * planned_design.md:71-72: "the IO crate will guarantee that all operations in group n are completed
+ * before any IO operations in group n+1 are started"; outputs "will also be grouped").
+ * Every get_ranges call belongs to the backend's current group (0 at construction).  next_group()
+ * closes the current group and returns the id of the new one: requests submitted from then on are
+ * held back -- not even opened -- until every request of all earlier groups has delivered all of its
+ * items (chunks and errors) to the completion channel, so items arrive in non-decreasing group order.
+ * Within a group completions stay unordered.  Thread-safe; never blocks. */
+uint64_t lsio_uring_cuda_next_group(lsio_uring_cuda* self);
+/* The group new submissions are tagged with. */
+uint64_t lsio_uring_cuda_current_group(const lsio_uring_cuda* self);
+
 /* Completion::completion(): a new handle on the backend's receiver (drop it yourself). */
 lsio_completion* lsio_uring_cuda_completion(lsio_uring_cuda* self);
 

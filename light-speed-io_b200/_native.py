@@ -98,6 +98,7 @@ for _name, _res, _args in [
     ("lsio_aligned_bytes_backing_len", ctypes.c_size_t, [_vp]),
     ("lsio_aligned_bytes_copy_to_host", ctypes.c_int64, [_vp, _vp, ctypes.c_size_t]),
     ("lsio_aligned_bytes_drop", None, [_vp]),
+    ("lsio_aligned_bytes_to_dlpack", ctypes.c_int, [_vp, ctypes.c_uint8, ctypes.c_uint8, _vp, ctypes.c_int32, ctypes.POINTER(_vp)]),
 ]:
     getattr(lib, _name).restype = _res
     getattr(lib, _name).argtypes = _args
@@ -111,7 +112,7 @@ class CChunk(ctypes.Structure):
 class COutput(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int32), ("opcode", ctypes.c_uint8), ("kind", ctypes.c_uint8), ("checksums", ctypes.c_uint16),
                 ("device", ctypes.c_int32), ("crc32c", ctypes.c_uint32), ("xxh64", ctypes.c_uint64), ("chunk", CChunk),
-                ("context", ctypes.c_char * 256)]
+                ("group", ctypes.c_uint64), ("context", ctypes.c_char * 256)]
 
 
 CHECKSUM_NONE, CHECKSUM_CRC32C, CHECKSUM_XXH64 = 0, 1, 2
@@ -154,6 +155,8 @@ for _name, _res, _args in [
     ("lsio_uring_cuda_get_ranges", ctypes.c_int, [_vp, ctypes.c_char_p, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t]),
     ("lsio_uring_cuda_get_ranges_on", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_char_p, _vp, _vp, ctypes.c_size_t, _vp, ctypes.c_size_t]),
     ("lsio_uring_cuda_completion", _vp, [_vp]),
+    ("lsio_uring_cuda_next_group", ctypes.c_uint64, [_vp]),
+    ("lsio_uring_cuda_current_group", ctypes.c_uint64, [_vp]),
     ("lsio_uring_cuda_get_stats", ctypes.c_int, [_vp, ctypes.POINTER(CStats)]),
     ("lsio_uring_cuda_last_error", ctypes.c_char_p, []),
     ("lsio_uring_cuda_free", None, [_vp]),

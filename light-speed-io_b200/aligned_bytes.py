@@ -82,6 +82,35 @@ class AlignedBytesMut:
             pass
 
 
+_DL_DTYPES = {"uint8": (1, 8), "int8": (0, 8), "uint16": (1, 16), "int16": (0, 16), "uint32": (1, 32), "int32": (0, 32),
+              "uint64": (1, 64), "int64": (0, 64), "float16": (2, 16), "float32": (2, 32), "float64": (2, 64), "bfloat16": (4, 16)}
+_capsule_new = ctypes.pythonapi.PyCapsule_New
+_capsule_new.restype = ctypes.py_object
+_capsule_new.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+# the destructor sees a capsule whose refcount is already 0: handle it as a raw pointer (a py_object
+# argument would incref/decref it and re-enter the deallocator)
+_capsule_is_valid = ctypes.PYFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p)(("PyCapsule_IsValid", ctypes.pythonapi))
+_capsule_get_pointer = ctypes.PYFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p)(("PyCapsule_GetPointer", ctypes.pythonapi))
+
+
+class _DLManaged(ctypes.Structure):  # the head of lsio_dl_managed_tensor: enough to reach `deleter`
+    _fields_ = [("data", ctypes.c_void_p), ("device_type", ctypes.c_int32), ("device_id", ctypes.c_int32), ("ndim", ctypes.c_int32),
+                ("dtype_code", ctypes.c_uint8), ("dtype_bits", ctypes.c_uint8), ("dtype_lanes", ctypes.c_uint16),
+                ("shape", ctypes.c_void_p), ("strides", ctypes.c_void_p), ("byte_offset", ctypes.c_uint64),
+                ("manager_ctx", ctypes.c_void_p), ("deleter", ctypes.CFUNCTYPE(None, ctypes.c_void_p))]
+
+
+@ctypes.PYFUNCTYPE(None, ctypes.c_void_p)
+def _dl_capsule_destructor(capsule):
+    # a consumer renames the capsule to "used_dltensor" and calls the deleter itself; unconsumed capsules are ours
+    if _capsule_is_valid(capsule, b"dltensor"):
+        p = _capsule_get_pointer(capsule, b"dltensor")
+        _DLManaged.from_address(p).deleter(p)
+
+
+_DL_CAPSULE_DESTRUCTOR = ctypes.cast(_dl_capsule_destructor, ctypes.c_void_p)
+
+
 class AlignedBytes:
     """Shared, re-sliceable, immutable view (lib.rs:116-166); may live in host or device memory."""
 
@@ -131,13 +160,28 @@ class AlignedBytes:
             raise AttributeError("not a device view")
         return {"shape": (self.len(),), "typestr": "|u1", "data": (self.as_ptr(), False), "version": 3, "strides": None}
 
-    def to_torch(self):
-        """Zero-copy uint8 torch tensor over a device view (keeps this view alive)."""
+    # ---- DLPack (include/lsio_aligned_bytes.h lsio_aligned_bytes_to_dlpack) ----
+    def __dlpack_device__(self):
+        return {"device": (2, self.device), "pinned": (3, 0), "host": (1, 0)}[self.memory_kind]
+
+    def __dlpack__(self, stream=None, dtype="uint8", shape=None, **_):
+        """A "dltensor" capsule over the view (zero copy; the capsule owns its own share of the
+        buffer).  The pack kernel's batch has retired before a chunk is handed out, so there is
+        nothing to order `stream` after."""
+        code, bits = _DL_DTYPES[str(dtype).replace("torch.", "")]
+        shp = None if shape is None else (ctypes.c_int64 * len(shape))(*shape)
+        out = ctypes.c_void_p()
+        rc = N.lib.lsio_aligned_bytes_to_dlpack(self._h, code, bits, shp, 0 if shape is None else len(shape), ctypes.byref(out))
+        if rc:
+            raise AlignedBytesError(f"to_dlpack: the view ({self.len()} B at {self.as_ptr():#x}) does not fit dtype={dtype} shape={shape}")
+        return _capsule_new(out.value, b"dltensor", _DL_CAPSULE_DESTRUCTOR)
+
+    def to_torch(self, dtype="uint8", shape=None):
+        """Zero-copy torch tensor over the view through DLPack: `dtype`/`shape` reinterpret the bytes
+        (the element size must divide the view's address and length)."""
         import torch
 
-        t = torch.as_tensor(self, device=f"cuda:{self.device}")
-        t._lsio_owner = self
-        return t
+        return torch.from_dlpack(self.__dlpack__(dtype=dtype, shape=shape))
 
     def drop(self):
         if self._h:

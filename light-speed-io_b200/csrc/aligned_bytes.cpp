@@ -146,6 +146,62 @@ int64_t lsio_aligned_bytes_copy_to_host(const lsio_aligned_bytes* self, void* ds
     }
     return (int64_t)n;
 }
+// ---- DLPack export ---------------------------------------------------------------------------------
+namespace {
+struct DlCtx {
+    lsio_dl_managed_tensor mt;
+    lsio_aligned_bytes view;  // the tensor's own share of the buffer
+    int64_t shape[8];
+};
+void dl_deleter(lsio_dl_managed_tensor* self) {
+    if (self) delete static_cast<DlCtx*>(self->manager_ctx);
+}
+}  // namespace
+
+int lsio_aligned_bytes_to_dlpack(const lsio_aligned_bytes* self, uint8_t dtype_code, uint8_t dtype_bits, const int64_t* shape, int32_t ndim,
+                                 lsio_dl_managed_tensor** out) {
+    if (!self || !out || dtype_bits == 0 || dtype_bits % 8 || dtype_code > 6) return LSIO_AB_ERR_ARG;
+    const size_t item = dtype_bits / 8, len = self->end - self->start;
+    const uint8_t* ptr = self->buf->buf + self->start;
+    if (len % item || ((uintptr_t)ptr % item)) return LSIO_AB_ERR_ARG;
+    if (shape ? (ndim < 1 || ndim > 8) : false) return LSIO_AB_ERR_ARG;
+    auto* c = new DlCtx();
+    if (shape) {
+        unsigned __int128 n = 1;
+        for (int i = 0; i < ndim; i++) {
+            if (shape[i] < 0) {
+                delete c;
+                return LSIO_AB_ERR_ARG;
+            }
+            c->shape[i] = shape[i];
+            n *= (uint64_t)shape[i];
+        }
+        if (n * item != len) {
+            delete c;
+            return LSIO_AB_ERR_ARG;
+        }
+    } else {
+        ndim = 1;
+        c->shape[0] = (int64_t)(len / item);
+    }
+    c->view = *self;
+    lsio_dl_tensor& t = c->mt.dl_tensor;
+    t.data = (void*)ptr;
+    t.device_type = self->buf->kind == MemKind::Device ? 2 : self->buf->kind == MemKind::Pinned ? 3 : 1;
+    t.device_id = self->buf->kind == MemKind::Device ? self->buf->device : 0;
+    t.ndim = ndim;
+    t.dtype_code = dtype_code;
+    t.dtype_bits = dtype_bits;
+    t.dtype_lanes = 1;
+    t.shape = c->shape;
+    t.strides = nullptr;
+    t.byte_offset = 0;
+    c->mt.manager_ctx = c;
+    c->mt.deleter = dl_deleter;
+    *out = &c->mt;
+    return 0;
+}
+
 void lsio_aligned_bytes_drop(lsio_aligned_bytes* self) { delete self; }
 void lsio_aligned_bytes_drop_many(lsio_aligned_bytes* const* views, size_t n) {
     for (size_t i = 0; i < n; i++) delete views[i];

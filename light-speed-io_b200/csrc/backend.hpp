@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <deque>
 #include <fstream>
+#include <map>
 #include <sstream>
 #include <thread>
 
@@ -38,6 +39,7 @@ inline uint64_t now_ns() {
 constexpr uint64_t kAlign = 512;  // crates/lsio_uring/src/sqe.rs:12
 
 struct Group;
+struct Backend;
 struct Request;
 using StagingLog = StagingLogT<Request>;
 using StageEntry = StageEntryT<Request>;
@@ -74,6 +76,8 @@ struct Request {
     std::vector<int64_t> starts, ends;
     std::vector<uint64_t> user_data;
     Group* grp = nullptr;
+    Backend* be = nullptr;   // set once the request is counted in its ordered group (see OpGroups)
+    uint64_t op_group = 0;   // ordered group it was submitted in (lsio_io lib.rs:6-8)
     struct statx stx;
     int fd = -1;
     bool have_fd = false, have_statx = false, planned = false;
@@ -85,9 +89,7 @@ struct Request {
     std::vector<ReadPlan> reads;
     std::vector<SegPlan> segs;
     std::atomic<uint32_t> reads_left{0};  // Arc<OpenFile> strong count, get_range.rs:78
-    ~Request() {
-        if (fd >= 0) close(fd);  // only reached when the backend is torn down with reads still queued
-    }
+    ~Request();  // io_uring_cuda.cpp: closes a left-over fd, reports the request finished to its ordered group
 };
 
 // operation.rs:7-12, plus Plan (a request that is open but still waits for HBM).
@@ -178,9 +180,21 @@ struct Group {
 
 using OutChannel = Channel<lsio_output>;
 
+// Ordered groups of operations: planned in the reference (lsio_io/src/lib.rs:6-8, planned_design.md:71-72),
+// built here.  A request counts as finished when the last reference to it is released, which the
+// device stage does only after the request's items are in the completion channel.
+struct OpGroups {
+    std::mutex mu;
+    uint64_t current = 0;                 // group that new submissions join
+    uint64_t running = 0;                 // oldest group that may issue I/O
+    std::map<uint64_t, uint64_t> alive;   // unfinished requests per group
+    std::deque<std::pair<size_t, Op>> held;  // requests of groups > running, in submission order (device group, op)
+};
+
 struct Backend {
     lsio_uring_cuda_config cfg;
     std::shared_ptr<OutChannel> out;
+    OpGroups op_groups;  // declared before `groups`: requests destroyed with a Group still find it
     std::vector<std::unique_ptr<Group>> groups;
     std::atomic<uint64_t> rr{0};
     std::atomic<bool> closing{false};

@@ -38,6 +38,7 @@ static void send_chunk(Group& g, const std::shared_ptr<Request>& rp, uint32_t ra
     view->end = p.dst_off + p.len;
     o.chunk.buffer = view;
     o.chunk.user_data = p.user_data;
+    o.group = r.op_group;
     be->stats.payload_bytes += p.len;
     g.out_pending.push_back(o);  // flushed by flush_outputs(): one lock + one wake-up per retired batch, not per chunk
 }

@@ -34,6 +34,38 @@ static void set_error(const char* fmt, ...) {
     va_end(ap);
     g_last_error = buf;
 }
+// ---- ordered groups (lsio_io/src/lib.rs:6-8) --------------------------------------------------------
+// Pops the held requests that `running` now admits. Caller holds og.mu; the ops are pushed after unlocking.
+static void release_held(OpGroups& og, std::vector<std::pair<size_t, Op>>& out) {
+    while (true) {
+        // running = the oldest group with unfinished requests, else the current group
+        og.running = og.alive.empty() ? og.current : std::min(og.alive.begin()->first, og.current);
+        bool any = false;
+        while (!og.held.empty() && og.held.front().second.req->op_group <= og.running) {
+            out.push_back(std::move(og.held.front()));
+            og.held.pop_front();
+            any = true;
+        }
+        if (!any) break;
+    }
+}
+
+Request::~Request() {
+    if (fd >= 0) close(fd);  // only reached when the backend is torn down with reads still queued
+    if (!be) return;
+    std::vector<std::pair<size_t, Op>> go;
+    {
+        OpGroups& og = be->op_groups;
+        std::lock_guard<std::mutex> lk(og.mu);
+        auto it = og.alive.find(op_group);
+        if (it != og.alive.end() && --it->second == 0) {
+            og.alive.erase(it);
+            if (!be->closing.load()) release_held(og, go);
+        }
+    }
+    for (auto& [gi, op] : go) be->groups[gi]->pool->push(std::move(op));
+}
+
 // ---- construction / teardown ----------------------------------------------------------------------
 static std::vector<int> numa_cpus_of_device(int device) {
     std::vector<int> cpus;
@@ -293,9 +325,36 @@ static int submit(lsio_uring_cuda* self, int group, const char* location, const 
     r->grp = be->groups[gi].get();
     Op op;
     op.kind = Op::GetRanges;
-    op.req = std::move(r);
+    op.req = r;
+    {
+        OpGroups& og = be->op_groups;
+        std::lock_guard<std::mutex> lk(og.mu);
+        r->op_group = og.current;
+        r->be = be;
+        og.alive[og.current]++;
+        if (og.current > og.running) {  // an earlier group is still in flight: hold the request back, unopened
+            og.held.emplace_back(gi, std::move(op));
+            return 0;
+        }
+    }
+    r.reset();
     be->groups[gi]->pool->push(std::move(op));  // threadpool.rs:134-137
     return 0;
+}
+
+uint64_t lsio_uring_cuda_next_group(lsio_uring_cuda* self) {
+    if (!self) return 0;
+    OpGroups& og = self->be->op_groups;
+    std::lock_guard<std::mutex> lk(og.mu);
+    og.current++;
+    if (og.alive.empty()) og.running = og.current;  // nothing in flight: the new group may start at once
+    return og.current;
+}
+uint64_t lsio_uring_cuda_current_group(const lsio_uring_cuda* self) {
+    if (!self) return 0;
+    OpGroups& og = self->be->op_groups;
+    std::lock_guard<std::mutex> lk(og.mu);
+    return og.current;
 }
 
 int lsio_uring_cuda_get_ranges(lsio_uring_cuda* self, const char* location, const int64_t* range_start, const int64_t* range_end, size_t n_ranges,
@@ -349,6 +408,13 @@ void lsio_uring_cuda_free(lsio_uring_cuda* self) {
     }
     joined.store(true);
     drainer.join();
+    {  // requests of later groups that were never admitted: dropped unopened
+        std::deque<std::pair<size_t, Op>> held;
+        {
+            std::lock_guard<std::mutex> lk(be->op_groups.mu);
+            held.swap(be->op_groups.held);
+        }
+    }
     for (auto& g : be->groups) free_group_cuda(*g);
     delete self;  // chunks already handed out keep the arena alive through their InnerBuffer
 }

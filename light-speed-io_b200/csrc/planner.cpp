@@ -19,6 +19,7 @@ void send_error(Backend* be, int status, uint8_t opcode, const Request& r, int r
     o.status = status;
     o.opcode = opcode;
     o.device = r.grp ? r.grp->device : -1;
+    o.group = r.op_group;
     if (range >= 0) {
         o.chunk.user_data = r.user_data[range];
         snprintf(o.context, sizeof o.context, "%s: %s (io_uring opcode %u, result %d). path=%s range=%lld..%lld user_data=%llu", what,

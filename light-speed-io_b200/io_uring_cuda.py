@@ -32,10 +32,10 @@ class Disconnected(Exception):
 class Chunk:
     """lsio_io::Chunk (lib.rs:50-56), plus the device-side proof of its bytes."""
 
-    __slots__ = ("buffer", "user_data", "crc32c", "xxh64", "device")
+    __slots__ = ("buffer", "user_data", "crc32c", "xxh64", "device", "group")
 
-    def __init__(self, buffer, user_data, crc32c, xxh64, device):
-        self.buffer, self.user_data, self.crc32c, self.xxh64, self.device = buffer, user_data, crc32c, xxh64, device
+    def __init__(self, buffer, user_data, crc32c, xxh64, device, group=0):
+        self.buffer, self.user_data, self.crc32c, self.xxh64, self.device, self.group = buffer, user_data, crc32c, xxh64, device, group
 
     def is_ok(self):
         return True
@@ -47,10 +47,10 @@ class Chunk:
 class IoError:
     """An `Err(anyhow::Error)` item of the completion channel (operation.rs:82-100)."""
 
-    __slots__ = ("status", "opcode", "user_data", "context")
+    __slots__ = ("status", "opcode", "user_data", "context", "group")
 
-    def __init__(self, status, opcode, user_data, context):
-        self.status, self.opcode, self.user_data, self.context = status, opcode, user_data, context
+    def __init__(self, status, opcode, user_data, context, group=0):
+        self.status, self.opcode, self.user_data, self.context, self.group = status, opcode, user_data, context, group
 
     @property
     def errno(self):
@@ -67,8 +67,8 @@ def _convert(o):
     if o.status == 0:
         crc = o.crc32c if (o.checksums & N.CHECKSUM_CRC32C) else None
         xx = o.xxh64 if (o.checksums & N.CHECKSUM_XXH64) else None
-        return Chunk(AlignedBytes(o.chunk.buffer), o.chunk.user_data, crc, xx, o.device)
-    return IoError(o.status, o.opcode, o.chunk.user_data, o.context.decode(errors="replace"))
+        return Chunk(AlignedBytes(o.chunk.buffer), o.chunk.user_data, crc, xx, o.device, o.group)
+    return IoError(o.status, o.opcode, o.chunk.user_data, o.context.decode(errors="replace"), o.group)
 
 
 class Receiver:
@@ -194,6 +194,15 @@ class IoUringCuda:
             rc = N.lib.lsio_uring_cuda_get_ranges_on(self._h, group, loc, starts.ctypes.data, ends.ctypes.data, len(starts), ud.ctypes.data, len(ud))
         if rc:
             raise ValueError(f"get_ranges rejected (rc={rc})")
+
+    def next_group(self):
+        """Close the current ordered group and open the next (planned in the reference: lsio_io lib.rs:6-8,
+        planned_design.md:71-72): requests submitted from now on start only after every earlier group has
+        delivered all of its items; items carry `.group`. Returns the new group id."""
+        return N.lib.lsio_uring_cuda_next_group(self._h)
+
+    def current_group(self):
+        return N.lib.lsio_uring_cuda_current_group(self._h)
 
     def completion(self):
         return self._rx

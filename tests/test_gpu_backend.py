@@ -560,3 +560,91 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
     finally:
         for d in dirs:
             shutil.rmtree(d, ignore_errors=True)
+
+
+def test_ordered_groups(lsio, oracle, cuda_dev, data_dir):
+    """Ordered groups of operations (planned in the reference, lsio_io/src/lib.rs:6-8 and
+    planned_design.md:71-72: "all operations in group n are completed before any IO operations in
+    group n+1 are started"; outputs are grouped too).  Items must arrive in non-decreasing group
+    order, errors included, with every group complete; within a group order is free."""
+    n_groups, files_per_group, nr = 5, 6, 24
+    size = 3 * MIB + 77
+    fns = []
+    for i in range(n_groups * files_per_group):
+        fn = os.path.join(data_dir, f"g{i}")
+        oracle.write_file(fn, 100 + i, size)
+        fns.append(fn)
+    rng = np.random.default_rng(11)
+    ranges = {}
+    with lsio.IoUringCuda(4, arena_bytes=256 << 20, staging_bytes=32 << 20, completion_bound=64) as u:
+        assert u.current_group() == 0
+        expected = []
+        for g in range(n_groups):
+            for k in range(files_per_group):
+                fi = g * files_per_group + k
+                rs = []
+                for j in range(nr):
+                    n = int(rng.integers(1, 200_000))
+                    s = int(rng.integers(0, size - n))
+                    rs.append((s, s + n))
+                ranges[fi] = rs
+                u.get_ranges(fns[fi], rs, [(fi << 32) | j for j in range(nr)])
+                expected += [g] * nr
+            # one failing request per group: its single Err item belongs to the group as well
+            u.get_ranges(os.path.join(data_dir, f"missing_{g}"), [(0, 10)], [0xFFFF0000 + g])
+            expected.append(g)
+            assert u.next_group() == g + 1
+        rx = u.completion()
+        items = _drain(rx, len(expected))
+        assert [c.group for c in items] == expected  # non-decreasing, each group complete before the next starts
+        ok = [c for c in items if c.is_ok()]
+        assert len(ok) == n_groups * files_per_group * nr
+        errs = [c for c in items if not c.is_ok()]
+        assert sorted(e.group for e in errs) == list(range(n_groups)) and all(e.errno == 2 for e in errs)
+        _check_chunks(oracle, ok, lambda ud: fns[ud >> 32], lambda ud: ranges[ud >> 32][ud & 0xFFFFFFFF])
+        # a later group submitted while nothing is in flight starts at once
+        g = u.next_group()
+        u.get_ranges(fns[0], [(0, 4096)], [7])
+        c = rx.recv_timeout(10.0)
+        assert c.is_ok() and c.group == g and c.user_data == 7
+
+
+def test_group_held_requests_dropped_on_teardown(lsio, oracle, cuda_dev, data_dir):
+    """Dropping the backend while later groups are still held back must not hang or leak."""
+    fn = os.path.join(data_dir, "gt")
+    oracle.write_file(fn, 5, 8 * MIB)
+    u = lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20, completion_bound=4)
+    for g in range(4):
+        u.get_ranges(fn, [(i * 4096, (i + 1) * 4096) for i in range(64)], range(64))  # 64 items > the channel bound: group 0 cannot finish
+        u.next_group()
+    rx = u.completion()
+    c = rx.recv_timeout(10.0)
+    assert c.is_ok() and c.group == 0
+    u.drop()
+    rx.drop()
+
+
+def test_chunks_as_torch_tensors_through_dlpack(lsio, oracle, cuda_dev, data_dir):
+    """Chunks in HBM become torch tensors without a copy (DLPack), typed and shaped, and keep their
+    HBM request buffer alive after the chunk view itself is dropped."""
+    import torch
+
+    fn = os.path.join(data_dir, "t")
+    a = np.random.default_rng(5).standard_normal((64, 128)).astype(np.float32)
+    with open(fn, "wb") as f:
+        f.write(b"\x00" * 1024 + a.tobytes() + b"\x00" * 300)
+    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20, pack_align=16) as u:
+        u.get_ranges(fn, [(1024, 1024 + a.nbytes), (1024 + 128 * 4 * 3, 1024 + 128 * 4 * 5), (1, 1001)], [0, 1, 2])
+        got = {c.user_data: c for c in _drain(u.completion(), 3)}
+        t = torch.from_dlpack(got[0].buffer)
+        assert t.is_cuda and t.dtype == torch.uint8 and t.data_ptr() == got[0].buffer.as_ptr()
+        full = got[0].buffer.to_torch("float32", a.shape)
+        rows = got[1].buffer.to_torch("float32", (2, 128))
+        raw = got[2].buffer.to_torch()
+        for c in got.values():
+            c.buffer.drop()
+        got.clear()
+        assert torch.equal(full.cpu(), torch.from_numpy(a))
+        assert torch.equal(rows.cpu(), torch.from_numpy(a[3:5]))
+        assert bytes(raw.cpu().numpy()) == (b"\x00" * 1024 + a.tobytes())[1:1001]
+        assert float(full.sum()) == pytest.approx(float(a.sum()), rel=1e-4)

@@ -225,3 +225,38 @@ def test_files_for_rank_is_a_partition(lsio):
 def test_native_host_components(lsio, which, name):
     rc = lsio._native.lib.lsio_uring_cuda_selftest(which)
     assert rc == 0, f"{name}: check {rc % 100} failed"
+
+
+def test_dlpack_export_of_host_views(lsio):
+    """SURVEY 8f rank 3 (the Python/PyTorch surface the reference only plans, README.md:74,85,103):
+    lsio_aligned_bytes_to_dlpack hands a view to torch / numpy without a copy; typed and shaped
+    reinterpretations are checked against size and address."""
+    import torch
+
+    m = lsio.AlignedBytesMut(8192, 512)
+    src = np.arange(8192, dtype=np.uint32).astype(np.uint8)
+    ctypes.memmove(m.as_mut_ptr(), src.ctypes.data, 8192)
+    a = m.freeze()
+    assert a.__dlpack_device__() == (1, 0)
+    t = torch.from_dlpack(a)
+    assert t.dtype == torch.uint8 and t.shape == (8192,) and t.data_ptr() == a.as_ptr()  # zero copy
+    assert np.array_equal(t.numpy(), src)
+    assert np.array_equal(np.from_dlpack(a), src)
+    f = a.to_torch("float32", (4, 16, 32))
+    assert f.dtype == torch.float32 and f.shape == (4, 16, 32) and f.data_ptr() == a.as_ptr()
+    assert np.array_equal(f.numpy().view(np.uint8).ravel(), src)
+    a.set_slice(512, 512 + 4 * 100)
+    assert a.to_torch("int32").shape == (100,)
+    with pytest.raises(lsio.AlignedBytesError):
+        a.to_torch("float32", (33, 3))  # size mismatch
+    a.set_slice(513, 517)
+    with pytest.raises(lsio.AlignedBytesError):
+        a.to_torch("int32")  # element size does not divide the address
+    a.set_slice(0, 3)
+    with pytest.raises(lsio.AlignedBytesError):
+        a.to_torch("uint16")  # nor the length
+    a.reset_slice()
+    cap = a.__dlpack__()  # an unconsumed capsule releases its share itself
+    del cap
+    a.drop()  # tensors keep the buffer alive after the view is gone
+    assert int(t[4097]) == src[4097] and np.array_equal(f.numpy().view(np.uint8).ravel(), src)
