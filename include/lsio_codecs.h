@@ -1,0 +1,76 @@
+/*
+ * lsio_codecs.h -- C ABI of the codec layer: chunks that the I/O path has landed in HBM are decoded
+ * in HBM.  The reference only plans this layer and holds no code for it:
+ *     planned_design.md:83-90   "Abstraction level 2: Parallel compute on chunks ... These crates will all
+ *                                consume the output channel from the IO layer ... lsio_codecs:
+ *                                Compression / decompression"
+ *     README.md:68-70           "Wrap a few decompression algorithms"
+ *     planned_design.md:100-104 Zarr as the first file format
+ * so the entry points below follow the published formats Zarr stores chunks in:
+ *     LZ4 block format            (numcodecs.LZ4 = 4-byte little-endian decoded size + one LZ4 block)
+ *     byte shuffle                (numcodecs.Shuffle / Blosc SHUFFLE, any element size)
+ *     Zarr v3 `crc32c` codec      (chunk bytes + their CRC-32C as 4 little-endian bytes): verified for free
+ *                                 from the checksum the pack kernel fuses into the landing, see
+ *                                 LSIO_CRC32C_RESIDUE
+ * Plain pointers and sizes only; `src`/`dst` are CUDA device addresses on `device`.  Return values as
+ * in lsio_cuda.h: 0, a negative errno-style code, or a positive cudaError_t.  No CPU fallback.
+ */
+#ifndef LSIO_CODECS_H
+#define LSIO_CODECS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One chunk (or independently compressed block of a chunk) to decode. */
+typedef struct lsio_codec_item {
+    uint64_t src;     /* device address of the encoded bytes; no alignment needed */
+    uint64_t dst;     /* device address of the output; no alignment needed; must not overlap src */
+    uint32_t src_len; /* encoded bytes */
+    uint32_t dst_cap; /* room at dst (lz4); ignored by shuffle/unshuffle, which write exactly src_len bytes */
+} lsio_codec_item;
+
+#define LSIO_CODEC_OK 0
+#define LSIO_CODEC_ERR_INPUT 1  /* encoded stream truncated or overrun */
+#define LSIO_CODEC_ERR_OUTPUT 2 /* decoded bytes would not fit dst_cap */
+#define LSIO_CODEC_ERR_OFFSET 3 /* LZ4 match offset 0 or reaching before the start of the output */
+
+typedef struct lsio_codec_result {
+    uint32_t out_len; /* bytes written at dst */
+    int32_t status;   /* LSIO_CODEC_* */
+} lsio_codec_result;
+
+/* LZ4 block decode of n independent blocks in one launch (one warp per block; the warp parses the
+ * token stream from a shared-memory window and copies literals and matches cooperatively).
+ * `items` and `results` are HOST arrays; the call uploads, launches on `stream`, downloads and
+ * synchronises.  A failed block sets its own status only. */
+int lsio_codecs_lz4_decompress(int device, const lsio_codec_item* items, size_t n, lsio_codec_result* results, void* stream);
+/* Asynchronous form for pipelines: `items_dev` / `results_dev` are device-accessible arrays
+ * (device or mapped pinned memory).  Enqueues exactly one kernel launch on `stream`. */
+int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_dev, size_t n, lsio_codec_result* results_dev, void* stream);
+
+/* Byte unshuffle (decode) / shuffle (encode) of n buffers of `elem_size`-byte elements:
+ * unshuffle: dst[i*elem + j] = src[j*cnt + i], cnt = src_len / elem_size; the src_len % elem_size
+ * trailing bytes are copied unchanged (numcodecs.Shuffle).  HBM-bound: 2 * src_len bytes per buffer.
+ * Host `items`; uploads, launches one kernel on `stream`, synchronises. */
+int lsio_codecs_unshuffle(int device, const lsio_codec_item* items, size_t n, uint32_t elem_size, void* stream);
+int lsio_codecs_shuffle(int device, const lsio_codec_item* items, size_t n, uint32_t elem_size, void* stream);
+/* Asynchronous forms: `items_dev` device-accessible, `tile_prefix_dev` = n+1 uint32 exclusive prefix sums
+ * of lsio_codecs_shuffle_tiles(src_len) per item (the last entry is the launch's tile count `n_tiles`). */
+uint32_t lsio_codecs_shuffle_tiles(uint32_t src_len);
+int lsio_codecs_unshuffle_async(int device, const lsio_codec_item* items_dev, const uint32_t* tile_prefix_dev, size_t n, uint32_t n_tiles,
+                                uint32_t elem_size, int forward, void* stream);
+
+/* Zarr v3 `crc32c` codec: CRC-32C over (bytes || CRC-32C(bytes) as 4 LE bytes) is this constant whatever
+ * the bytes are.  A chunk stored with that codec is therefore verified by comparing the CRC the pack
+ * kernel already computed over the landed range (lsio_output.crc32c) with the residue: no extra pass. */
+#define LSIO_CRC32C_RESIDUE 0x48674BC7u
+int lsio_codecs_crc32c_trailer_ok(uint32_t crc32c_of_chunk_with_trailer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

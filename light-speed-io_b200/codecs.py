@@ -1,0 +1,155 @@
+"""Host-side mirror of the codec layer (include/lsio_codecs.h): decode chunks where the I/O path
+landed them, in HBM.  The reference only plans this layer (`lsio_codecs`, planned_design.md:83-90:
+"These crates will all consume the output channel from the IO layer"; README.md:68-70); the codec
+names below are the Zarr ecosystem's (numcodecs.LZ4, numcodecs.Shuffle, the Zarr v3 `crc32c` codec).
+
+PyTorch is plumbing here (output tensors, streams); the work is done by the sm_100a kernels in
+csrc/codecs.cu.  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _native as N
+from .cuda_ops import _stream_ptr
+
+ITEM_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")])
+RESULT_DTYPE = np.dtype([("out_len", "<u4"), ("status", "<i4")])
+CRC32C_RESIDUE = 0x48674BC7
+STATUS_TEXT = {0: "ok", 1: "encoded stream truncated or overrun", 2: "decoded bytes do not fit", 3: "bad LZ4 match offset"}
+
+for _name, _res, _args in [
+    ("lsio_codecs_lz4_decompress", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    ("lsio_codecs_lz4_decompress_async", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    ("lsio_codecs_unshuffle", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_void_p]),
+    ("lsio_codecs_shuffle", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_void_p]),
+    ("lsio_codecs_shuffle_tiles", ctypes.c_uint32, [ctypes.c_uint32]),
+    ("lsio_codecs_unshuffle_async", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
+                                                   ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]),
+    ("lsio_codecs_crc32c_trailer_ok", ctypes.c_int, [ctypes.c_uint32]),
+]:
+    getattr(N.lib, _name).restype = _res
+    getattr(N.lib, _name).argtypes = _args
+
+
+class CodecError(Exception):
+    pass
+
+
+def make_items(src, dst, src_len, dst_cap=0):
+    """An lsio_codec_item array from per-chunk device addresses and sizes (arrays or scalars)."""
+    n = len(src)
+    items = np.zeros(n, dtype=ITEM_DTYPE)
+    items["src"], items["dst"], items["src_len"], items["dst_cap"] = src, dst, src_len, dst_cap
+    return items
+
+
+def lz4_decompress(items, device=0, stream=None):
+    """LZ4 block decode of every item in one launch; returns the lsio_codec_result array."""
+    items = np.ascontiguousarray(items, dtype=ITEM_DTYPE)
+    res = np.zeros(len(items), dtype=RESULT_DTYPE)
+    N.check(N.lib.lsio_codecs_lz4_decompress(int(device), items.ctypes.data, len(items), res.ctypes.data, _stream_ptr(stream)), "lz4_decompress")
+    return res
+
+
+def unshuffle(items, elem_size, device=0, stream=None):
+    items = np.ascontiguousarray(items, dtype=ITEM_DTYPE)
+    N.check(N.lib.lsio_codecs_unshuffle(int(device), items.ctypes.data, len(items), int(elem_size), _stream_ptr(stream)), "unshuffle")
+
+
+def shuffle(items, elem_size, device=0, stream=None):
+    items = np.ascontiguousarray(items, dtype=ITEM_DTYPE)
+    N.check(N.lib.lsio_codecs_shuffle(int(device), items.ctypes.data, len(items), int(elem_size), _stream_ptr(stream)), "shuffle")
+
+
+def crc32c_trailer_ok(crc32c_of_chunk_with_trailer):
+    return bool(N.lib.lsio_codecs_crc32c_trailer_ok(int(crc32c_of_chunk_with_trailer) & 0xFFFFFFFF))
+
+
+# ---- codec descriptions, named after their numcodecs / Zarr v3 counterparts ----------------------------
+class Crc32c:
+    """Zarr v3 `crc32c` codec: the stored chunk ends with the CRC-32C of what precedes it (4 LE bytes).
+    Decoding verifies it from the CRC the pack kernel fused into the landing -- no pass over the data --
+    and drops the 4 bytes."""
+
+
+class LZ4:
+    """numcodecs.LZ4: `header` bytes (4: the decoded size, little-endian) then one LZ4 block."""
+
+    def __init__(self, header=4):
+        self.header = header
+
+
+class Shuffle:
+    """numcodecs.Shuffle(elementsize): byte planes back to elements."""
+
+    def __init__(self, elementsize=4):
+        self.elementsize = elementsize
+
+
+class CodecPipeline:
+    """The decode side of a Zarr codec chain, applied to a whole batch of landed chunks at once.
+
+    `codecs` is in ENCODE order as Zarr metadata lists it, e.g. [Shuffle(4), LZ4(), Crc32c()] (filters,
+    compressor, checksum); decode runs it backwards.  Every chunk decodes to `decoded_nbytes` bytes (a Zarr
+    array's chunk shape is fixed), so the result is one (n_chunks, decoded_nbytes) uint8 tensor in HBM,
+    chunk i in row i -- ready to be viewed as the array dtype and stacked into a training batch."""
+
+    def __init__(self, codecs, decoded_nbytes, device=0):
+        self.codecs, self.decoded_nbytes, self.device = list(codecs), int(decoded_nbytes), int(device)
+        if self.decoded_nbytes % 16:
+            raise ValueError("decoded_nbytes must be a multiple of 16 (rows are addressed as 16-byte vectors)")
+
+    def decode(self, chunks, stream=None):
+        """chunks: lsio Chunk items (device views, kept alive by the caller until this returns).
+        Returns the decoded (n, decoded_nbytes) uint8 tensor; raises CodecError naming the first bad chunk."""
+        import torch
+
+        n = len(chunks)
+        dev = torch.device("cuda", self.device)
+        src = np.array([c.buffer.as_ptr() for c in chunks], dtype=np.uint64)
+        src_len = np.array([c.buffer.len() for c in chunks], dtype=np.int64)
+        cur = None  # tensor holding the current stage's rows (None: still the chunk buffers themselves)
+        for codec in reversed(self.codecs):
+            if isinstance(codec, Crc32c):
+                for i, c in enumerate(chunks):
+                    if c.crc32c is None:
+                        raise CodecError("Crc32c needs the backend's fused CRC-32C (checksum=CHECKSUM_CRC32C)")
+                    if src_len[i] < 4 or not crc32c_trailer_ok(c.crc32c):
+                        raise CodecError(f"chunk {i} (user_data={c.user_data}): crc32c trailer mismatch")
+                src_len = src_len - 4
+            elif isinstance(codec, LZ4):
+                out = torch.empty((n, self.decoded_nbytes), dtype=torch.uint8, device=dev)
+                dst = out.data_ptr() + np.arange(n, dtype=np.uint64) * np.uint64(self.decoded_nbytes)
+                if np.any(src_len < codec.header):
+                    raise CodecError("chunk shorter than its LZ4 header")
+                items = make_items(src + np.uint64(codec.header), dst, src_len - codec.header, self.decoded_nbytes)
+                res = lz4_decompress(items, self.device, stream)
+                bad = np.flatnonzero((res["status"] != 0) | (res["out_len"] != self.decoded_nbytes))
+                if len(bad):
+                    i = int(bad[0])
+                    raise CodecError(f"chunk {i} (user_data={chunks[i].user_data}): lz4 {STATUS_TEXT.get(int(res['status'][i]), '?')}, "
+                                     f"{int(res['out_len'][i])} of {self.decoded_nbytes} bytes")
+                cur, src = out, dst
+                src_len = np.full(n, self.decoded_nbytes, dtype=np.int64)
+            elif isinstance(codec, Shuffle):
+                if np.any(src_len != self.decoded_nbytes):
+                    raise CodecError("Shuffle input is not decoded_nbytes long")
+                out = torch.empty((n, self.decoded_nbytes), dtype=torch.uint8, device=dev)
+                dst = out.data_ptr() + np.arange(n, dtype=np.uint64) * np.uint64(self.decoded_nbytes)
+                unshuffle(make_items(src, dst, src_len), codec.elementsize, self.device, stream)
+                cur, src = out, dst
+            else:
+                raise TypeError(f"unknown codec {codec!r}")
+        if cur is None:  # no data-moving stage: gather the (verified) chunks into rows with the pack kernel
+            from .cuda_ops import PackPlan
+
+            cur = torch.empty((n, self.decoded_nbytes), dtype=torch.uint8, device=dev)
+            if np.any(src_len != self.decoded_nbytes):
+                raise CodecError("stored chunk size differs from decoded_nbytes")
+            dst = cur.data_ptr() + np.arange(n, dtype=np.uint64) * np.uint64(self.decoded_nbytes)
+            plan = PackPlan(self.device, src, dst, src_len.astype(np.uint64), store=True, crc32c=False)
+            plan.launch(None, stream)
+            torch.cuda.synchronize(dev)
+            plan.close()
+        return cur

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_build", "liblsio_oracle.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("lsio_oracle.c", "lsio_uring_ref.c", "lsio_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("lsio_oracle.c", "lsio_uring_ref.c", "lsio_codecs_oracle.c", "lsio_oracle.h", "Makefile")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     return LIB_PATH
@@ -282,3 +282,53 @@ def bench_read_ranges(paths, per_file_ranges, n_worker_threads, sqpoll=True, mod
     secs = L.lsio_ref_bench_read_ranges(arr, len(paths), st.ctypes.data, en.ctypes.data, cnt.ctypes.data, n_worker_threads, int(sqpoll), mode,
                                         ctypes.byref(b), ctypes.byref(e))
     return secs, b.value, e.value
+
+
+# ---- codec layer oracle (oracle/lsio_codecs_oracle.c) ----------------------------------------------
+L.lsio_oracle_lz4_decompress.restype = ctypes.c_int64
+L.lsio_oracle_lz4_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+L.lsio_oracle_lz4_compress.restype = ctypes.c_int64
+L.lsio_oracle_lz4_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+L.lsio_oracle_lz4_compress_bound.restype = ctypes.c_size_t
+L.lsio_oracle_lz4_compress_bound.argtypes = [ctypes.c_size_t]
+L.lsio_oracle_shuffle.restype = None
+L.lsio_oracle_shuffle.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
+L.lsio_oracle_unshuffle.restype = None
+L.lsio_oracle_unshuffle.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
+
+
+def _u8(data):
+    return np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else data, dtype=np.uint8)
+
+
+def lz4_decompress(data, cap):
+    """LZ4 block decode; returns the decoded bytes or raises ValueError(code)."""
+    src = _u8(data)
+    dst = np.empty(max(cap, 1), dtype=np.uint8)
+    n = L.lsio_oracle_lz4_decompress(src.ctypes.data, len(src), dst.ctypes.data, cap)
+    if n < 0:
+        raise ValueError(n)
+    return dst[:n]
+
+
+def lz4_compress(data):
+    src = _u8(data)
+    cap = L.lsio_oracle_lz4_compress_bound(len(src))
+    dst = np.empty(cap, dtype=np.uint8)
+    n = L.lsio_oracle_lz4_compress(src.ctypes.data, len(src), dst.ctypes.data, cap)
+    assert n >= 0
+    return dst[:n].copy()
+
+
+def shuffle(data, elem):
+    src = _u8(data)
+    dst = np.empty_like(src)
+    L.lsio_oracle_shuffle(src.ctypes.data, dst.ctypes.data, len(src), elem)
+    return dst
+
+
+def unshuffle(data, elem):
+    src = _u8(data)
+    dst = np.empty_like(src)
+    L.lsio_oracle_unshuffle(src.ctypes.data, dst.ctypes.data, len(src), elem)
+    return dst

@@ -1,0 +1,219 @@
+"""GPU parity tests of the codec layer (-m gpu): csrc/codecs.cu through the C ABI (include/lsio_codecs.h)
+against the oracle (oracle/lsio_codecs_oracle.c) and liblz4's own vectors, bit-exact, then end to end
+behind the I/O path: encoded Zarr-like chunks in files -> get_ranges -> HBM -> CodecPipeline.decode."""
+import json
+import os
+import struct
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_codec_vectors import RECIPES, recipe_bytes  # noqa: E402
+
+
+def _to_dev(torch, data, lead=0, slack=64):
+    """Device copy of `data` starting `lead` bytes into a fresh buffer (to exercise misalignment)."""
+    t = torch.zeros(lead + len(data) + slack, dtype=torch.uint8, device="cuda:0")
+    if len(data):
+        t[lead:lead + len(data)] = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+    return t
+
+
+def _lz4_batch(lsio, torch, blocks, caps, src_lead=0, dst_lead=0):
+    """Decode `blocks` (compressed bytes) in one launch. Returns (results, outputs with 32-byte guard bands)."""
+    srcs = [_to_dev(torch, b, lead=(src_lead + 3 * i) % 16 if src_lead else 0) for i, b in enumerate(blocks)]
+    leads = [(src_lead + 3 * i) % 16 if src_lead else 0 for i in range(len(blocks))]
+    outs = [torch.full((32 + dst_lead + c + 32,), 0xAB, dtype=torch.uint8, device="cuda:0") for c in caps]
+    items = lsio.codecs.make_items([s.data_ptr() + l for s, l in zip(srcs, leads)], [o.data_ptr() + 32 + dst_lead for o in outs],
+                                   [len(b) for b in blocks], caps)
+    res = lsio.codecs.lz4_decompress(items)
+    torch.cuda.synchronize()
+    return res, [o.cpu().numpy() for o in outs]
+
+
+def test_lz4_golden_vectors_from_liblz4(lsio, oracle, cuda_dev):
+    import torch
+
+    vs = json.load(open(os.path.join(HERE, "golden", "codecs.json")))["vectors"]
+    blocks = [bytes.fromhex(v["lz4_hex"]) for v in vs]
+    for src_lead, dst_lead in ((0, 0), (5, 3)):
+        res, outs = _lz4_batch(lsio, torch, blocks, [v["decoded_len"] for v in vs], src_lead, dst_lead)
+        for v, r, o in zip(vs, res, outs):
+            want = recipe_bytes(v)
+            assert r["status"] == 0 and r["out_len"] == len(want), (v["kind"], r)
+            body = o[32 + dst_lead:32 + dst_lead + len(want)]
+            assert body.tobytes() == want, v["kind"]
+            assert oracle.crc32c(body) == v["decoded_crc32c"]
+            assert np.all(o[:32 + dst_lead] == 0xAB) and np.all(o[32 + dst_lead + len(want):] == 0xAB)  # nothing outside dst
+
+
+def test_lz4_random_blocks_match_the_oracle(lsio, oracle, cuda_dev):
+    """Many blocks per launch, both compressors (oracle's greedy one and liblz4), ragged sizes, misaligned."""
+    import pyarrow as pa
+    import torch
+
+    codec = pa.Codec("lz4_raw")
+    rng = np.random.default_rng(7)
+    datas = []
+    for i in range(300):
+        n = int(rng.integers(1, 40000))
+        kind = i % 5
+        if kind == 0:
+            d = rng.integers(0, int(rng.integers(2, 256)), n, dtype=np.uint8).tobytes()
+        elif kind == 1:
+            d = np.cumsum(rng.integers(-2, 3, n // 4 + 1)).astype("<f4").tobytes()[:n]
+        elif kind == 2:
+            d = oracle.shuffle(np.cumsum(rng.integers(-2, 3, n // 4 + 1)).astype("<i4").tobytes(), 4).tobytes()[:n]
+        elif kind == 3:
+            p = int(rng.integers(1, 70))
+            d = (rng.integers(0, 256, p, dtype=np.uint8).tobytes() * (n // p + 1))[:n]
+        else:
+            d = bytes(n) if i % 2 else rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        datas.append(d)
+    datas += [rng.integers(0, 3, n, dtype=np.uint8).tobytes() for n in range(1, 40)]
+    blocks = [oracle.lz4_compress(d).tobytes() if i % 2 else codec.compress(d).to_pybytes() for i, d in enumerate(datas)]
+    for b, d in zip(blocks, datas):
+        assert oracle.lz4_decompress(b, len(d)).tobytes() == d
+    res, outs = _lz4_batch(lsio, torch, blocks, [len(d) for d in datas], src_lead=1, dst_lead=7)
+    for i, (d, r, o) in enumerate(zip(datas, res, outs)):
+        assert r["status"] == 0 and r["out_len"] == len(d), (i, r, len(d))
+        assert o[39:39 + len(d)].tobytes() == d, i
+        assert np.all(o[:39] == 0xAB) and np.all(o[39 + len(d):] == 0xAB), i
+
+
+def test_lz4_large_block_and_long_runs(lsio, oracle, cuda_dev):
+    import torch
+
+    rng = np.random.default_rng(9)
+    d = (rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes() + bytes(1_000_000) + rng.integers(0, 5, 700_000, dtype=np.uint8).tobytes()
+         + rng.integers(0, 256, 50_000, dtype=np.uint8).tobytes() * 4)
+    b = oracle.lz4_compress(d).tobytes()
+    res, outs = _lz4_batch(lsio, torch, [b], [len(d) + 100])  # cap larger than needed: out_len reports the real size
+    assert res[0]["status"] == 0 and res[0]["out_len"] == len(d)
+    assert outs[0][32:32 + len(d)].tobytes() == d and np.all(outs[0][32 + len(d):] == 0xAB)
+
+
+def test_lz4_malformed_blocks_report_their_own_status(lsio, oracle, cuda_dev):
+    import torch
+
+    C = lsio.codecs
+    good = recipe_bytes({"kind": "lowent", "n": 3000, "seed": 2, "alphabet": 4})
+    cg = oracle.lz4_compress(good).tobytes()
+    blocks = [cg, cg, cg[:len(cg) // 2], bytes([0x10, 0x41, 0x00, 0x00, 0x50, 1, 2, 3, 4, 5]), bytes([0x10, 0x41, 0x02, 0x00, 0x50, 1, 2, 3, 4, 5]),
+              bytes([0xF0, 0xFF]), cg]
+    caps = [len(good), len(good) - 1, len(good), 100, 100, 100, len(good)]
+    res, outs = _lz4_batch(lsio, torch, blocks, caps)
+    st = [int(r["status"]) for r in res]
+    assert st[0] == 0 and st[6] == 0 and outs[0][32:32 + len(good)].tobytes() == good and outs[6][32:32 + len(good)].tobytes() == good
+    assert st[1] == 2  # LSIO_CODEC_ERR_OUTPUT
+    try:
+        want = oracle.lz4_decompress(blocks[2], caps[2])
+        assert st[2] == 0 and res[2]["out_len"] == len(want)
+    except ValueError:
+        assert st[2] == 1
+    assert st[3] == 3 and st[4] == 3 and st[5] == 1
+    for o, c in zip(outs, caps):
+        assert np.all(o[:32] == 0xAB) and np.all(o[32 + c:] == 0xAB)  # a failing block never writes outside its dst
+    # an empty block is an error, not a hang; an empty batch is a no-op
+    t = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
+    res = C.lz4_decompress(C.make_items([t.data_ptr()], [t.data_ptr() + 32], [0], [10]))
+    assert res[0]["status"] == 1
+    assert len(C.lz4_decompress(C.make_items([], [], [], []))) == 0
+
+
+@pytest.mark.parametrize("elem", [1, 2, 3, 4, 8, 16, 12])
+def test_shuffle_and_unshuffle_match_the_oracle(lsio, oracle, cuda_dev, elem):
+    import torch
+
+    C = lsio.codecs
+    rng = np.random.default_rng(elem)
+    sizes = [0, 1, elem, 16 * elem, 4096, 16384, 16384 + 16, 65536 + 4 * elem, 100_003, 1 << 20, (1 << 20) + elem + 1]
+    for src_lead, dst_lead in ((0, 0), (0, 8), (4, 0), (1, 5)):
+        datas = [rng.integers(0, 256, n, dtype=np.uint8) for n in sizes]
+        srcs = [_to_dev(torch, d.tobytes(), lead=src_lead) for d in datas]
+        for forward in (False, True):
+            outs = [torch.full((32 + dst_lead + len(d) + 32,), 0xCD, dtype=torch.uint8, device="cuda:0") for d in datas]
+            items = C.make_items([s.data_ptr() + src_lead for s in srcs], [o.data_ptr() + 32 + dst_lead for o in outs], [len(d) for d in datas])
+            (C.shuffle if forward else C.unshuffle)(items, elem)
+            torch.cuda.synchronize()
+            for d, o in zip(datas, outs):
+                h = o.cpu().numpy()
+                want = (oracle.shuffle if forward else oracle.unshuffle)(d, elem)
+                assert np.array_equal(h[32 + dst_lead:32 + dst_lead + len(d)], want), (elem, len(d), forward, src_lead, dst_lead)
+                assert np.all(h[:32 + dst_lead] == 0xCD) and np.all(h[32 + dst_lead + len(d):] == 0xCD)
+
+
+def test_shuffle_round_trip_at_full_size(lsio, cuda_dev):
+    """Size-independent property at a size the oracle is not run on: unshuffle(shuffle(x)) == x, 1 GiB."""
+    import torch
+
+    C = lsio.codecs
+    n_chunks, nbytes = 256, 4 << 20
+    x = torch.randint(0, 256, (n_chunks, nbytes), dtype=torch.uint8, device="cuda:0")
+    y, z = torch.empty_like(x), torch.empty_like(x)
+    step = np.arange(n_chunks, dtype=np.uint64) * np.uint64(nbytes)
+    for elem in (2, 4, 8):
+        C.shuffle(C.make_items(x.data_ptr() + step, y.data_ptr() + step, np.full(n_chunks, nbytes)), elem)
+        C.unshuffle(C.make_items(y.data_ptr() + step, z.data_ptr() + step, np.full(n_chunks, nbytes)), elem)
+        assert torch.equal(x, z)
+        assert not torch.equal(x, y)
+        # plane 0 of chunk 0 holds byte 0 of every element
+        assert torch.equal(y[0, :nbytes // elem], x[0, ::elem])
+
+
+def test_zarr_like_chunks_through_the_whole_path(lsio, oracle, cuda_dev, data_dir):
+    """Chunks encoded as a Zarr codec chain [Shuffle(4), LZ4, crc32c] packed back to back in shard files ->
+    get_ranges (unaligned ranges) -> HBM -> CodecPipeline.decode -> the original float32 arrays, bit-exact."""
+    import torch
+
+    C = lsio.codecs
+    rng = np.random.default_rng(21)
+    chunk_shape, n_files, per_file = (64, 64), 6, 20
+    nbytes = int(np.prod(chunk_shape)) * 4
+    arrays, ranges, fns = {}, {}, []
+    for f in range(n_files):
+        fn = os.path.join(data_dir, f"shard{f}")
+        fns.append(fn)
+        blob = bytearray(rng.integers(0, 256, int(rng.integers(1, 700)), dtype=np.uint8).tobytes())  # unaligned start
+        rs = []
+        for k in range(per_file):
+            a = (np.cumsum(rng.standard_normal(chunk_shape), axis=1) * 0.01).astype("<f4").round(2)
+            arrays[(f, k)] = a
+            body = oracle.lz4_compress(oracle.shuffle(a.tobytes(), 4)).tobytes()
+            stored = struct.pack("<I", nbytes) + body  # numcodecs.LZ4 framing
+            stored += struct.pack("<I", oracle.crc32c(stored))  # Zarr v3 crc32c codec
+            rs.append((len(blob), len(blob) + len(stored)))
+            blob += stored
+        blob += b"tail"
+        with open(fn, "wb") as fh:
+            fh.write(blob)
+        ranges[f] = rs
+    pipe = C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], nbytes)
+    with lsio.IoUringCuda(3, arena_bytes=128 << 20, staging_bytes=16 << 20) as u:
+        for f in range(n_files):
+            u.get_ranges(fns[f], ranges[f], [(f << 32) | k for k in range(per_file)])
+        chunks = [u.completion().recv_timeout(20.0) for _ in range(n_files * per_file)]
+        assert all(c.is_ok() for c in chunks)
+        out = pipe.decode(chunks)
+        assert out.shape == (n_files * per_file, nbytes) and out.is_cuda
+        got = out.view(torch.float32).reshape(-1, *chunk_shape).cpu().numpy()
+        for i, c in enumerate(chunks):
+            assert np.array_equal(got[i], arrays[(c.user_data >> 32, c.user_data & 0xFFFFFFFF)]), c.user_data
+        # a corrupted chunk is caught by the fused CRC without touching the data again
+        with open(fns[0], "r+b") as fh:
+            fh.seek(ranges[0][3][0] + 40)
+            b = fh.read(1)
+            fh.seek(ranges[0][3][0] + 40)
+            fh.write(bytes([b[0] ^ 0x10]))
+            fh.flush()
+            os.fsync(fh.fileno())
+        u.get_ranges(fns[0], ranges[0], list(range(per_file)))
+        again = [u.completion().recv_timeout(20.0) for _ in range(per_file)]
+        with pytest.raises(C.CodecError, match="crc32c"):
+            pipe.decode(again)
+        ok = [c for c in again if c.user_data != 3]
+        assert pipe.decode(ok).shape[0] == per_file - 1
