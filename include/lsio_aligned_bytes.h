@@ -70,6 +70,9 @@ int64_t lsio_aligned_bytes_copy_to_host(const lsio_aligned_bytes* self, void* ds
 void lsio_aligned_bytes_drop(lsio_aligned_bytes* self);
 /* Drops the `buffer` of n consecutive lsio_output-like records: views[i] may be NULL. */
 void lsio_aligned_bytes_drop_many(lsio_aligned_bytes* const* views, size_t n);
+/* as_ptr() and len() of n views in one call (NULL views give 0, 0): what a consumer that hands a whole batch
+ * of chunks to a kernel needs (the codec layer, lsio_codecs.h). */
+void lsio_aligned_bytes_describe_many(lsio_aligned_bytes* const* views, size_t n, uint64_t* ptrs, uint64_t* lens);
 
 
 /* ---- DLPack export (the Python / PyTorch surface the reference only plans,

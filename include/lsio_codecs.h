@@ -58,11 +58,14 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
  * Host `items`; uploads, launches one kernel on `stream`, synchronises. */
 int lsio_codecs_unshuffle(int device, const lsio_codec_item* items, size_t n, uint32_t elem_size, void* stream);
 int lsio_codecs_shuffle(int device, const lsio_codec_item* items, size_t n, uint32_t elem_size, void* stream);
-/* Asynchronous forms: `items_dev` device-accessible, `tile_prefix_dev` = n+1 uint32 exclusive prefix sums
- * of lsio_codecs_shuffle_tiles(src_len) per item (the last entry is the launch's tile count `n_tiles`). */
+/* Asynchronous form: `items_dev` device-accessible; `tile_map_dev` = n_tiles pairs {item index, tile index
+ * within the item} of uint32, one per 16 KiB tile of every item, in launch order -- built on the host with
+ * lsio_codecs_shuffle_tile_map (returns the tile count; writes at most cap_tiles pairs; tile_map may be NULL to
+ * only count).  Enqueues exactly one kernel launch on `stream`; forward != 0 shuffles, 0 unshuffles. */
 uint32_t lsio_codecs_shuffle_tiles(uint32_t src_len);
-int lsio_codecs_unshuffle_async(int device, const lsio_codec_item* items_dev, const uint32_t* tile_prefix_dev, size_t n, uint32_t n_tiles,
-                                uint32_t elem_size, int forward, void* stream);
+int64_t lsio_codecs_shuffle_tile_map(const uint32_t* src_lens, size_t n, uint32_t* tile_map, size_t cap_tiles);
+int lsio_codecs_unshuffle_async(int device, const lsio_codec_item* items_dev, const uint32_t* tile_map_dev, uint32_t n_tiles, uint32_t elem_size,
+                                int forward, void* stream);
 
 /* Zarr v3 `crc32c` codec: CRC-32C over (bytes || CRC-32C(bytes) as 4 LE bytes) is this constant whatever
  * the bytes are.  A chunk stored with that codec is therefore verified by comparing the CRC the pack

@@ -182,6 +182,8 @@ lib.lsio_completion_recv_batch.restype = ctypes.c_int
 lib.lsio_completion_recv_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(COutput), ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
 lib.lsio_aligned_bytes_drop_many.restype = None
 lib.lsio_aligned_bytes_drop_many.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+lib.lsio_aligned_bytes_describe_many.restype = None
+lib.lsio_aligned_bytes_describe_many.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
 lib.lsio_probe_read_ceiling.restype = ctypes.c_int
 lib.lsio_probe_read_ceiling.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
                                         ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]

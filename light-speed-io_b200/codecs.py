@@ -24,8 +24,9 @@ for _name, _res, _args in [
     ("lsio_codecs_unshuffle", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_void_p]),
     ("lsio_codecs_shuffle", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_void_p]),
     ("lsio_codecs_shuffle_tiles", ctypes.c_uint32, [ctypes.c_uint32]),
-    ("lsio_codecs_unshuffle_async", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32,
-                                                   ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]),
+    ("lsio_codecs_shuffle_tile_map", ctypes.c_int64, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]),
+    ("lsio_codecs_unshuffle_async", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                                   ctypes.c_int, ctypes.c_void_p]),
     ("lsio_codecs_crc32c_trailer_ok", ctypes.c_int, [ctypes.c_uint32]),
 ]:
     getattr(N.lib, _name).restype = _res
@@ -60,6 +61,17 @@ def unshuffle(items, elem_size, device=0, stream=None):
 def shuffle(items, elem_size, device=0, stream=None):
     items = np.ascontiguousarray(items, dtype=ITEM_DTYPE)
     N.check(N.lib.lsio_codecs_shuffle(int(device), items.ctypes.data, len(items), int(elem_size), _stream_ptr(stream)), "shuffle")
+
+
+def shuffle_tile_map(src_lens):
+    """The {item, tile} table lsio_codecs_unshuffle_async wants, as an (n_tiles, 2) uint32 array."""
+    lens = np.ascontiguousarray(src_lens, dtype=np.uint32)
+    n_tiles = N.lib.lsio_codecs_shuffle_tile_map(lens.ctypes.data, len(lens), None, 0)
+    if n_tiles < 0:
+        raise CodecError(f"shuffle_tile_map: {n_tiles}")
+    tm = np.zeros((n_tiles, 2), dtype=np.uint32)
+    N.lib.lsio_codecs_shuffle_tile_map(lens.ctypes.data, len(lens), tm.ctypes.data, n_tiles)
+    return tm
 
 
 def crc32c_trailer_ok(crc32c_of_chunk_with_trailer):
@@ -103,20 +115,40 @@ class CodecPipeline:
     def decode(self, chunks, stream=None):
         """chunks: lsio Chunk items (device views, kept alive by the caller until this returns).
         Returns the decoded (n, decoded_nbytes) uint8 tensor; raises CodecError naming the first bad chunk."""
-        import torch
-
-        n = len(chunks)
-        dev = torch.device("cuda", self.device)
         src = np.array([c.buffer.as_ptr() for c in chunks], dtype=np.uint64)
         src_len = np.array([c.buffer.len() for c in chunks], dtype=np.int64)
+        if any(isinstance(c, Crc32c) for c in self.codecs) and any(c.crc32c is None for c in chunks):
+            raise CodecError("Crc32c needs the backend's fused CRC-32C (checksum=CHECKSUM_CRC32C)")
+        crcs = np.array([c.crc32c or 0 for c in chunks], dtype=np.uint32)
+        return self._decode(src, src_len, crcs, np.array([c.user_data for c in chunks], dtype=np.uint64), stream)
+
+    def decode_records(self, records, stream=None):
+        """The same for a record array from Receiver.recv_batch (the C `lsio_output` layout): no per-chunk Python
+        work.  Every record must be an Ok chunk; the caller still owns the buffers (Receiver.drop_buffers)."""
+        if len(records) and np.any(records["status"] != 0):
+            i = int(np.flatnonzero(records["status"] != 0)[0])
+            raise CodecError(f"record {i} is an error item: {bytes(records['context'][i]).split(b'\0')[0].decode(errors='replace')}")
+        n = len(records)
+        views = np.ascontiguousarray(records["chunk"]["buffer"], dtype=np.uint64)
+        src, lens = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+        N.lib.lsio_aligned_bytes_describe_many(views.ctypes.data, n, src.ctypes.data, lens.ctypes.data)
+        if any(isinstance(c, Crc32c) for c in self.codecs) and n and not np.all(records["checksums"] & N.CHECKSUM_CRC32C):
+            raise CodecError("Crc32c needs the backend's fused CRC-32C (checksum=CHECKSUM_CRC32C)")
+        return self._decode(src, lens.astype(np.int64), np.ascontiguousarray(records["crc32c"], dtype=np.uint32),
+                            np.ascontiguousarray(records["chunk"]["user_data"], dtype=np.uint64), stream)
+
+    def _decode(self, src, src_len, crcs, user_data, stream):
+        import torch
+
+        n = len(src)
+        dev = torch.device("cuda", self.device)
         cur = None  # tensor holding the current stage's rows (None: still the chunk buffers themselves)
         for codec in reversed(self.codecs):
             if isinstance(codec, Crc32c):
-                for i, c in enumerate(chunks):
-                    if c.crc32c is None:
-                        raise CodecError("Crc32c needs the backend's fused CRC-32C (checksum=CHECKSUM_CRC32C)")
-                    if src_len[i] < 4 or not crc32c_trailer_ok(c.crc32c):
-                        raise CodecError(f"chunk {i} (user_data={c.user_data}): crc32c trailer mismatch")
+                bad = np.flatnonzero((crcs != CRC32C_RESIDUE) | (src_len < 4))
+                if len(bad):
+                    i = int(bad[0])
+                    raise CodecError(f"chunk {i} (user_data={int(user_data[i])}): crc32c trailer mismatch")
                 src_len = src_len - 4
             elif isinstance(codec, LZ4):
                 out = torch.empty((n, self.decoded_nbytes), dtype=torch.uint8, device=dev)
@@ -128,7 +160,7 @@ class CodecPipeline:
                 bad = np.flatnonzero((res["status"] != 0) | (res["out_len"] != self.decoded_nbytes))
                 if len(bad):
                     i = int(bad[0])
-                    raise CodecError(f"chunk {i} (user_data={chunks[i].user_data}): lz4 {STATUS_TEXT.get(int(res['status'][i]), '?')}, "
+                    raise CodecError(f"chunk {i} (user_data={int(user_data[i])}): lz4 {STATUS_TEXT.get(int(res['status'][i]), '?')}, "
                                      f"{int(res['out_len'][i])} of {self.decoded_nbytes} bytes")
                 cur, src = out, dst
                 src_len = np.full(n, self.decoded_nbytes, dtype=np.int64)

@@ -206,5 +206,11 @@ void lsio_aligned_bytes_drop(lsio_aligned_bytes* self) { delete self; }
 void lsio_aligned_bytes_drop_many(lsio_aligned_bytes* const* views, size_t n) {
     for (size_t i = 0; i < n; i++) delete views[i];
 }
+void lsio_aligned_bytes_describe_many(lsio_aligned_bytes* const* views, size_t n, uint64_t* ptrs, uint64_t* lens) {
+    for (size_t i = 0; i < n; i++) {
+        ptrs[i] = views[i] ? (uint64_t)(uintptr_t)(views[i]->buf->buf + views[i]->start) : 0;
+        lens[i] = views[i] ? views[i]->end - views[i]->start : 0;
+    }
+}
 
 }  // extern "C"

@@ -3,16 +3,17 @@
 // README.md:68-70) and holds no code for it; formats follow the published LZ4 block format and
 // numcodecs.Shuffle.  Product code: no oracle, no CPU fallback.
 //
-//   lz4_kernel        one warp per block.  LZ4 is a serial token stream, so the parallelism is (a) across
-//                     blocks and (b) inside each copy: every lane parses the same tokens from a shared-memory
-//                     window of the compressed input (refilled with coalesced 16-byte loads), literals and
-//                     matches are copied by the 32 lanes.  A match that overlaps its own output
+//   lz4_kernel        one team of 8 (or 32) lanes per block.  LZ4 is a serial token stream, so the parallelism
+//                     is (a) across blocks and (b) inside each copy: every lane of the team parses the same
+//                     tokens from a shared-memory window of the compressed input (refilled with coalesced
+//                     16-byte loads), literals and matches are copied by the team's lanes.  A match that overlaps its own output
 //                     (offset < length) is periodic, so byte i is out[op - offset + i % offset]: every byte
 //                     of a match is independent of the others and only depends on bytes before `op`.
 //   shuffle_kernel    byte (un)shuffle as a tiled gather: each thread assembles one 16-byte output vector from
 //                     16/E bytes of each of the E byte planes (register transpose, PRMT), warp accesses are
 //                     contiguous in every plane and in the output.  HBM-bound: 2 bytes moved per byte.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.hpp"
@@ -24,66 +25,107 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 // LZ4 block decode
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kLzWarps = 8;     // blocks decoded per CTA
-constexpr int kLzWin = 1024;    // bytes of compressed input staged per warp
+// Real chunks decode to very short sequences (measured on shuffled float32 data: 7.7 output bytes per
+// sequence, 1.6 literal + 6 match bytes), so the kernel is bound by instructions ISSUED per sequence, not by
+// bytes: a TEAM of T lanes (8 by default, four blocks per warp) decodes one block, every lane of the team
+// parsing the same tokens.  T = 32 is kept for launches with few blocks.
+constexpr int kLzThreads = 256;
+constexpr int kLzWin = 512;  // bytes of compressed input staged per team
 
+template <int T>
 struct LzIn {
     const uint8_t* src;  // compressed bytes
     uint32_t n;          // their count
     uint32_t lead;       // src - (src rounded down to 16): window coordinates are relative to the aligned base
-    uint8_t* win;        // this warp's shared-memory window
+    uint8_t* win;        // this team's shared-memory window
     uint32_t ws;         // window start (multiple of 16, aligned-base coordinates)
-    int lane;
+    unsigned mask;       // the team's lanes
+    int l;               // lane within the team
 };
 
-// Stage [ws, ws + kLzWin) of the aligned-base coordinates: 64 vectors, two per lane.
-__device__ __forceinline__ void lz_fill(LzIn& in) {
-    const uint8_t* abase = in.src - in.lead;
-    __syncwarp();
+// Stage [ws, ws + kLzWin) of the aligned-base coordinates with coalesced 16-byte loads.
+// Out of line and by value: keeps the per-sequence loop compact and the caller's state in registers.
+template <int T>
+__device__ __noinline__ void lz_fill_window(const uint8_t* abase, uint32_t lead, uint32_t n, uint8_t* win, uint32_t ws, unsigned mask, int l) {
+    __syncwarp(mask);
 #pragma unroll
-    for (int r = 0; r < kLzWin / 16 / 32; r++) {
-        const uint32_t voff = in.ws + 16u * (uint32_t)(in.lane + 32 * r);  // aligned-base coordinate of this vector
+    for (int r = 0; r < kLzWin / 16 / T; r++) {
+        const uint32_t voff = ws + 16u * (uint32_t)(l + T * r);  // aligned-base coordinate of this vector
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (voff >= in.lead && voff + 16 <= in.lead + in.n) {
+        if (voff >= lead && voff + 16 <= lead + n) {
             v = *reinterpret_cast<const uint4*>(abase + voff);
-        } else if (voff + 16 > in.lead && voff < in.lead + in.n) {  // edge vector: only bytes inside [src, src+n)
-            uint8_t b[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) b[k] = (voff + k >= in.lead && voff + k < in.lead + in.n) ? abase[voff + k] : (uint8_t)0;
-            v.x = b[0] | b[1] << 8 | b[2] << 16 | (uint32_t)b[3] << 24;
-            v.y = b[4] | b[5] << 8 | b[6] << 16 | (uint32_t)b[7] << 24;
-            v.z = b[8] | b[9] << 8 | b[10] << 16 | (uint32_t)b[11] << 24;
-            v.w = b[12] | b[13] << 8 | b[14] << 16 | (uint32_t)b[15] << 24;
+        } else if (voff + 16 > lead && voff < lead + n) {  // edge vector: only bytes inside [src, src+n)
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 16; k++)
+                if (voff + k >= lead && voff + k < lead + n) w[k >> 2] |= (uint32_t)abase[voff + k] << (8 * (k & 3));
+            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>(in.win + 16 * (in.lane + 32 * r)) = v;
+        *reinterpret_cast<uint4*>(win + 16 * (l + T * r)) = v;
     }
-    __syncwarp();
+    __syncwarp(mask);
 }
-// Byte `ip` of the compressed stream (ip < n, uniform across the warp).
-__device__ __forceinline__ uint32_t lz_byte(LzIn& in, uint32_t ip) {
+template <int T>
+__device__ __forceinline__ void lz_fill(LzIn<T>& in) {
+    lz_fill_window<T>(in.src - in.lead, in.lead, in.n, in.win, in.ws, in.mask, in.l);
+}
+// Byte `ip` of the compressed stream (uniform across the team), refilling the window when it has moved on.
+template <int T>
+__device__ __forceinline__ uint32_t lz_byte(LzIn<T>& in, uint32_t ip) {
     const uint32_t p = ip + in.lead;
-    if (p - in.ws >= (uint32_t)kLzWin) {  // also true when p < ws (never happens: ip only grows)
+    if (p - in.ws >= (uint32_t)kLzWin) {
         in.ws = p & ~15u;
         lz_fill(in);
     }
     return in.win[p - in.ws];
 }
 
-__global__ void __launch_bounds__(kLzWarps * 32) lz4_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
-                                                            lsio_codec_result* __restrict__ results) {
-    __shared__ __align__(16) uint8_t s_win[kLzWarps][kLzWin];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t idx = blockIdx.x * kLzWarps + warp;
-    if (idx >= n_items) return;
+// Cooperative copy of a long run (literals from the compressed stream, or a match that does not overlap its
+// own output): destination-aligned 32-bit stores, source words realigned with a funnel shift.
+template <int T>
+__device__ __forceinline__ void lz_copy_long(uint8_t* d, const uint8_t* s, uint32_t len, int l) {
+    const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(d) & 3)) & 3u;  // len >= 64 > head
+    if ((uint32_t)l < head) d[l] = s[l];
+    d += head;
+    s += head;
+    len -= head;
+    const uint32_t words = len >> 2, sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(d);
+    if (sh == 0) {
+        for (uint32_t i = l; i < words; i += T) dw[i] = sw[i];
+    } else {
+        // sw[i + 1] is the aligned word that holds the last byte needed: never beyond the word of a valid byte
+        for (uint32_t i = l; i < words; i += T) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
+    }
+    const uint32_t done = words << 2;
+    if ((uint32_t)l < len - done) d[done + l] = s[done + l];
+}
+
+// One block advances by one sequence per ~900 cycles whatever the team size (measured: 16 MB/s per block on
+// shuffled float32 data; a dependent chain of ~80 instructions and four shared-memory reads per sequence), so
+// throughput comes from blocks in flight.  Tried and rejected: mirroring the last 16/32 KiB of output in shared
+// memory so that matches never wait for L2 -- no gain per block (4.0 -> 4.2 GB/s at 256 blocks of 1 MiB; the
+// match reads are not on the critical path), and the lost occupancy cost 2-5x at larger launches.
+template <int T>
+__global__ void __launch_bounds__(kLzThreads) lz4_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
+                                                         lsio_codec_result* __restrict__ results) {
+    constexpr int kTeams = kLzThreads / T;
+    __shared__ __align__(16) uint8_t s_lz[kTeams * kLzWin];
+    const int team = threadIdx.x / T, l = threadIdx.x % T;
+    const uint32_t idx = blockIdx.x * kTeams + team;
+    if (idx >= n_items) return;  // whole teams leave: every later sync is masked to one team
     const lsio_codec_item it = items[idx];
-    LzIn in;
+    LzIn<T> in;
     in.src = reinterpret_cast<const uint8_t*>(it.src);
     in.n = it.src_len;
     in.lead = (uint32_t)(it.src & 15);
-    in.win = s_win[warp];
+    in.win = s_lz + team * kLzWin;
     in.ws = 0;
-    in.lane = lane;
+    in.mask = T == 32 ? 0xFFFFFFFFu : (((1u << (T & 31)) - 1u) << ((threadIdx.x & 31) / T * T));
+    in.l = l;
     uint8_t* dst = reinterpret_cast<uint8_t*>(it.dst);
+    __builtin_assume(__isGlobal(dst));  // LDG/STG instead of generic loads and stores
+    __builtin_assume(__isGlobal(in.src));
     const uint32_t n = it.src_len, cap = it.dst_cap;
     uint32_t ip = 0, op = 0;
     int status = LSIO_CODEC_OK;
@@ -91,9 +133,29 @@ __global__ void __launch_bounds__(kLzWarps * 32) lz4_kernel(const lsio_codec_ite
     else lz_fill(in);
     while (status == LSIO_CODEC_OK) {
         if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
-        const uint32_t token = lz_byte(in, ip++);
-        uint32_t lit = token >> 4;
-        if (lit == 15) {
+        // one check per sequence: token + up to 14 literals + offset + one length byte inside the window
+        uint32_t q = ip + in.lead - in.ws;
+        if (q + 20 > (uint32_t)kLzWin) {
+            in.ws = (ip + in.lead) & ~15u;
+            lz_fill(in);
+            q = ip + in.lead - in.ws;
+        }
+        const uint8_t* w = in.win + q;
+        const uint32_t token = w[0];
+        uint32_t lit = token >> 4, ml = token & 15, offset;
+        if (lit < 15) {  // the common case: everything up to the offset sits in the window
+            if (lit > n - ip - 1) { status = LSIO_CODEC_ERR_INPUT; break; }
+            if (lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
+            if ((uint32_t)l < lit) dst[op + l] = w[1 + l];
+            if (T < 16 && (uint32_t)l + T < lit) dst[op + l + T] = w[1 + l + T];
+            ip += 1 + lit;
+            op += lit;
+            if (ip == n) break;  // the last sequence has literals only
+            if (n - ip < 2) { status = LSIO_CODEC_ERR_INPUT; break; }
+            offset = w[1 + lit] | (uint32_t)w[2 + lit] << 8;
+            ip += 2;
+        } else {
+            ip++;
             uint32_t b;
             do {
                 if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
@@ -101,27 +163,22 @@ __global__ void __launch_bounds__(kLzWarps * 32) lz4_kernel(const lsio_codec_ite
                 lit += b;
             } while (b == 255);
             if (status) break;
-        }
-        if (lit > n - ip) { status = LSIO_CODEC_ERR_INPUT; break; }
-        if (lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
-        if (lit) {
-            const uint32_t p = ip + in.lead;
-            if (p >= in.ws && p + lit <= in.ws + (uint32_t)kLzWin) {  // short runs: straight from the window
-                const uint8_t* w = in.win + (p - in.ws);
-                for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = w[i];
+            if (lit > n - ip) { status = LSIO_CODEC_ERR_INPUT; break; }
+            if (lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
+            if (lit >= 64) {
+                lz_copy_long<T>(dst + op, in.src + ip, lit, l);
             } else {
                 const uint8_t* s = in.src + ip;
-                for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = s[i];
+                for (uint32_t i = l; i < lit; i += T) dst[op + i] = s[i];
             }
             ip += lit;
             op += lit;
+            if (ip == n) break;
+            if (n - ip < 2) { status = LSIO_CODEC_ERR_INPUT; break; }
+            offset = lz_byte(in, ip);
+            offset |= lz_byte(in, ip + 1) << 8;
+            ip += 2;
         }
-        if (ip == n) break;  // the last sequence has literals only
-        if (n - ip < 2) { status = LSIO_CODEC_ERR_INPUT; break; }
-        uint32_t offset = lz_byte(in, ip);
-        offset |= lz_byte(in, ip + 1) << 8;
-        ip += 2;
-        uint32_t ml = token & 15;
         if (ml == 15) {
             uint32_t b;
             do {
@@ -134,17 +191,21 @@ __global__ void __launch_bounds__(kLzWarps * 32) lz4_kernel(const lsio_codec_ite
         ml += 4;
         if (offset == 0 || offset > op) { status = LSIO_CODEC_ERR_OFFSET; break; }
         if (ml > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
-        __syncwarp();  // the literals above (and everything before them) are visible to every lane's match reads
+        __syncwarp(in.mask);  // the literals above (and everything before them) are visible to the team's match reads
         const uint8_t* m = dst + op - offset;
         if (offset >= ml) {
-            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = m[i];
-        } else {  // overlapping match = periodic extension of the last `offset` bytes
-            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = m[i % offset];
+            if (ml >= 64) {
+                lz_copy_long<T>(dst + op, m, ml, l);
+            } else {
+                for (uint32_t i = l; i < ml; i += T) dst[op + i] = m[i];
+            }
+        } else {  // a match overlapping its own output is the periodic extension of the last `offset` bytes
+            for (uint32_t i = l; i < ml; i += T) dst[op + i] = m[i % offset];
         }
         op += ml;
-        __syncwarp();
+        __syncwarp(in.mask);
     }
-    if (lane == 0) {
+    if (l == 0) {
         results[idx].out_len = op;
         results[idx].status = status;
     }
@@ -156,66 +217,69 @@ __global__ void __launch_bounds__(kLzWarps * 32) lz4_kernel(const lsio_codec_ite
 constexpr uint32_t kShufTile = 16384;  // bytes of one buffer handled by one CTA
 constexpr int kShufThreads = 256;
 
-template <int E> struct PlaneT;
-template <> struct PlaneT<2> { using T = uint64_t; };
-template <> struct PlaneT<4> { using T = uint32_t; };
-template <> struct PlaneT<8> { using T = uint16_t; };
-template <> struct PlaneT<16> { using T = uint8_t; };
+template <int V> struct UIntOf;
+template <> struct UIntOf<4> { using T = uint32_t; };
+template <> struct UIntOf<8> { using T = uint64_t; };
 
-// Output vector `e0 / V` of an unshuffle: elements [e0, e0 + V), V = 16 / E, gathered from the E planes.
-template <int E>
-__device__ __forceinline__ uint4 unshuffle_vec(const uint8_t* __restrict__ src, uint32_t cnt, uint32_t e0) {
-    using T = typename PlaneT<E>::T;
+// One GROUP = V consecutive elements: V bytes of each of the E planes on the planar side, E*V contiguous bytes
+// (NV 16-byte vectors) on the other.  (E, V) = (2, 8), (4, 4): one vector per group; (8, 4): two; (16, 4): four --
+// plane accesses are never narrower than 32 bits (2-byte plane loads made E = 8 LSU-bound: 58-77 % of HBM peak).
+template <int E, int V>
+__device__ __forceinline__ void unshuffle_group(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cnt, uint32_t g) {
+    using T = typename UIntOf<V>::T;
+    constexpr int NV = E * V / 16;
     uint64_t pl[E];
 #pragma unroll
-    for (int j = 0; j < E; j++) pl[j] = (uint64_t)__ldg(reinterpret_cast<const T*>(src + (size_t)j * cnt + e0));
-    uint32_t w[4] = {0, 0, 0, 0};
+    for (int j = 0; j < E; j++) pl[j] = (uint64_t)__ldg(reinterpret_cast<const T*>(src + (size_t)j * cnt + (size_t)g * V));
+    uint32_t w[NV * 4];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int i = k / E, j = k % E;  // output byte k = byte j of element e0 + i = byte i of plane j's word
+    for (int k = 0; k < NV * 4; k++) w[k] = 0;
+#pragma unroll
+    for (int k = 0; k < E * V; k++) {
+        const int i = k / E, j = k % E;  // contiguous byte k = byte j of element i of the group = byte i of plane j's word
         w[k / 4] |= ((uint32_t)(pl[j] >> (8 * i)) & 255u) << (8 * (k % 4));
     }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    uint4* o = reinterpret_cast<uint4*>(dst + (size_t)g * (E * V));
+#pragma unroll
+    for (int v = 0; v < NV; v++) o[v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
 }
-// Input vector of a shuffle scattered to the E planes.
-template <int E>
-__device__ __forceinline__ void shuffle_vec(uint4 v, uint8_t* __restrict__ dst, uint32_t cnt, uint32_t e0) {
-    using T = typename PlaneT<E>::T;
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+template <int E, int V>
+__device__ __forceinline__ void shuffle_group(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cnt, uint32_t g) {
+    using T = typename UIntOf<V>::T;
+    constexpr int NV = E * V / 16;
+    uint32_t w[NV * 4];
+    const uint4* in = reinterpret_cast<const uint4*>(src + (size_t)g * (E * V));
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const uint4 x = __ldg(in + v);
+        w[4 * v] = x.x, w[4 * v + 1] = x.y, w[4 * v + 2] = x.z, w[4 * v + 3] = x.w;
+    }
     uint64_t pl[E];
 #pragma unroll
     for (int j = 0; j < E; j++) pl[j] = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < E * V; k++) {
         const int i = k / E, j = k % E;
         pl[j] |= (uint64_t)((w[k / 4] >> (8 * (k % 4))) & 255u) << (8 * i);
     }
 #pragma unroll
-    for (int j = 0; j < E; j++) *reinterpret_cast<T*>(dst + (size_t)j * cnt + e0) = (T)pl[j];
+    for (int j = 0; j < E; j++) *reinterpret_cast<T*>(dst + (size_t)j * cnt + (size_t)g * V) = (T)pl[j];
 }
 
-template <int E, bool kForward>
-__device__ __forceinline__ void shuffle_tile_fast(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cnt, uint32_t v0, uint32_t v1) {
-    constexpr int V = 16 / E;
-    constexpr int U = 4;  // vectors in flight per thread
-    uint32_t v = v0 + threadIdx.x;
-    for (; v + (U - 1) * kShufThreads < v1; v += U * kShufThreads) {
-        uint4 r[U];
-        if (kForward) {
+template <int E, int V, bool kForward>
+__device__ __forceinline__ void shuffle_tile_fast(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cnt, uint32_t g0, uint32_t g1) {
+    constexpr int U = 64 / (E * V) > 1 ? 64 / (E * V) : 1;  // groups per thread per pass: 64 bytes of each side in flight
+    uint32_t g = g0 + threadIdx.x;
+    for (; g + (U - 1) * kShufThreads < g1; g += U * kShufThreads) {
 #pragma unroll
-            for (int u = 0; u < U; u++) r[u] = __ldg(reinterpret_cast<const uint4*>(src) + v + u * kShufThreads);
-#pragma unroll
-            for (int u = 0; u < U; u++) shuffle_vec<E>(r[u], dst, cnt, (v + u * kShufThreads) * V);
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; u++) r[u] = unshuffle_vec<E>(src, cnt, (v + u * kShufThreads) * V);
-#pragma unroll
-            for (int u = 0; u < U; u++) reinterpret_cast<uint4*>(dst)[v + u * kShufThreads] = r[u];
+        for (int u = 0; u < U; u++) {
+            if (kForward) shuffle_group<E, V>(src, dst, cnt, g + u * kShufThreads);
+            else unshuffle_group<E, V>(src, dst, cnt, g + u * kShufThreads);
         }
     }
-    for (; v < v1; v += kShufThreads) {
-        if (kForward) shuffle_vec<E>(__ldg(reinterpret_cast<const uint4*>(src) + v), dst, cnt, v * V);
-        else reinterpret_cast<uint4*>(dst)[v] = unshuffle_vec<E>(src, cnt, v * V);
+    for (; g < g1; g += kShufThreads) {
+        if (kForward) shuffle_group<E, V>(src, dst, cnt, g);
+        else unshuffle_group<E, V>(src, dst, cnt, g);
     }
 }
 
@@ -231,41 +295,34 @@ __device__ __forceinline__ void shuffle_bytes(const uint8_t* __restrict__ src, u
     }
 }
 
+// tile_map[blockIdx.x] = {item, tile within the item}: one load instead of a search over the items' prefix sums
+// (a 17-step binary search per CTA cost 25-30 % of the HBM roofline at 16 KiB chunks).
 template <bool kForward>
-__global__ void __launch_bounds__(kShufThreads) shuffle_kernel(const lsio_codec_item* __restrict__ items, const uint32_t* __restrict__ tile_prefix,
-                                                               uint32_t n_items, uint32_t elem) {
-    __shared__ uint32_t s_item;
-    if (threadIdx.x == 0) {  // the item whose tile range holds blockIdx.x
-        uint32_t lo = 0, hi = n_items;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (tile_prefix[mid] <= blockIdx.x) lo = mid;
-            else hi = mid;
-        }
-        s_item = lo;
-    }
-    __syncthreads();
-    const uint32_t item = s_item;
-    const lsio_codec_item it = items[item];
+__global__ void __launch_bounds__(kShufThreads) shuffle_kernel(const lsio_codec_item* __restrict__ items, const uint2* __restrict__ tile_map,
+                                                               uint32_t elem) {
+    const uint2 tm = __ldg(tile_map + blockIdx.x);
+    const lsio_codec_item it = items[tm.x];
     const uint8_t* src = reinterpret_cast<const uint8_t*>(it.src);
     uint8_t* dst = reinterpret_cast<uint8_t*>(it.dst);
+    __builtin_assume(__isGlobal(src));
+    __builtin_assume(__isGlobal(dst));
     const uint32_t len = it.src_len, cnt = elem ? len / elem : 0;
-    const uint32_t tile = blockIdx.x - tile_prefix[item];
-    const uint32_t b0 = tile * kShufTile, b1 = min(len, b0 + kShufTile);
-    // vector path: whole 16-byte vectors of the contiguous side that lie inside the cnt*elem body, when every
-    // plane access is naturally aligned
-    const uint32_t V = (elem == 2 || elem == 4 || elem == 8 || elem == 16) ? 16 / elem : 0;
+    const uint32_t b0 = tm.y * kShufTile, b1 = min(len, b0 + kShufTile);
+    // vector path: whole groups of the contiguous side that lie inside the cnt*elem body, when every plane access
+    // is naturally aligned
+    const uint32_t V = elem == 2 ? 8 : (elem == 4 || elem == 8 || elem == 16) ? 4 : 0;
     const uint64_t contig = kForward ? it.src : it.dst, planar = kForward ? it.dst : it.src;
     uint32_t vec_end = b0;  // bytes [b0, vec_end) go through the vector path
     if (V && (contig & 15) == 0 && (planar % V) == 0 && (cnt % V) == 0) {
-        vec_end = min(b1, (cnt * elem) & ~15u);
+        const uint32_t gb = elem * V;  // bytes per group: 16, 16, 32, 64 (all divide the tile size)
+        vec_end = min(b1, cnt * elem / gb * gb);
         if (vec_end < b0) vec_end = b0;
-        const uint32_t v0 = b0 / 16, v1 = vec_end / 16;
+        const uint32_t g0 = b0 / gb, g1 = vec_end / gb;
         switch (elem) {
-            case 2: shuffle_tile_fast<2, kForward>(src, dst, cnt, v0, v1); break;
-            case 4: shuffle_tile_fast<4, kForward>(src, dst, cnt, v0, v1); break;
-            case 8: shuffle_tile_fast<8, kForward>(src, dst, cnt, v0, v1); break;
-            default: shuffle_tile_fast<16, kForward>(src, dst, cnt, v0, v1); break;
+            case 2: shuffle_tile_fast<2, 8, kForward>(src, dst, cnt, g0, g1); break;
+            case 4: shuffle_tile_fast<4, 4, kForward>(src, dst, cnt, g0, g1); break;
+            case 8: shuffle_tile_fast<8, 4, kForward>(src, dst, cnt, g0, g1); break;
+            default: shuffle_tile_fast<16, 4, kForward>(src, dst, cnt, g0, g1); break;
         }
     }
     if (vec_end < b1) shuffle_bytes<kForward>(src, dst, len, elem, cnt, vec_end, b1);
@@ -292,7 +349,14 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     if (!n) return 0;
     DeviceGuard dg(device);
     if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
-    lz4_kernel<<<(unsigned)((n + kLzWarps - 1) / kLzWarps), kLzWarps * 32, 0, (cudaStream_t)stream>>>(items_dev, (uint32_t)n, results_dev);
+    // Many blocks: four blocks per warp (4x fewer instructions issued per sequence, which is what bounds the kernel
+    // then).  Few blocks: a warp per block (more warps in flight, 4x wider copies).  Crossover measured between
+    // 4096 and 8192 blocks of 64 KiB (tools/codec_bench.py).
+    int team = n > 6144 ? 8 : 32;
+    if (const char* e = getenv("LSIO_LZ4_VARIANT")) team = atoi(e) == 8 ? 8 : 32;  // measurement knob (tools/codec_bench.py)
+    cudaStream_t st = (cudaStream_t)stream;
+    if (team == 8) lz4_kernel<8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else lz4_kernel<32><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -320,15 +384,32 @@ int lsio_codecs_lz4_decompress(int device, const lsio_codec_item* items, size_t 
 
 uint32_t lsio_codecs_shuffle_tiles(uint32_t src_len) { return (uint32_t)(((uint64_t)src_len + kShufTile - 1) / kShufTile); }
 
-int lsio_codecs_unshuffle_async(int device, const lsio_codec_item* items_dev, const uint32_t* tile_prefix_dev, size_t n, uint32_t n_tiles,
-                                uint32_t elem_size, int forward, void* stream) {
-    if ((!items_dev || !tile_prefix_dev) && n) return -EINVAL;
-    if (elem_size == 0 || n > 0xFFFFFFF0u) return -EINVAL;
-    if (!n || !n_tiles) return 0;
+int64_t lsio_codecs_shuffle_tile_map(const uint32_t* src_lens, size_t n, uint32_t* tile_map, size_t cap_tiles) {
+    if (!src_lens && n) return -EINVAL;
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t t = lsio_codecs_shuffle_tiles(src_lens[i]);
+        if (tile_map && total + t <= cap_tiles)
+            for (uint32_t k = 0; k < t; k++) {
+                tile_map[2 * (total + k)] = (uint32_t)i;
+                tile_map[2 * (total + k) + 1] = k;
+            }
+        total += t;
+    }
+    if (total > 0x7FFFFFFFu) return -E2BIG;
+    return (int64_t)total;
+}
+
+int lsio_codecs_unshuffle_async(int device, const lsio_codec_item* items_dev, const uint32_t* tile_map_dev, uint32_t n_tiles, uint32_t elem_size,
+                                int forward, void* stream) {
+    if ((!items_dev || !tile_map_dev) && n_tiles) return -EINVAL;
+    if (elem_size == 0) return -EINVAL;
+    if (!n_tiles) return 0;
     DeviceGuard dg(device);
     if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
-    if (forward) shuffle_kernel<true><<<n_tiles, kShufThreads, 0, (cudaStream_t)stream>>>(items_dev, tile_prefix_dev, (uint32_t)n, elem_size);
-    else shuffle_kernel<false><<<n_tiles, kShufThreads, 0, (cudaStream_t)stream>>>(items_dev, tile_prefix_dev, (uint32_t)n, elem_size);
+    const uint2* tm = reinterpret_cast<const uint2*>(tile_map_dev);
+    if (forward) shuffle_kernel<true><<<n_tiles, kShufThreads, 0, (cudaStream_t)stream>>>(items_dev, tm, elem_size);
+    else shuffle_kernel<false><<<n_tiles, kShufThreads, 0, (cudaStream_t)stream>>>(items_dev, tm, elem_size);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -339,27 +420,26 @@ static int shuffle_host_items(int device, const lsio_codec_item* items, size_t n
     if (elem_size == 0) return -EINVAL;
     if (int rc = check_device(device)) return rc;
     if (!n) return 0;
-    std::vector<uint32_t> prefix(n + 1, 0);
-    uint64_t total = 0;
-    for (size_t i = 0; i < n; i++) {
-        prefix[i] = (uint32_t)total;
-        total += lsio_codecs_shuffle_tiles(items[i].src_len);
-        if (total > 0x7FFFFFFFu) return -E2BIG;
-    }
-    prefix[n] = (uint32_t)total;
+    std::vector<uint32_t> lens(n);
+    for (size_t i = 0; i < n; i++) lens[i] = items[i].src_len;
+    const int64_t total = lsio_codecs_shuffle_tile_map(lens.data(), n, nullptr, 0);
+    if (total < 0) return (int)total;
+    if (total == 0) return 0;
+    std::vector<uint32_t> map(2 * (size_t)total);
+    lsio_codecs_shuffle_tile_map(lens.data(), n, map.data(), (size_t)total);
     DeviceGuard dg(device);
     if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
     cudaStream_t st = (cudaStream_t)stream;
     char* d = nullptr;
-    LSIO_CUDA_TRY(cudaMallocAsync((void**)&d, n * sizeof(lsio_codec_item) + (n + 1) * sizeof(uint32_t), st));
+    LSIO_CUDA_TRY(cudaMallocAsync((void**)&d, n * sizeof(lsio_codec_item) + map.size() * sizeof(uint32_t), st));
     lsio_codec_item* d_items = reinterpret_cast<lsio_codec_item*>(d);
-    uint32_t* d_prefix = reinterpret_cast<uint32_t*>(d + n * sizeof(lsio_codec_item));
+    uint32_t* d_map = reinterpret_cast<uint32_t*>(d + n * sizeof(lsio_codec_item));
     LSIO_CUDA_TRY(cudaMemcpyAsync(d_items, items, n * sizeof(lsio_codec_item), cudaMemcpyHostToDevice, st));
-    LSIO_CUDA_TRY(cudaMemcpyAsync(d_prefix, prefix.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    int rc = lsio_codecs_unshuffle_async(device, d_items, d_prefix, n, (uint32_t)total, elem_size, forward, stream);
+    LSIO_CUDA_TRY(cudaMemcpyAsync(d_map, map.data(), map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    int rc = lsio_codecs_unshuffle_async(device, d_items, d_map, (uint32_t)total, elem_size, forward, stream);
     if (rc) return rc;
     LSIO_CUDA_TRY(cudaFreeAsync(d, st));
-    LSIO_CUDA_TRY(cudaStreamSynchronize(st));  // `prefix` and `items` are pageable host memory: keep the call self-contained
+    LSIO_CUDA_TRY(cudaStreamSynchronize(st));  // `map` and `items` are pageable host memory: keep the call self-contained
     return 0;
 }
 

@@ -23,10 +23,13 @@ def _to_dev(torch, data, lead=0, slack=64):
     return t
 
 
-def _lz4_batch(lsio, torch, blocks, caps, src_lead=0, dst_lead=0):
-    """Decode `blocks` (compressed bytes) in one launch. Returns (results, outputs with 32-byte guard bands)."""
-    srcs = [_to_dev(torch, b, lead=(src_lead + 3 * i) % 16 if src_lead else 0) for i, b in enumerate(blocks)]
-    leads = [(src_lead + 3 * i) % 16 if src_lead else 0 for i in range(len(blocks))]
+def _lz4_batch(lsio, torch, blocks, caps, src_lead=0, dst_lead=0, replicate=1):
+    """Decode `blocks` (compressed bytes) in one launch. Returns (results, outputs with 32-byte guard bands).
+    replicate=k decodes every block k times (into separate outputs): launches of more than 2048 blocks take
+    the 8-lanes-per-block kernel variant, smaller ones the warp-per-block variant."""
+    srcs = [_to_dev(torch, b, lead=(src_lead + 3 * i) % 16 if src_lead else 0) for i, b in enumerate(blocks)] * replicate
+    leads = [(src_lead + 3 * i) % 16 if src_lead else 0 for i in range(len(blocks))] * replicate
+    blocks, caps = list(blocks) * replicate, list(caps) * replicate
     outs = [torch.full((32 + dst_lead + c + 32,), 0xAB, dtype=torch.uint8, device="cuda:0") for c in caps]
     items = lsio.codecs.make_items([s.data_ptr() + l for s, l in zip(srcs, leads)], [o.data_ptr() + 32 + dst_lead for o in outs],
                                    [len(b) for b in blocks], caps)
@@ -40,9 +43,10 @@ def test_lz4_golden_vectors_from_liblz4(lsio, oracle, cuda_dev):
 
     vs = json.load(open(os.path.join(HERE, "golden", "codecs.json")))["vectors"]
     blocks = [bytes.fromhex(v["lz4_hex"]) for v in vs]
-    for src_lead, dst_lead in ((0, 0), (5, 3)):
-        res, outs = _lz4_batch(lsio, torch, blocks, [v["decoded_len"] for v in vs], src_lead, dst_lead)
-        for v, r, o in zip(vs, res, outs):
+    for src_lead, dst_lead, rep in ((0, 0, 1), (5, 3, 1), (2, 9, 160)):
+        res, outs = _lz4_batch(lsio, torch, blocks, [v["decoded_len"] for v in vs], src_lead, dst_lead, rep)
+        assert len(res) == len(vs) * rep
+        for v, r, o in zip(vs * rep, res, outs):
             want = recipe_bytes(v)
             assert r["status"] == 0 and r["out_len"] == len(want), (v["kind"], r)
             body = o[32 + dst_lead:32 + dst_lead + len(want)]
@@ -51,10 +55,16 @@ def test_lz4_golden_vectors_from_liblz4(lsio, oracle, cuda_dev):
             assert np.all(o[:32 + dst_lead] == 0xAB) and np.all(o[32 + dst_lead + len(want):] == 0xAB)  # nothing outside dst
 
 
-def test_lz4_random_blocks_match_the_oracle(lsio, oracle, cuda_dev):
-    """Many blocks per launch, both compressors (oracle's greedy one and liblz4), ragged sizes, misaligned."""
+@pytest.mark.parametrize("variant", [None, "8", "32"])
+def test_lz4_random_blocks_match_the_oracle(lsio, oracle, cuda_dev, monkeypatch, variant):
+    """Many blocks per launch, both compressors (oracle's greedy one and liblz4), ragged sizes, misaligned.
+    Both kernel variants (LSIO_LZ4_VARIANT: teams of 8 lanes, or a warp per block) must give the same bytes;
+    None = the library's own choice by launch size."""
     import pyarrow as pa
     import torch
+
+    if variant:
+        monkeypatch.setenv("LSIO_LZ4_VARIANT", variant)
 
     codec = pa.Codec("lz4_raw")
     rng = np.random.default_rng(7)
@@ -78,23 +88,28 @@ def test_lz4_random_blocks_match_the_oracle(lsio, oracle, cuda_dev):
     blocks = [oracle.lz4_compress(d).tobytes() if i % 2 else codec.compress(d).to_pybytes() for i, d in enumerate(datas)]
     for b, d in zip(blocks, datas):
         assert oracle.lz4_decompress(b, len(d)).tobytes() == d
-    res, outs = _lz4_batch(lsio, torch, blocks, [len(d) for d in datas], src_lead=1, dst_lead=7)
-    for i, (d, r, o) in enumerate(zip(datas, res, outs)):
-        assert r["status"] == 0 and r["out_len"] == len(d), (i, r, len(d))
-        assert o[39:39 + len(d)].tobytes() == d, i
-        assert np.all(o[:39] == 0xAB) and np.all(o[39 + len(d):] == 0xAB), i
+    for rep in (1, 7):  # 339 blocks: warp per block; 2373 blocks: 8 lanes per block
+        res, outs = _lz4_batch(lsio, torch, blocks, [len(d) for d in datas], src_lead=1, dst_lead=7, replicate=rep)
+        for i, (d, r, o) in enumerate(zip(datas * rep, res, outs)):
+            assert r["status"] == 0 and r["out_len"] == len(d), (i, r, len(d))
+            assert o[39:39 + len(d)].tobytes() == d, i
+            assert np.all(o[:39] == 0xAB) and np.all(o[39 + len(d):] == 0xAB), i
 
 
-def test_lz4_large_block_and_long_runs(lsio, oracle, cuda_dev):
+@pytest.mark.parametrize("variant", ["8", "32"])
+def test_lz4_large_block_and_long_runs(lsio, oracle, cuda_dev, monkeypatch, variant):
     import torch
 
+    monkeypatch.setenv("LSIO_LZ4_VARIANT", variant)
     rng = np.random.default_rng(9)
     d = (rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes() + bytes(1_000_000) + rng.integers(0, 5, 700_000, dtype=np.uint8).tobytes()
          + rng.integers(0, 256, 50_000, dtype=np.uint8).tobytes() * 4)
     b = oracle.lz4_compress(d).tobytes()
-    res, outs = _lz4_batch(lsio, torch, [b], [len(d) + 100])  # cap larger than needed: out_len reports the real size
-    assert res[0]["status"] == 0 and res[0]["out_len"] == len(d)
-    assert outs[0][32:32 + len(d)].tobytes() == d and np.all(outs[0][32 + len(d):] == 0xAB)
+    for lead in (0, 1, 2, 3):  # long runs are copied as realigned 32-bit words: every relative alignment
+        res, outs = _lz4_batch(lsio, torch, [b], [len(d) + 100], src_lead=lead, dst_lead=(5 * lead) % 4)  # cap larger than needed: out_len reports the real size
+        assert res[0]["status"] == 0 and res[0]["out_len"] == len(d)
+        o = outs[0][32 + (5 * lead) % 4:]
+        assert o[:len(d)].tobytes() == d and np.all(o[len(d):] == 0xAB)
 
 
 def test_lz4_malformed_blocks_report_their_own_status(lsio, oracle, cuda_dev):
@@ -106,7 +121,17 @@ def test_lz4_malformed_blocks_report_their_own_status(lsio, oracle, cuda_dev):
     blocks = [cg, cg, cg[:len(cg) // 2], bytes([0x10, 0x41, 0x00, 0x00, 0x50, 1, 2, 3, 4, 5]), bytes([0x10, 0x41, 0x02, 0x00, 0x50, 1, 2, 3, 4, 5]),
               bytes([0xF0, 0xFF]), cg]
     caps = [len(good), len(good) - 1, len(good), 100, 100, 100, len(good)]
-    res, outs = _lz4_batch(lsio, torch, blocks, caps)
+    for rep in (1, 300):
+        _check_malformed(lsio, oracle, torch, good, blocks, caps, rep)
+    t = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
+    res = C.lz4_decompress(C.make_items([t.data_ptr()], [t.data_ptr() + 32], [0], [10]))
+    assert res[0]["status"] == 1
+    assert len(C.lz4_decompress(C.make_items([], [], [], []))) == 0
+
+
+def _check_malformed(lsio, oracle, torch, good, blocks, caps, rep):
+    res, outs = _lz4_batch(lsio, torch, blocks, caps, replicate=rep)
+    res, outs = res[-len(blocks):], outs[-len(blocks):]
     st = [int(r["status"]) for r in res]
     assert st[0] == 0 and st[6] == 0 and outs[0][32:32 + len(good)].tobytes() == good and outs[6][32:32 + len(good)].tobytes() == good
     assert st[1] == 2  # LSIO_CODEC_ERR_OUTPUT
@@ -118,11 +143,6 @@ def test_lz4_malformed_blocks_report_their_own_status(lsio, oracle, cuda_dev):
     assert st[3] == 3 and st[4] == 3 and st[5] == 1
     for o, c in zip(outs, caps):
         assert np.all(o[:32] == 0xAB) and np.all(o[32 + c:] == 0xAB)  # a failing block never writes outside its dst
-    # an empty block is an error, not a hang; an empty batch is a no-op
-    t = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
-    res = C.lz4_decompress(C.make_items([t.data_ptr()], [t.data_ptr() + 32], [0], [10]))
-    assert res[0]["status"] == 1
-    assert len(C.lz4_decompress(C.make_items([], [], [], []))) == 0
 
 
 @pytest.mark.parametrize("elem", [1, 2, 3, 4, 8, 16, 12])
@@ -203,6 +223,18 @@ def test_zarr_like_chunks_through_the_whole_path(lsio, oracle, cuda_dev, data_di
         got = out.view(torch.float32).reshape(-1, *chunk_shape).cpu().numpy()
         for i, c in enumerate(chunks):
             assert np.array_equal(got[i], arrays[(c.user_data >> 32, c.user_data & 0xFFFFFFFF)]), c.user_data
+        # the same through the record-array path (Receiver.recv_batch -> decode_records): no per-chunk Python work
+        for f in range(n_files):
+            u.get_ranges(fns[f], ranges[f], [(f << 32) | k for k in range(per_file)])
+        recs = []
+        while sum(len(r) for r in recs) < n_files * per_file:
+            recs.append(u.completion().recv_batch(1024, timeout=20.0))
+        rec = np.concatenate(recs)
+        out2 = pipe.decode_records(rec)
+        got2 = out2.view(torch.float32).reshape(-1, *chunk_shape).cpu().numpy()
+        for i, ud in enumerate(rec["chunk"]["user_data"].tolist()):
+            assert np.array_equal(got2[i], arrays[(ud >> 32, ud & 0xFFFFFFFF)]), ud
+        lsio.Receiver.drop_buffers(rec)
         # a corrupted chunk is caught by the fused CRC without touching the data again
         with open(fns[0], "r+b") as fh:
             fh.seek(ranges[0][3][0] + 40)

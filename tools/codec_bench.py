@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--single", default=None, help="kind:block_bytes:blocks:variant -- time just this LZ4 launch (for ncu)")
     args = ap.parse_args()
     import ctypes
 
@@ -44,19 +45,18 @@ def main():
     st = torch.cuda.current_stream()
 
     # ---- shuffle: device-resident items, async entry point, CUDA events on the launching stream ----
-    for nbytes, n_chunks in ((16 << 10, 65536), (64 << 10, 16384), (1 << 20, 2048), (4 << 20, 512)) if not args.quick else ((1 << 20, 1024),):
+    for nbytes, n_chunks in () if args.single else ((16 << 10, 65536), (64 << 10, 16384), (1 << 20, 2048), (4 << 20, 512)) if not args.quick else ((1 << 20, 1024),):
         x = torch.randint(0, 256, (n_chunks, nbytes), dtype=torch.uint8, device="cuda:0")
         y = torch.empty_like(x)
         step = np.arange(n_chunks, dtype=np.uint64) * np.uint64(nbytes)
         items = C.make_items(x.data_ptr() + step, y.data_ptr() + step, np.full(n_chunks, nbytes))
-        tiles = np.zeros(n_chunks + 1, dtype=np.uint32)
-        tiles[1:] = np.cumsum([N.lib.lsio_codecs_shuffle_tiles(nbytes)] * n_chunks)
+        tiles = C.shuffle_tile_map(np.full(n_chunks, nbytes))
         d_items = torch.from_numpy(items.view(np.uint8)).cuda()
         d_tiles = torch.from_numpy(tiles.view(np.int32)).cuda()
         for elem in (2, 4, 8):
             for fwd in (0, 1):
                 def launch():
-                    N.check(N.lib.lsio_codecs_unshuffle_async(0, d_items.data_ptr(), d_tiles.data_ptr(), n_chunks, int(tiles[-1]), elem, fwd,
+                    N.check(N.lib.lsio_codecs_unshuffle_async(0, d_items.data_ptr(), d_tiles.data_ptr(), len(tiles), elem, fwd,
                                                               ctypes.c_void_p(st.cuda_stream)), "shuffle")
                 ms = time_launches(torch, launch)
                 gbs = 2 * n_chunks * nbytes / ms / 1e6
@@ -73,8 +73,20 @@ def main():
         "incompressible": lambda n: rng.integers(0, 256, n, dtype=np.uint8).tobytes(),
         "zeros": lambda n: bytes(n),
     }
+    configs = [(16 << 10, 65536), (64 << 10, 16384), (64 << 10, 8192), (64 << 10, 4096), (64 << 10, 2048), (64 << 10, 592), (1 << 20, 4096), (1 << 20, 1024),
+               (1 << 20, 256), (4 << 20, 256)]
+    if args.quick:
+        configs = [(64 << 10, 4096)]
+    variants = ("auto", "8", "32")
+    if args.single:
+        k, bb, nb, var = args.single.split(":")
+        kinds = {k: kinds[k]}
+        configs = [(int(bb), int(nb))]
+        variants = (var,)
     for kind, gen in kinds.items():
-        for nbytes, n_blocks in ((16 << 10, 65536), (64 << 10, 16384), (64 << 10, 2048), (1 << 20, 1024)) if not args.quick else ((64 << 10, 4096),):
+        for nbytes, n_blocks in configs:
+            if not args.single and kind in ("incompressible", "zeros") and (nbytes, n_blocks) not in ((16 << 10, 65536), (64 << 10, 2048), (1 << 20, 1024)):
+                continue
             pool = [oracle.lz4_compress(gen(nbytes)).tobytes() for _ in range(16)]
             offs = np.cumsum([0] + [(len(p) + 15) // 16 * 16 for p in pool])
             blob = np.zeros(int(offs[-1]) + 64, dtype=np.uint8)
@@ -93,19 +105,26 @@ def main():
 
             def launch():
                 N.check(N.lib.lsio_codecs_lz4_decompress_async(0, d_items.data_ptr(), n_blocks, d_res.data_ptr(), ctypes.c_void_p(st.cuda_stream)), "lz4")
-            ms = time_launches(torch, launch, iters=3, warm=1)
-            res = d_res.cpu().numpy().reshape(-1, 2)
-            assert np.all(res[:, 1] == 0) and np.all(res[:, 0] == nbytes), (kind, res[:4])
             comp = int(lens.sum())
             t0 = time.perf_counter()
             for p in pool:
                 oracle.lz4_decompress(p, nbytes)
             cpu_gbs = 16 * nbytes / (time.perf_counter() - t0) / 1e9
-            rec = {"kind": kind, "block_bytes": nbytes, "blocks": n_blocks, "ratio": n_blocks * nbytes / comp, "ms": ms,
-                   "decoded_gbs": n_blocks * nbytes / ms / 1e6, "hbm_traffic_gbs": (n_blocks * nbytes + comp) / ms / 1e6,
-                   "frac_of_hbm_peak": (n_blocks * nbytes + comp) / ms / 1e6 / hbm, "cpu_oracle_1core_gbs": cpu_gbs}
+            rec = {"kind": kind, "block_bytes": nbytes, "blocks": n_blocks, "ratio": n_blocks * nbytes / comp, "cpu_oracle_1core_gbs": cpu_gbs, "variants": {}}
+            for variant in variants:
+                if variant == "auto":
+                    os.environ.pop("LSIO_LZ4_VARIANT", None)
+                else:
+                    os.environ["LSIO_LZ4_VARIANT"] = variant
+                d_res.zero_()
+                ms = time_launches(torch, launch, iters=3, warm=1)
+                res = d_res.cpu().numpy().reshape(-1, 2)
+                assert np.all(res[:, 1] == 0) and np.all(res[:, 0] == nbytes), (kind, variant, res[:4])
+                rec["variants"][variant] = {"ms": ms, "decoded_gbs": n_blocks * nbytes / ms / 1e6,
+                                            "frac_of_hbm_peak": (n_blocks * nbytes + comp) / ms / 1e6 / hbm}
+            os.environ.pop("LSIO_LZ4_VARIANT", None)
             out["lz4"].append(rec)
-            print(rec, flush=True)
+            print(kind, nbytes, n_blocks, "ratio %.2f" % rec["ratio"], {k: round(v["decoded_gbs"], 1) for k, v in rec["variants"].items()}, flush=True)
             del d_src, d_out
     if args.json:
         with open(args.json, "w") as f:
