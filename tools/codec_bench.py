@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--single", default=None, help="kind:block_bytes:blocks:variant -- time just this LZ4 launch (for ncu)")
+    ap.add_argument("--single-shuffle", default=None, help="chunk_bytes:chunks:elem:forward -- time just this shuffle launch (for ncu)")
     args = ap.parse_args()
     import ctypes
 
@@ -45,7 +46,14 @@ def main():
     st = torch.cuda.current_stream()
 
     # ---- shuffle: device-resident items, async entry point, CUDA events on the launching stream ----
-    for nbytes, n_chunks in () if args.single else ((16 << 10, 65536), (64 << 10, 16384), (1 << 20, 2048), (4 << 20, 512)) if not args.quick else ((1 << 20, 1024),):
+    shuf_cfgs = ((16 << 10, 65536), (64 << 10, 16384), (1 << 20, 2048), (4 << 20, 512)) if not args.quick else ((1 << 20, 1024),)
+    shuf_elems, shuf_dirs = (2, 4, 8), (0, 1)
+    if args.single_shuffle:
+        cb, nc, el, fw = (int(x) for x in args.single_shuffle.split(":"))
+        shuf_cfgs, shuf_elems, shuf_dirs = ((cb, nc),), (el,), (fw,)
+    elif args.single:
+        shuf_cfgs = ()
+    for nbytes, n_chunks in shuf_cfgs:
         x = torch.randint(0, 256, (n_chunks, nbytes), dtype=torch.uint8, device="cuda:0")
         y = torch.empty_like(x)
         step = np.arange(n_chunks, dtype=np.uint64) * np.uint64(nbytes)
@@ -53,8 +61,8 @@ def main():
         tiles = C.shuffle_tile_map(np.full(n_chunks, nbytes))
         d_items = torch.from_numpy(items.view(np.uint8)).cuda()
         d_tiles = torch.from_numpy(tiles.view(np.int32)).cuda()
-        for elem in (2, 4, 8):
-            for fwd in (0, 1):
+        for elem in shuf_elems:
+            for fwd in shuf_dirs:
                 def launch():
                     N.check(N.lib.lsio_codecs_unshuffle_async(0, d_items.data_ptr(), d_tiles.data_ptr(), len(tiles), elem, fwd,
                                                               ctypes.c_void_p(st.cuda_stream)), "shuffle")
@@ -65,6 +73,8 @@ def main():
                 print(out["shuffle"][-1], flush=True)
         del x, y
 
+    if args.single_shuffle:
+        return
     # ---- lz4: a pool of distinct compressed blocks, replicated to the launch size ----
     rng = np.random.default_rng(0)
     kinds = {
