@@ -21,6 +21,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "lsio_io.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -72,6 +74,39 @@ int lsio_codecs_unshuffle_async(int device, const lsio_codec_item* items_dev, co
  * kernel already computed over the landed range (lsio_output.crc32c) with the residue: no extra pass. */
 #define LSIO_CRC32C_RESIDUE 0x48674BC7u
 int lsio_codecs_crc32c_trailer_ok(uint32_t crc32c_of_chunk_with_trailer);
+
+
+/* ---- the decode side of a Zarr codec chain over a whole batch of completion-channel items ----------------
+ * What a `lsio_codecs` crate would expose to the layers above (planned_design.md:83-90: "These crates will all
+ * consume the output channel from the IO layer"): hand it the lsio_output records of a recv_batch and get one
+ * dense (n, decoded_nbytes) array in HBM, chunk i in row i.  Stages are listed in ENCODE order, as Zarr metadata
+ * lists codecs (filters, compressor, checksum); decoding runs them backwards. */
+#define LSIO_CODEC_STAGE_SHUFFLE 1u /* param = element size in bytes (numcodecs.Shuffle) */
+#define LSIO_CODEC_STAGE_LZ4 2u     /* param = header bytes before the LZ4 block (numcodecs.LZ4: 4) */
+#define LSIO_CODEC_STAGE_CRC32C 3u  /* Zarr v3 crc32c codec: verified from lsio_output.crc32c, 4 bytes dropped */
+typedef struct lsio_codec_stage {
+    uint32_t kind;
+    uint32_t param;
+} lsio_codec_stage;
+
+typedef struct lsio_codec_pipeline lsio_codec_pipeline;
+
+/* `decoded_nbytes` (a multiple of 16) is what every chunk decodes to; `max_batch` bounds n of one decode call.
+ * Owns pinned descriptor/result arrays and, when two data-moving stages are chained, a max_batch x
+ * decoded_nbytes scratch buffer in HBM.  For double buffering create two pipelines and alternate. */
+int lsio_codec_pipeline_create(int device, const lsio_codec_stage* stages, size_t n_stages, uint64_t decoded_nbytes, uint32_t max_batch,
+                               lsio_codec_pipeline** out);
+/* Enqueues the decode of `n` items on `stream` (at most 2 kernel launches, no host synchronisation) into
+ * `out_dev` (n rows of decoded_nbytes, 16-byte aligned).  Every item must be an Ok chunk on the pipeline's
+ * device; the chunks must stay alive until lsio_codec_pipeline_finish returns.  One decode in flight per pipeline. */
+int lsio_codec_pipeline_decode(lsio_codec_pipeline* self, const lsio_output* outputs, size_t n, void* out_dev, void* stream);
+/* Waits for the decode enqueued last.  status[i] (may be NULL) receives LSIO_CODEC_* per item, with
+ * LSIO_CODEC_ERR_CHECKSUM for a crc32c trailer mismatch and LSIO_CODEC_ERR_OUTPUT when a chunk decoded to a
+ * size other than decoded_nbytes.  Returns the number of bad items (0 = all rows valid) or a negative/CUDA code. */
+#define LSIO_CODEC_ERR_CHECKSUM 4
+#define LSIO_CODEC_ERR_ITEM 5 /* the item was an Err, not a chunk, or lives on another device */
+int64_t lsio_codec_pipeline_finish(lsio_codec_pipeline* self, int32_t* status);
+void lsio_codec_pipeline_destroy(lsio_codec_pipeline* self);
 
 #ifdef __cplusplus
 }

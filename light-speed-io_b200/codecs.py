@@ -16,7 +16,9 @@ from .cuda_ops import _stream_ptr
 ITEM_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")])
 RESULT_DTYPE = np.dtype([("out_len", "<u4"), ("status", "<i4")])
 CRC32C_RESIDUE = 0x48674BC7
-STATUS_TEXT = {0: "ok", 1: "encoded stream truncated or overrun", 2: "decoded bytes do not fit", 3: "bad LZ4 match offset"}
+STATUS_TEXT = {0: "ok", 1: "encoded stream truncated or overrun", 2: "decoded size differs from decoded_nbytes", 3: "bad LZ4 match offset",
+               4: "crc32c trailer mismatch", 5: "not an Ok chunk on this device"}
+STAGE_SHUFFLE, STAGE_LZ4, STAGE_CRC32C = 1, 2, 3
 
 for _name, _res, _args in [
     ("lsio_codecs_lz4_decompress", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
@@ -28,6 +30,11 @@ for _name, _res, _args in [
     ("lsio_codecs_unshuffle_async", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
                                                    ctypes.c_int, ctypes.c_void_p]),
     ("lsio_codecs_crc32c_trailer_ok", ctypes.c_int, [ctypes.c_uint32]),
+    ("lsio_codec_pipeline_create", ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32,
+                                                  ctypes.POINTER(ctypes.c_void_p)]),
+    ("lsio_codec_pipeline_decode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    ("lsio_codec_pipeline_finish", ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("lsio_codec_pipeline_destroy", None, [ctypes.c_void_p]),
 ]:
     getattr(N.lib, _name).restype = _res
     getattr(N.lib, _name).argtypes = _args
@@ -122,20 +129,76 @@ class CodecPipeline:
         crcs = np.array([c.crc32c or 0 for c in chunks], dtype=np.uint32)
         return self._decode(src, src_len, crcs, np.array([c.user_data for c in chunks], dtype=np.uint64), stream)
 
-    def decode_records(self, records, stream=None):
-        """The same for a record array from Receiver.recv_batch (the C `lsio_output` layout): no per-chunk Python
-        work.  Every record must be an Ok chunk; the caller still owns the buffers (Receiver.drop_buffers)."""
-        if len(records) and np.any(records["status"] != 0):
-            i = int(np.flatnonzero(records["status"] != 0)[0])
-            raise CodecError(f"record {i} is an error item: {bytes(records['context'][i]).split(b'\0')[0].decode(errors='replace')}")
+    # ---- record arrays (Receiver.recv_batch): the native pipeline, lsio_codec_pipeline_* ----
+    def _native(self, n):
+        if getattr(self, "_h", None) is None or n > self._max_batch:
+            self.close()
+            stages = []
+            for c in self.codecs:
+                if isinstance(c, Shuffle):
+                    stages.append((STAGE_SHUFFLE, c.elementsize))
+                elif isinstance(c, LZ4):
+                    stages.append((STAGE_LZ4, c.header))
+                elif isinstance(c, Crc32c):
+                    stages.append((STAGE_CRC32C, 0))
+                else:
+                    raise TypeError(f"unknown codec {c!r}")
+            arr = np.array(stages, dtype=np.uint32).reshape(-1, 2)
+            h = ctypes.c_void_p()
+            self._max_batch = max(int(n), 16384)
+            N.check(N.lib.lsio_codec_pipeline_create(self.device, arr.ctypes.data, len(stages), self.decoded_nbytes, self._max_batch, ctypes.byref(h)),
+                    "codec_pipeline_create (encode order must be Shuffle, LZ4, Crc32c)")
+            self._h = h
+        return self._h
+
+    def submit_records(self, records, out=None, stream=None):
+        """Enqueue the decode of a record array from Receiver.recv_batch (the C `lsio_output` layout) on `stream`
+        and return the (n, decoded_nbytes) uint8 output tensor at once: no per-chunk Python work, no host
+        synchronisation.  Call finish() before using the rows or dropping the records' buffers; one decode in
+        flight per pipeline (use two pipelines to overlap decoding with receiving)."""
+        import torch
+
+        records = np.ascontiguousarray(records)
         n = len(records)
-        views = np.ascontiguousarray(records["chunk"]["buffer"], dtype=np.uint64)
-        src, lens = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
-        N.lib.lsio_aligned_bytes_describe_many(views.ctypes.data, n, src.ctypes.data, lens.ctypes.data)
-        if any(isinstance(c, Crc32c) for c in self.codecs) and n and not np.all(records["checksums"] & N.CHECKSUM_CRC32C):
-            raise CodecError("Crc32c needs the backend's fused CRC-32C (checksum=CHECKSUM_CRC32C)")
-        return self._decode(src, lens.astype(np.int64), np.ascontiguousarray(records["crc32c"], dtype=np.uint32),
-                            np.ascontiguousarray(records["chunk"]["user_data"], dtype=np.uint64), stream)
+        if out is None:
+            out = torch.empty((n, self.decoded_nbytes), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        self._pending = (records, out)
+        N.check(N.lib.lsio_codec_pipeline_decode(self._native(n), records.ctypes.data, n, out.data_ptr(), _stream_ptr(stream)), "codec_pipeline_decode")
+        return out
+
+    def finish(self):
+        """Wait for submit_records' decode; raises CodecError naming the first bad chunk."""
+        if getattr(self, "_pending", None) is None:
+            return
+        records, _ = self._pending
+        self._pending = None
+        status = np.zeros(len(records), dtype=np.int32)
+        bad = N.lib.lsio_codec_pipeline_finish(self._h, status.ctypes.data)
+        if bad < 0:
+            N.check(int(-bad), "codec_pipeline_finish")
+        if bad:
+            i = int(np.flatnonzero(status)[0])
+            raise CodecError(f"{bad} bad chunk(s); first: chunk {i} (user_data={int(records['chunk']['user_data'][i])}): "
+                             f"{STATUS_TEXT.get(int(status[i]), status[i])}")
+
+    def decode_records(self, records, stream=None):
+        """submit_records + finish."""
+        out = self.submit_records(records, stream=stream)
+        self.finish()
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            N.lib.lsio_codec_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _decode(self, src, src_len, crcs, user_data, stream):
         import torch

@@ -249,3 +249,64 @@ def test_zarr_like_chunks_through_the_whole_path(lsio, oracle, cuda_dev, data_di
             pipe.decode(again)
         ok = [c for c in again if c.user_data != 3]
         assert pipe.decode(ok).shape[0] == per_file - 1
+        # and by the native pipeline, which names the chunk
+        u.get_ranges(fns[0], ranges[0], list(range(per_file)))
+        rec = u.completion().recv_batch(per_file, timeout=20.0)
+        while len(rec) < per_file:
+            rec = np.concatenate([rec, u.completion().recv_batch(per_file - len(rec), timeout=20.0)])
+        with pytest.raises(C.CodecError, match=r"user_data=3\): crc32c trailer mismatch"):
+            pipe.decode_records(rec)
+        lsio.Receiver.drop_buffers(rec)
+
+
+@pytest.mark.parametrize("chain", ["", "shuffle", "lz4", "crc", "shuffle+lz4", "lz4+crc", "shuffle+crc"])
+def test_native_pipeline_stage_combinations(lsio, oracle, cuda_dev, data_dir, chain):
+    """lsio_codec_pipeline_* with every subset of the chain [Shuffle, LZ4, Crc32c], asynchronous submit/finish,
+    two batches in flight on two pipelines; rows compared with the arrays the shards were encoded from."""
+    import torch
+
+    C = lsio.codecs
+    rng = np.random.default_rng(len(chain))
+    nbytes, n = 8192, 300
+    names = [c for c in chain.split("+") if c]
+    codecs = [{"shuffle": C.Shuffle(8), "lz4": C.LZ4(), "crc": C.Crc32c()}[c] for c in names]
+    arrays, blob, ranges = [], bytearray(b"x" * 13), []
+    for i in range(n):
+        a = np.cumsum(rng.integers(-5, 6, nbytes // 8)).astype("<i8")
+        arrays.append(a)
+        b = a.tobytes()
+        if "shuffle" in names:
+            b = oracle.shuffle(b, 8).tobytes()
+        if "lz4" in names:
+            b = struct.pack("<I", nbytes) + oracle.lz4_compress(b).tobytes()
+        if "crc" in names:
+            b += struct.pack("<I", oracle.crc32c(b))
+        ranges.append((len(blob), len(blob) + len(b)))
+        blob += b
+    fn = os.path.join(data_dir, "s")
+    with open(fn, "wb") as fh:
+        fh.write(blob + b"end")
+    pipes = [C.CodecPipeline(codecs, nbytes), C.CodecPipeline(codecs, nbytes)]
+    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20) as u:
+        u.get_ranges(fn, ranges, range(n))
+        recs, got = [], 0
+        while got < n:
+            r = u.completion().recv_batch(100, timeout=20.0)
+            recs.append(r)
+            got += len(r)
+        outs = [pipes[i % 2].submit_records(r) if i < 2 else None for i, r in enumerate(recs)]
+        for i, r in enumerate(recs):  # at most two decodes in flight
+            pipes[i % 2].finish()
+            if i + 2 < len(recs):
+                outs[i + 2] = pipes[i % 2].submit_records(recs[i + 2])
+        for r, o in zip(recs, outs):
+            h = o.cpu().numpy().view("<i8")
+            for row, ud in zip(h, r["chunk"]["user_data"].tolist()):
+                assert np.array_equal(row, arrays[ud]), (chain, ud)
+            lsio.Receiver.drop_buffers(r)
+    for p in pipes:
+        p.close()
+    # stages out of encode order are refused
+    if len(codecs) >= 2:
+        with pytest.raises(lsio._native.LsioCudaError):
+            C.CodecPipeline(codecs[::-1], nbytes).decode_records(recs[0][:0])

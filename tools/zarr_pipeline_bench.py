@@ -63,7 +63,8 @@ def main():
         n = per_file * args.files
         stored_bytes = sum(e - s for rs in ranges for s, e in rs)
         decoded_bytes = n * nbytes
-        pipe = C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], nbytes)
+        pipes = [C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], nbytes) for _ in range(2)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
         expect = torch.from_numpy(np.stack([p[0] for p in pool])).cuda()
         results = []
         with L.IoUringCuda(args.workers, arena_bytes=8 << 30, completion_bound=65536) as u:
@@ -74,19 +75,29 @@ def main():
                 for f in range(args.files):
                     u.get_ranges(fns[f], ranges[f], [(f << 32) | k for k in range(per_file)])
                 got, t_decode, outs = 0, 0.0, []
-                pending = []
+                pending, inflight, k = [], [], 0  # two pipelines: batch k decodes while batch k+1 is received
                 while got < n:
                     rec = rx.recv_batch(min(args.batch, n - got), timeout=30.0)  # numpy record array over lsio_output
                     pending.append(rec)
                     got += len(rec)
                     if sum(len(r) for r in pending) >= args.batch or got == n:
                         rec = np.concatenate(pending)
-                        td = time.perf_counter()
-                        out = pipe.decode_records(rec)
-                        t_decode += time.perf_counter() - td
-                        outs.append((out, rec["chunk"]["user_data"].tolist()))
-                        L.Receiver.drop_buffers(rec)
                         pending = []
+                        td = time.perf_counter()
+                        if len(inflight) == 2:
+                            p0, r0 = inflight.pop(0)
+                            p0.finish()
+                            L.Receiver.drop_buffers(r0)
+                        out = pipes[k % 2].submit_records(rec, stream=streams[k % 2])
+                        t_decode += time.perf_counter() - td
+                        inflight.append((pipes[k % 2], rec))
+                        outs.append((out, rec["chunk"]["user_data"].tolist()))
+                        k += 1
+                td = time.perf_counter()
+                for p0, r0 in inflight:
+                    p0.finish()
+                    L.Receiver.drop_buffers(r0)
+                t_decode += time.perf_counter() - td
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
                 # verify every decoded row against the array it was encoded from (outside the timed region)
@@ -95,9 +106,9 @@ def main():
                     idx = torch.tensor([which[ud >> 32][ud & 0xFFFFFFFF] for ud in uds], device="cuda")
                     bad += int((out.view(torch.float32) != expect[idx]).any(dim=1).sum())
                 if rep:
-                    results.append({"seconds": dt, "decode_seconds": t_decode, "bad_chunks": bad,
+                    results.append({"seconds": dt, "bad_chunks": bad,
                                     "stored_gib_s": stored_bytes / dt / 2**30, "decoded_gib_s": decoded_bytes / dt / 2**30,
-                                    "decode_stage_decoded_gib_s": decoded_bytes / t_decode / 2**30})
+                                    "decode_wait_seconds": t_decode})
                 del outs
         # CPU baseline: the oracle decoder on one core over a bounded sample (pread + crc + lz4 + unshuffle)
         t0 = time.perf_counter()
