@@ -159,8 +159,14 @@ static int init_group(Group& g) {
         DeviceGuard d(dev);
         cudaFree(p);
     });
-    LSIO_CUDA_TRY(cudaStreamCreateWithFlags(&g.s_copy, cudaStreamNonBlocking));
-    LSIO_CUDA_TRY(cudaStreamCreateWithFlags(&g.s_pack, cudaStreamNonBlocking));
+    // The landing path runs at the highest stream priority: a consumer's own kernels on the same GPU (the codec
+    // layer decoding the previous batch, a training step) fill every SM for milliseconds, and a pack launch queued
+    // behind them stalls the staging log and with it the reads.  With priority the block scheduler places the pack
+    // CTAs first as SMs drain (measured with LZ4 decode running beside the I/O: see DESIGN 3.3).
+    int prio_lo = 0, prio_hi = 0;
+    LSIO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    LSIO_CUDA_TRY(cudaStreamCreateWithPriority(&g.s_copy, cudaStreamNonBlocking, prio_hi));
+    LSIO_CUDA_TRY(cudaStreamCreateWithPriority(&g.s_pack, cudaStreamNonBlocking, prio_hi));
     const size_t max_segs = 8192, max_tiles = 1 << 16;
     g.batches.resize(8);
     for (Batch& b : g.batches) {

@@ -310,3 +310,75 @@ def test_native_pipeline_stage_combinations(lsio, oracle, cuda_dev, data_dir, ch
     if len(codecs) >= 2:
         with pytest.raises(lsio._native.LsioCudaError):
             C.CodecPipeline(codecs[::-1], nbytes).decode_records(recs[0][:0])
+
+
+def test_zarr_v3_sharded_read(lsio, oracle, cuda_dev, data_dir):
+    """A caller of the path (lsio_b200.zarr_shard): Zarr v3 `sharding_indexed` shards -- inner chunks in shuffled order
+    with gaps and missing chunks, the index (u64 offset/nbytes pairs + crc32c) at the END of the file -- read as two
+    ordered groups: indexes through negative ranges (lsio_io lib.rs:19-23), then the inner chunks they point to,
+    decoded by the native pipeline.  Also: index at the start, a subset of chunks, a corrupted index."""
+    import torch
+
+    Z, C = lsio.zarr_shard, lsio.codecs
+    rng = np.random.default_rng(33)
+    n_shards, n_inner, shape = 5, 48, (32, 32)
+    nbytes = int(np.prod(shape)) * 4
+    arrays, paths = {}, []
+    for s in range(n_shards):
+        location = "start" if s == 4 else "end"
+        order = rng.permutation(n_inner)
+        missing = set(rng.choice(n_inner, 5, replace=False).tolist())
+        table = np.full((n_inner, 2), 0xFFFFFFFFFFFFFFFF, dtype="<u8")
+        body = bytearray()
+        base = Z.index_nbytes(n_inner) if location == "start" else 0
+        for k in order:
+            if int(k) in missing:
+                continue
+            a = (np.cumsum(rng.standard_normal(shape), axis=0) * 0.1).astype("<f4").round(1)
+            arrays[(s, int(k))] = a
+            stored = struct.pack("<I", nbytes) + oracle.lz4_compress(oracle.shuffle(a.tobytes(), 4)).tobytes()
+            stored += struct.pack("<I", oracle.crc32c(stored))
+            body += bytes(int(rng.integers(0, 9)))  # gaps between inner chunks are allowed
+            table[k] = (base + len(body), len(stored))
+            body += stored
+        index = table.tobytes() + struct.pack("<I", oracle.crc32c(table.tobytes()))
+        fn = os.path.join(data_dir, f"c{s}")
+        with open(fn, "wb") as fh:
+            fh.write(index + bytes(body) if location == "start" else bytes(body) + index)
+        paths.append(fn)
+    pipe = C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], nbytes)
+    with lsio.IoUringCuda(3, arena_bytes=64 << 20, staging_bytes=16 << 20) as u:
+        rx = u.completion()
+        total, present = Z.read_shards(u, paths[:4], n_inner)
+        assert total == 4 * (n_inner - 5) and all(len(p) == n_inner - 5 for p in present)
+        recs = []
+        while sum(len(r) for r in recs) < total:
+            recs.append(rx.recv_batch(1024, timeout=20.0))
+        rec = np.concatenate(recs)
+        assert np.all(rec["group"] == rec["group"][0])  # all of them in the chunk group
+        rows = pipe.decode_records(rec).view(torch.float32).reshape(-1, *shape).cpu().numpy()
+        seen = set()
+        for row, ud in zip(rows, rec["chunk"]["user_data"].tolist()):
+            key = (ud >> 32, ud & 0xFFFFFFFF)
+            assert np.array_equal(row, arrays[key]), key
+            seen.add(key)
+        assert seen == {k for k in arrays if k[0] < 4}
+        lsio.Receiver.drop_buffers(rec)
+        # index at the start of the file, only some chunks wanted (missing ones are skipped)
+        wanted = [list(range(0, n_inner, 3))]
+        total, present = Z.read_shards(u, paths[4:], n_inner, wanted=wanted, index_location="start")
+        assert set(present[0].tolist()) == {k for k in wanted[0] if (4, k) in arrays} and total == len(present[0])
+        chunks = [rx.recv_timeout(20.0) for _ in range(total)]
+        rows = pipe.decode(chunks).view(torch.float32).reshape(-1, *shape).cpu().numpy()
+        for row, c in zip(rows, chunks):
+            assert c.user_data >> 32 == 0 and np.array_equal(row, arrays[(4, c.user_data & 0xFFFFFFFF)])
+        # a corrupted index is refused by the fused CRC
+        with open(paths[0], "r+b") as fh:
+            fh.seek(-20, os.SEEK_END)
+            b = fh.read(1)
+            fh.seek(-20, os.SEEK_END)
+            fh.write(bytes([b[0] ^ 1]))
+            fh.flush()
+            os.fsync(fh.fileno())
+        with pytest.raises(Z.ShardIndexError, match="crc32c"):
+            Z.read_shards(u, paths[:1], n_inner)

@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="chunks decoded per CodecPipeline.decode call")
     ap.add_argument("--workers", type=int, default=8)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--arena-gib", type=int, default=8)
+    ap.add_argument("--no-decode", action="store_true", help="I/O path only: receive and drop (the ceiling the decode competes with)")
+    ap.add_argument("--ranges-per-request", type=int, default=0, help="0 = one get_ranges call per file")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
     import torch
@@ -60,20 +63,28 @@ def main():
             fns.append(fn)
             ranges.append(rs)
             which.append(wh)
+        which_arr = np.array(which, dtype=np.int64)
         n = per_file * args.files
         stored_bytes = sum(e - s for rs in ranges for s, e in rs)
         decoded_bytes = n * nbytes
+        # a reader gets these as arrays straight from the shard index; building them is not part of the timed path
+        starts = [np.array([r[0] for r in rs], dtype=np.int64) for rs in ranges]
+        ends = [np.array([r[1] for r in rs], dtype=np.int64) for rs in ranges]
+        uds = [(np.uint64(f) << np.uint64(32)) | np.arange(per_file, dtype=np.uint64) for f in range(args.files)]
         pipes = [C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], nbytes) for _ in range(2)]
         streams = [torch.cuda.Stream(), torch.cuda.Stream()]
         expect = torch.from_numpy(np.stack([p[0] for p in pool])).cuda()
         results = []
-        with L.IoUringCuda(args.workers, arena_bytes=8 << 30, completion_bound=65536) as u:
+        with L.IoUringCuda(args.workers, arena_bytes=args.arena_gib << 30, completion_bound=65536) as u:
             rx = u.completion()
             for rep in range(args.reps + 1):
                 torch.cuda.synchronize()
+                st0 = u.stats()
                 t0 = time.perf_counter()
+                rpr = args.ranges_per_request or per_file
                 for f in range(args.files):
-                    u.get_ranges(fns[f], ranges[f], [(f << 32) | k for k in range(per_file)])
+                    for a in range(0, per_file, rpr):
+                        u.get_ranges_arrays(fns[f], starts[f][a:a + rpr], ends[f][a:a + rpr], uds[f][a:a + rpr])
                 got, t_decode, outs = 0, 0.0, []
                 pending, inflight, k = [], [], 0  # two pipelines: batch k decodes while batch k+1 is received
                 while got < n:
@@ -83,6 +94,9 @@ def main():
                     if sum(len(r) for r in pending) >= args.batch or got == n:
                         rec = np.concatenate(pending)
                         pending = []
+                        if args.no_decode:
+                            L.Receiver.drop_buffers(rec)
+                            continue
                         td = time.perf_counter()
                         if len(inflight) == 2:
                             p0, r0 = inflight.pop(0)
@@ -91,7 +105,7 @@ def main():
                         out = pipes[k % 2].submit_records(rec, stream=streams[k % 2])
                         t_decode += time.perf_counter() - td
                         inflight.append((pipes[k % 2], rec))
-                        outs.append((out, rec["chunk"]["user_data"].tolist()))
+                        outs.append((out, rec["chunk"]["user_data"]))
                         k += 1
                 td = time.perf_counter()
                 for p0, r0 in inflight:
@@ -102,11 +116,13 @@ def main():
                 dt = time.perf_counter() - t0
                 # verify every decoded row against the array it was encoded from (outside the timed region)
                 bad = 0
-                for out, uds in outs:
-                    idx = torch.tensor([which[ud >> 32][ud & 0xFFFFFFFF] for ud in uds], device="cuda")
+                for out, uds_ in outs:
+                    idx = torch.from_numpy(which_arr[(uds_ >> np.uint64(32)).astype(np.int64), (uds_ & np.uint64(0xFFFFFFFF)).astype(np.int64)]).cuda()
                     bad += int((out.view(torch.float32) != expect[idx]).any(dim=1).sum())
+                st1 = u.stats()
                 if rep:
-                    results.append({"seconds": dt, "bad_chunks": bad,
+                    results.append({"arena_stalls": st1["arena_stalls"] - st0["arena_stalls"], "staging_stalls": st1["staging_stalls"] - st0["staging_stalls"],
+                                    "reads": st1["reads"] - st0["reads"], "h2d_copies": st1["h2d_copies"] - st0["h2d_copies"], "seconds": dt, "bad_chunks": bad,
                                     "stored_gib_s": stored_bytes / dt / 2**30, "decoded_gib_s": decoded_bytes / dt / 2**30,
                                     "decode_wait_seconds": t_decode})
                 del outs
