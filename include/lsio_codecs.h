@@ -106,6 +106,8 @@ int lsio_codec_pipeline_decode(lsio_codec_pipeline* self, const lsio_output* out
 #define LSIO_CODEC_ERR_CHECKSUM 4
 #define LSIO_CODEC_ERR_ITEM 5 /* the item was an Err, not a chunk, or lives on another device */
 int64_t lsio_codec_pipeline_finish(lsio_codec_pipeline* self, int32_t* status);
+/* Measurement aid: device time of the decode finished last, split into its first launch (LZ4 when present) and the rest. */
+int lsio_codec_pipeline_last_ms(lsio_codec_pipeline* self, float* first_stage_ms, float* rest_ms);
 void lsio_codec_pipeline_destroy(lsio_codec_pipeline* self);
 
 #ifdef __cplusplus

@@ -47,8 +47,10 @@ typedef struct lsio_uring_cuda_config {
     uint64_t staging_bytes;     /* pinned + io_uring-registered staging ring per device                      */
     uint64_t arena_bytes;       /* HBM arena per device that request buffers are carved from                 */
     uint64_t max_read_bytes;    /* reads (merged or not) are cut at this size; default 1 MiB, <= 1 GiB        */
-    uint64_t min_copy_bytes;    /* H2D copies are coalesced up to at least this many bytes                   */
-    uint32_t flush_us;          /* ...or until the oldest landed read has waited this long                   */
+    uint64_t min_copy_bytes;    /* a pack launch (staging_mode 0: and its coalesced H2D copy) is batched up to at least this
+                                   many landed bytes (default 64 MiB) ...                                                     */
+    uint32_t flush_us;          /* ...or until the oldest landed extent has waited this long (default 2000), or the burst is
+                                   over (nothing being read and 100 us without a landing)                                   */
     uint32_t merge_ranges;      /* 1 = ranges of one request whose padded spans touch/overlap share one read    */
     uint64_t merge_gap_bytes;   /* ...also when separated by at most this many bytes (the gap is read and dropped) */
     uint32_t statx_via_ring;    /* 1 = the reference's two unlinked SQEs per file, openat + statx (get_ranges.rs:49-65):

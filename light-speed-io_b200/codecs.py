@@ -34,6 +34,7 @@ for _name, _res, _args in [
                                                   ctypes.POINTER(ctypes.c_void_p)]),
     ("lsio_codec_pipeline_decode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     ("lsio_codec_pipeline_finish", ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("lsio_codec_pipeline_last_ms", ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     ("lsio_codec_pipeline_destroy", None, [ctypes.c_void_p]),
 ]:
     getattr(N.lib, _name).restype = _res
@@ -182,6 +183,12 @@ class CodecPipeline:
             i = int(np.flatnonzero(status)[0])
             raise CodecError(f"{bad} bad chunk(s); first: chunk {i} (user_data={int(records['chunk']['user_data'][i])}): "
                              f"{STATUS_TEXT.get(int(status[i]), status[i])}")
+
+    def last_ms(self):
+        """(first stage, rest) device milliseconds of the decode finished last (measurement aid)."""
+        a, b = ctypes.c_float(), ctypes.c_float()
+        N.check(N.lib.lsio_codec_pipeline_last_ms(self._h, ctypes.byref(a), ctypes.byref(b)), "codec_pipeline_last_ms")
+        return a.value, b.value
 
     def decode_records(self, records, stream=None):
         """submit_records + finish."""

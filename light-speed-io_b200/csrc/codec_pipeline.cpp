@@ -25,7 +25,7 @@ struct lsio_codec_pipeline {
     uint32_t* d_tile_map = nullptr;  // rows are uniform: the {row, tile} table of max_batch rows serves any n
     uint32_t tiles_per_row = 0;
     uint8_t* scratch = nullptr;  // lz4 output when a shuffle stage follows
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;  // t0..t1: the lz4 launch, t1..done: the rest (timing aid)
     std::vector<int32_t> host_status;  // per item, decided on the host (crc, bad item)
     size_t n_inflight = 0;
     bool inflight = false;
@@ -41,6 +41,8 @@ static void free_pipeline(lsio_codec_pipeline* p) {
     if (p->d_tile_map) cudaFree(p->d_tile_map);
     if (p->scratch) cudaFree(p->scratch);
     if (p->done) cudaEventDestroy(p->done);
+    if (p->t0) cudaEventDestroy(p->t0);
+    if (p->t1) cudaEventDestroy(p->t1);
     delete p;
 }
 
@@ -54,7 +56,9 @@ static int init_pipeline(lsio_codec_pipeline* p) {
     LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&p->d_items_lz4, p->items_lz4, 0));
     LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&p->d_items_shuf, p->items_shuf, 0));
     LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&p->d_results, p->results, 0));
-    LSIO_CUDA_TRY(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+    LSIO_CUDA_TRY(cudaEventCreate(&p->done));
+    LSIO_CUDA_TRY(cudaEventCreate(&p->t0));
+    LSIO_CUDA_TRY(cudaEventCreate(&p->t1));
     if (p->has_shuffle) {
         p->tiles_per_row = lsio_codecs_shuffle_tiles((uint32_t)p->nbytes);
         std::vector<uint32_t> lens(p->max_batch, (uint32_t)p->nbytes), map(2 * (size_t)p->max_batch * p->tiles_per_row);
@@ -150,10 +154,12 @@ int lsio_codec_pipeline_decode(lsio_codec_pipeline* p, const lsio_output* output
         }
         if (!p->has_lz4 && !p->has_shuffle && ok) copies.push_back(lsio_cuda_segment{src, (uint64_t)(uintptr_t)(out + i * p->nbytes), p->nbytes});
     }
+    LSIO_CUDA_TRY(cudaEventRecord(p->t0, st));
     if (p->has_lz4) {
         int rc = lsio_codecs_lz4_decompress_async(p->device, p->d_items_lz4, n, p->d_results, stream);
         if (rc) return rc;
     }
+    LSIO_CUDA_TRY(cudaEventRecord(p->t1, st));
     if (p->has_shuffle) {
         int rc = lsio_codecs_unshuffle_async(p->device, p->d_items_shuf, p->d_tile_map, (uint32_t)n * p->tiles_per_row, p->elem, 0, stream);
         if (rc) return rc;
@@ -186,6 +192,14 @@ int64_t lsio_codec_pipeline_finish(lsio_codec_pipeline* p, int32_t* status) {
         bad += s != LSIO_CODEC_OK;
     }
     return bad;
+}
+
+int lsio_codec_pipeline_last_ms(lsio_codec_pipeline* p, float* first_stage_ms, float* rest_ms) {
+    if (!p || p->inflight) return -EINVAL;
+    DeviceGuard dg(p->device);
+    if (first_stage_ms) LSIO_CUDA_TRY(cudaEventElapsedTime(first_stage_ms, p->t0, p->t1));
+    if (rest_ms) LSIO_CUDA_TRY(cudaEventElapsedTime(rest_ms, p->t1, p->done));
+    return 0;
 }
 
 void lsio_codec_pipeline_destroy(lsio_codec_pipeline* p) {

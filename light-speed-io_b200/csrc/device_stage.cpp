@@ -230,7 +230,7 @@ void device_main(Group& g) {
         if (g.copy_seq < avail && !g.free_batches.empty()) {
             uint64_t s = g.copy_seq, bytes = 0, run_phys0 = g.log.at(s).log_off % cap;
             size_t nsegs = 0, ntiles = 0;
-            uint64_t oldest = 0;
+            uint64_t oldest = 0, newest = 0;
             bool hit_limit = false;
             for (; s < avail; s++) {
                 StageEntry& e = g.log.at(s);
@@ -252,6 +252,7 @@ void device_main(Group& g) {
                     ns += rd.nsegs;
                     if (!oldest) oldest = e.landed_ns;
                 }
+                newest = std::max(newest, e.landed_ns);
                 if (nsegs + ns > max_segs || ntiles + t > max_tiles || (bytes && bytes + e.len > max_batch_bytes)) {
                     hit_limit = true;
                     break;
@@ -262,8 +263,12 @@ void device_main(Group& g) {
             }
             if (s > g.copy_seq) {
                 const bool draining = g.stop_device.load(std::memory_order_relaxed);
-                const bool timed_out = oldest && now_ns() - oldest > (uint64_t)cfg.flush_us * 1000;
-                if (hit_limit || bytes >= cfg.min_copy_bytes || timed_out || draining || (!oldest)) {
+                const uint64_t now = now_ns();
+                const bool timed_out = oldest && now - oldest > (uint64_t)cfg.flush_us * 1000;
+                // Nothing else is being read and nothing has landed for a moment: the burst is over, do not make a
+                // lone request wait out flush_us (batches are kept large only while extents keep arriving).
+                const bool idle = s == avail && newest && now - newest > (uint64_t)std::min<uint32_t>(cfg.flush_us, 100) * 1000;
+                if (hit_limit || bytes >= cfg.min_copy_bytes || timed_out || idle || draining || (!oldest)) {
                     int rc = flush_run(g, g.copy_seq, s);
                     if (rc) {
                         // A CUDA call failed while enqueueing: report every range of the run in-band and

@@ -226,8 +226,11 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     // with 256-512 KiB reads and 3.8 with 2 MiB ones (more, smaller requests in flight).  In staging_mode 0 reads of
     // <= 1 MiB matter for another reason: the slot is handed to the H2D DMA while still in the 2 MiB per-core L2.
     cfg->max_read_bytes = 512ull << 10;
-    cfg->min_copy_bytes = 8ull << 20;
-    cfg->flush_us = 200;
+    // A pack launch is worth batching: every launch re-stages 148 x 128 KiB of CRC tables and competes with the H2D
+    // DMA.  Measured on C2 (alternating runs on one box): 8 MiB / 200 us 41.7 GiB/s, 32 MiB / 1 ms 44.7, 64 MiB / 2 ms
+    // 45.5, 128 MiB / 4 ms (2 GiB log) 45.6.  A burst that ends is flushed after 100 us of silence (device_stage.cpp).
+    cfg->min_copy_bytes = 64ull << 20;
+    cfg->flush_us = 2000;
     cfg->merge_ranges = 1;
     cfg->merge_gap_bytes = 0;
     cfg->statx_via_ring = 0;

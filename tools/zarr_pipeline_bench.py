@@ -51,7 +51,7 @@ def make_pool(nbytes, n_distinct=64, seed=0):
 
 
 def run(chunk_kib=64, chunks=262144, files=256, batch=32768, workers=8, reps=3, arena_gib=8, ranges_per_request=0, no_decode=False,
-        cpu_baseline=False, directory="/dev/shm"):
+        cpu_baseline=False, directory="/dev/shm", **backend_config):
     import torch
 
     import lsio_b200 as L
@@ -89,7 +89,7 @@ def run(chunk_kib=64, chunks=262144, files=256, batch=32768, workers=8, reps=3, 
         streams = [torch.cuda.Stream(), torch.cuda.Stream()]
         expect = torch.from_numpy(np.stack([p[0] for p in pool])).cuda()
         results = []
-        with L.IoUringCuda(workers, arena_bytes=arena_gib << 30, completion_bound=65536) as u:
+        with L.IoUringCuda(workers, arena_bytes=arena_gib << 30, completion_bound=65536, **backend_config) as u:
             rx = u.completion()
             for rep in range(reps + 1):
                 torch.cuda.synchronize()
@@ -100,7 +100,7 @@ def run(chunk_kib=64, chunks=262144, files=256, batch=32768, workers=8, reps=3, 
                 for f in range(files):
                     for a in range(0, per_file, rpr):
                         u.get_ranges_arrays(fns[f], starts[f][a:a + rpr], ends[f][a:a + rpr], uds[f][a:a + rpr])
-                got, t_decode, outs = 0, 0.0, []
+                got, t_decode, outs, trace = 0, 0.0, [], []
                 pending, inflight, k = [], [], 0  # two pipelines: batch k decodes while batch k+1 is received
                 while got < n:
                     rec = rx.recv_batch(min(batch, n - got), timeout=30.0)  # numpy record array over lsio_output
@@ -116,15 +116,21 @@ def run(chunk_kib=64, chunks=262144, files=256, batch=32768, workers=8, reps=3, 
                         if len(inflight) == 2:
                             p0, r0 = inflight.pop(0)
                             p0.finish()
+                            tf = time.perf_counter()
                             L.Receiver.drop_buffers(r0)
+                            trace.append(("finish", round(tf - td, 4), "drop", round(time.perf_counter() - tf, 4), "dev_ms", [round(x, 1) for x in p0.last_ms()]))
+                        ts = time.perf_counter()
                         out = pipes[k % 2].submit_records(rec, stream=streams[k % 2])
+                        trace.append(("submit", round(time.perf_counter() - ts, 4), "at", round(ts - t0, 4)))
                         t_decode += time.perf_counter() - td
                         inflight.append((pipes[k % 2], rec))
                         outs.append((out, rec["chunk"]["user_data"]))
                         k += 1
                 td = time.perf_counter()
                 for p0, r0 in inflight:
+                    tf = time.perf_counter()
                     p0.finish()
+                    trace.append(("finish", round(time.perf_counter() - tf, 4), "at", round(tf - t0, 4), "dev_ms", [round(x, 1) for x in p0.last_ms()]))
                     L.Receiver.drop_buffers(r0)
                 t_decode += time.perf_counter() - td
                 torch.cuda.synchronize()
@@ -140,7 +146,7 @@ def run(chunk_kib=64, chunks=262144, files=256, batch=32768, workers=8, reps=3, 
                     results.append({"seconds": dt, "decode_wait_seconds": t_decode, "bad_chunks": bad, "kernel_launches": launches,
                                     "stored_gib_s": stored_bytes / dt / 2**30, "decoded_gib_s": decoded_bytes / dt / 2**30,
                                     "arena_stalls": st1["arena_stalls"] - st0["arena_stalls"], "staging_stalls": st1["staging_stalls"] - st0["staging_stalls"],
-                                    "reads": st1["reads"] - st0["reads"], "h2d_copies": st1["h2d_copies"] - st0["h2d_copies"]})
+                                    "reads": st1["reads"] - st0["reads"], "h2d_copies": st1["h2d_copies"] - st0["h2d_copies"], "trace": trace})
                 del outs
         for p in pipes:
             p.close()
@@ -182,8 +188,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ranges-per-request", type=int, default=0, help="0 = one get_ranges call per file")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--min-copy-mib", type=int, default=0, help="backend knob: pack launches are batched up to at least this much")
+    ap.add_argument("--flush-us", type=int, default=0, help="backend knob: ...or until the oldest landed extent has waited this long")
     a = ap.parse_args()
-    rec = run(a.chunk_kib, a.chunks, a.files, a.batch, a.workers, a.reps, a.arena_gib, a.ranges_per_request, a.no_decode, not a.no_cpu_baseline)
+    cfg = {}
+    if a.min_copy_mib:
+        cfg["min_copy_bytes"] = a.min_copy_mib << 20
+    if a.flush_us:
+        cfg["flush_us"] = a.flush_us
+    rec = run(a.chunk_kib, a.chunks, a.files, a.batch, a.workers, a.reps, a.arena_gib, a.ranges_per_request, a.no_decode, not a.no_cpu_baseline, **cfg)
     print(json.dumps(rec))
     if a.json:
         with open(a.json, "w") as fh:
