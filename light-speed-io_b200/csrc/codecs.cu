@@ -106,9 +106,12 @@ __device__ __forceinline__ void lz_copy_long(uint8_t* d, const uint8_t* s, uint3
 // throughput comes from blocks in flight.  Tried and rejected: mirroring the last 16/32 KiB of output in shared
 // memory so that matches never wait for L2 -- no gain per block (4.0 -> 4.2 GB/s at 256 blocks of 1 MiB; the
 // match reads are not on the critical path), and the lost occupancy cost 2-5x at larger launches.
-template <int T>
-__global__ void __launch_bounds__(kLzThreads) lz4_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
-                                                         lsio_codec_result* __restrict__ results) {
+// Also tried and rejected: deferring a short match's stores by one sequence so that its loads overlap the next
+// parse (software pipelining; +7 % at 16,384 blocks, but 8 more live registers: -20 % wherever occupancy counts).
+// kMinCtas: 8 CTAs per SM (32 registers, a few spilled bytes) pays once a launch has enough blocks to fill them.
+template <int T, int kMinCtas>
+__global__ void __launch_bounds__(kLzThreads, kMinCtas) lz4_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
+                                                                   lsio_codec_result* __restrict__ results) {
     constexpr int kTeams = kLzThreads / T;
     __shared__ __align__(16) uint8_t s_lz[kTeams * kLzWin];
     const int team = threadIdx.x / T, l = threadIdx.x % T;
@@ -352,11 +355,14 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     // Many blocks: four blocks per warp (4x fewer instructions issued per sequence, which is what bounds the kernel
     // then).  Few blocks: a warp per block (more warps in flight, 4x wider copies).  Crossover measured between
     // 4096 and 8192 blocks of 64 KiB (tools/codec_bench.py).
-    int team = n > 6144 ? 8 : 32;
-    if (const char* e = getenv("LSIO_LZ4_VARIANT")) team = atoi(e) == 8 ? 8 : 32;  // measurement knob (tools/codec_bench.py)
+    // Measured on shuffled float32 chunks of 64 KiB (GB/s decoded): 16,384 blocks 122 (5 CTAs/SM) vs 116 (8 CTAs/SM);
+    // 32,768 blocks 174 with 8; 65,536 blocks of 16 KiB 167 vs 193.
+    int variant = n > 24576 ? 88 : n > 6144 ? 8 : 32;  // 88: teams of 8, 8 CTAs/SM; 8: teams of 8, 5 CTAs/SM; 32: a warp per block
+    if (const char* e = getenv("LSIO_LZ4_VARIANT")) variant = atoi(e);  // measurement knob (tools/codec_bench.py)
     cudaStream_t st = (cudaStream_t)stream;
-    if (team == 8) lz4_kernel<8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
-    else lz4_kernel<32><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    if (variant == 88) lz4_kernel<8, 8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else if (variant == 8) lz4_kernel<8, 5><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else lz4_kernel<32, 1><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());
     return 0;

@@ -508,8 +508,9 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                 merge_gap_bytes=int(rng.choice([0, 4096])), checksum=int(rng.integers(0, 4)), pack_align=int(rng.choice([1, 16, 512])),
                 sq_entries=int(rng.choice([8, 64])), completion_bound=int(rng.choice([4, 1024])), statx_via_ring=int(rng.integers(0, 2)),
                 o_direct=int(rng.integers(0, 2)), poll_sleep_us=int(rng.choice([0, 50])), arena_bytes=96 << 20, staging_bytes=32 << 20,
+                min_copy_bytes=int(rng.choice([1 << 20, 8 << 20, 64 << 20])), flush_us=int(rng.choice([50, 200, 2000])),
             )
-            expect = {}
+            expect, group_of = {}, {}
             with lsio.IoUringCuda(int(rng.integers(1, 5)), **cfg) as u:
                 ud = 0
                 for fn, size in [files[int(k)] for k in rng.integers(0, len(files), 10)]:
@@ -531,9 +532,12 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                     ids = list(range(ud, ud + len(rs)))
                     for k, r in zip(ids, rs):
                         expect[k] = (fn, size, r)
+                        group_of[k] = u.current_group()
                     ud += len(rs)
                     u.get_ranges(fn, rs, ids)
-                seen = set()
+                    if rng.integers(0, 3) == 0:
+                        u.next_group()  # ordered groups at random points (sometimes several requests per group, sometimes one)
+                seen, last_group = set(), 0
                 rx = u.completion()
                 for n_got in range(len(expect)):
                     if n_got % 37 == 0 and it % 3 == 0:
@@ -541,6 +545,8 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                     c = rx.recv_timeout(30.0)
                     assert c.user_data not in seen, f"duplicate item for {c.user_data} with {cfg}"
                     seen.add(c.user_data)
+                    assert c.group == group_of[c.user_data] and c.group >= last_group, (cfg, c, last_group)  # items arrive in group order
+                    last_group = c.group
                     fn, size, (s, e) = expect[c.user_data]
                     rc, rr = oracle.resolve_range(size, s, e)
                     valid = rc == 0 and rr.end_off <= size and rr.end_off > rr.start_off
