@@ -257,7 +257,7 @@ def run_e2e(args, dev, paths, file_ids, expect_crc, steps, warmup, workers, o_di
     starts, ends = chunk_ranges()
     ud_lo = np.arange(N_CHUNKS, dtype=np.uint64)
     u = L.IoUringCuda(workers, devices=(dev.index,), arena_bytes=args.arena_gib << 30, staging_bytes=args.staging_mib << 20, o_direct=int(o_direct),
-                      min_copy_bytes=args.min_copy_mib << 20, flush_us=args.flush_us, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
+                      min_copy_bytes=args.min_copy_mib << 20, flush_us=args.flush_us, pack_threads=args.pack_threads, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
                       staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib)
     try:
         for _ in range(warmup):
@@ -653,6 +653,7 @@ def main():
     ap.add_argument("--staging-mib", type=int, default=1024)
     ap.add_argument("--arena-gib", type=int, default=8)
     ap.add_argument("--min-copy-mib", type=int, default=64)
+    ap.add_argument("--pack-threads", type=int, default=0, help="threads per CTA of the pipeline's pack launches (0 = 1024)")
     ap.add_argument("--flush-us", type=int, default=2000, help="a pack batch is launched once it holds --min-copy-mib or its oldest extent has waited this long")
     ap.add_argument("--sq-entries", type=int, default=64)
     ap.add_argument("--max-read-kib", type=int, default=512, help="reads (merged or split) are cut at this size")

@@ -72,6 +72,10 @@ typedef struct lsio_uring_cuda_config {
     uint32_t host_slots_per_worker; /* staging_mode 1: slots per worker (default 4) */
     uint32_t host_slot_kib;     /* staging_mode 1: slot (extent) size in KiB, >= max_read_bytes (default 2048): the
                                    granularity of the H2D copies; several reads of max_read_bytes can be in flight in one */
+    uint32_t pack_threads;      /* threads per CTA of the pipeline's pack launches: 0 = 1024 (one CTA fills an SM: the
+                                   configuration the kernel reaches the HBM roofline with); 256 = small footprint for a GPU
+                                   shared with the consumer's own kernels (a 1024-thread CTA waits for a whole SM to drain,
+                                   a 256-thread one for a single slot); the pipeline is PCIe-bound either way              */
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {

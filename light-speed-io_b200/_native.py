@@ -139,7 +139,8 @@ class CConfig(ctypes.Structure):
                 ("max_read_bytes", ctypes.c_uint64), ("min_copy_bytes", ctypes.c_uint64), ("flush_us", ctypes.c_uint32),
                 ("merge_ranges", ctypes.c_uint32), ("merge_gap_bytes", ctypes.c_uint64),
                 ("statx_via_ring", ctypes.c_uint32), ("poll_sleep_us", ctypes.c_uint32), ("zero_copy", ctypes.c_uint32),
-                ("staging_mode", ctypes.c_uint32), ("host_slots_per_worker", ctypes.c_uint32), ("host_slot_kib", ctypes.c_uint32)]
+                ("staging_mode", ctypes.c_uint32), ("host_slots_per_worker", ctypes.c_uint32), ("host_slot_kib", ctypes.c_uint32),
+                ("pack_threads", ctypes.c_uint32)]
 
 
 class CStats(ctypes.Structure):

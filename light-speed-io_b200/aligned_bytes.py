@@ -5,6 +5,7 @@ Same names and behaviour as crates/lsio_aligned_bytes/src/lib.rs: `AlignedBytesM
 `as_ptr`, `as_slice`, `clone`.  Where the reference returns Err / panics, these raise.
 """
 import ctypes
+import sys
 
 import numpy as np
 
@@ -76,6 +77,8 @@ class AlignedBytesMut:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():
+            return  # interpreter exit: no native (CUDA) calls from the garbage collector; the process is going away
         try:
             self.drop()
         except Exception:
@@ -189,6 +192,8 @@ class AlignedBytes:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():
+            return  # interpreter exit: no native (CUDA) calls from the garbage collector; the process is going away
         try:
             self.drop()
         except Exception:

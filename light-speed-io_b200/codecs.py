@@ -7,6 +7,7 @@ PyTorch is plumbing here (output tensors, streams); the work is done by the sm_1
 csrc/codecs.cu.  There is no CPU fallback.
 """
 import ctypes
+import sys
 
 import numpy as np
 
@@ -202,6 +203,8 @@ class CodecPipeline:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():
+            return  # interpreter exit: no native (CUDA) calls from the garbage collector; the process is going away
         try:
             self.close()
         except Exception:

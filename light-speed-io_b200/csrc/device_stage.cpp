@@ -161,7 +161,7 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
         }
         LSIO_CUDA_TRY(cudaMemcpyAsync(b->dev_desc, b->host_desc, b->lay.upload_bytes, cudaMemcpyHostToDevice, g.s_pack));
         unsigned launches = 0;
-        int rc = pack_batch_launch(g.device, b->lay, b->dev_desc, b->counts, flags, b->crc_dev, g.s_pack, &launches);
+        int rc = pack_batch_launch(g.device, b->lay, b->dev_desc, b->counts, flags, b->crc_dev, g.s_pack, &launches, be->cfg.pack_threads);
         if (rc) return rc;
         be->stats.pack_launches++;
         be->stats.kernel_launches += launches;

@@ -34,9 +34,9 @@ bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCo
 // One-time per-device set-up (GF(2) tables to the device, kernel attributes). 0 or error code.
 int pack_prepare_device(int device);
 // Enqueues the pack kernel (+ fold kernel if any segment spans several tiles). The device must
-// be current. Returns 0 or a cudaError_t.
+// be current. `threads` per CTA: 0 = 1024 (the roofline configuration), or a smaller multiple of 32. Returns 0 or a cudaError_t.
 int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, const PackBatchCounts& c, uint32_t flags,
-                      uint32_t* crc_out, cudaStream_t stream, unsigned* launches);
+                      uint32_t* crc_out, cudaStream_t stream, unsigned* launches, unsigned threads);
 
 // misc_kernels.cu: XXH64 of n spans, arrays device-accessible, asynchronous on `stream`.
 int xxh64_launch_async(const uint64_t* ptrs_dev, const uint64_t* lens_dev, size_t n, uint64_t* out_dev, cudaStream_t stream);

@@ -47,7 +47,6 @@ namespace {
 
 constexpr uint32_t kPoly = gf2::kPoly;  // CRC-32C, reflected
 constexpr int kThreads = 1024;
-constexpr int kWarps = kThreads / 32;
 #ifndef LSIO_TILE_ROWS
 #define LSIO_TILE_ROWS 64  // 32 KiB tiles: measured 88 -> 92 % of HBM peak vs 16 KiB (per-tile overhead, DRAM locality)
 #endif
@@ -365,8 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
     const int tid = threadIdx.x, lane = tid & 31;
     if (kCrc) {
         // replicate the 4 KiB G table into the lane-private layout; copy the small tables
-        for (int i = tid; i < 1024 * 32; i += kThreads) sh[kSmG + i] = __ldg(p.tables + kG + (i >> 5));
-        for (int i = tid; i < kSmWords - kSmH; i += kThreads) sh[kSmH + i] = __ldg(p.tables + kH + i);
+        for (int i = tid; i < 1024 * 32; i += blockDim.x) sh[kSmG + i] = __ldg(p.tables + kG + (i >> 5));
+        for (int i = tid; i < kSmWords - kSmH; i += blockDim.x) sh[kSmH + i] = __ldg(p.tables + kH + i);
         __syncthreads();
     }
     const char* ltb = (const char*)(sh + kSmG) + lane * 4;
@@ -423,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
     // the last warp to run dry re-arms the scheduler for the next launch of this batch / plan
     if (lane == 0) {
         const uint32_t done = atomicAdd(p.sched + 1, 1u);
-        if (done == gridDim.x * kWarps - 1) {
+        if (done == gridDim.x * (blockDim.x >> 5) - 1) {
             p.sched[0] = 0;
             p.sched[1] = 0;
         }
@@ -537,7 +536,9 @@ bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCo
 }
 
 int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, const PackBatchCounts& c, uint32_t flags,
-                      uint32_t* crc_out, cudaStream_t st, unsigned* launches) {
+                      uint32_t* crc_out, cudaStream_t st, unsigned* launches, unsigned threads) {
+    if (threads == 0) threads = kThreads;
+    if (threads % 32 || threads > (unsigned)kThreads) return -EINVAL;
     const bool store = flags & LSIO_CUDA_PACK_STORE, crc = flags & LSIO_CUDA_PACK_CRC32C;
     if (launches) *launches = 0;
     if (c.ntiles == 0) return 0;
@@ -548,10 +549,12 @@ int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, c
     char* base = (char*)dev_block;
     Params p{(const Seg*)base, (const uint2*)(base + lay.off_tiles), c.ntiles, (uint32_t*)(base + lay.off_partials),
              (const uint32_t*)(base + lay.off_multi), c.nmulti, crc_out, tables, (uint32_t*)(base + lay.off_sched)};
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms, c.ntiles);
-    if (store && crc) pack_kernel<true, true><<<grid, kThreads, kSmBytes, st>>>(p);
-    else if (crc) pack_kernel<false, true><<<grid, kThreads, kSmBytes, st>>>(p);
-    else pack_kernel<true, false><<<grid, kThreads, 0, st>>>(p);
+    // one CTA per SM; `threads` < 1024 is the small-footprint launch for a GPU shared with the consumer's kernels
+    // (a 1024-thread CTA with 64 registers per thread needs a whole SM to itself)
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms, (c.ntiles + threads / 32 - 1) / (threads / 32));
+    if (store && crc) pack_kernel<true, true><<<grid, threads, kSmBytes, st>>>(p);
+    else if (crc) pack_kernel<false, true><<<grid, threads, kSmBytes, st>>>(p);
+    else pack_kernel<true, false><<<grid, threads, 0, st>>>(p);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     if (launches) ++*launches;
     LSIO_CUDA_TRY(cudaGetLastError());
@@ -616,7 +619,7 @@ int lsio_cuda_pack_plan_launch(lsio_cuda_pack_plan* plan, uint32_t* crc_out_dev,
     if ((plan->flags & LSIO_CUDA_PACK_CRC32C) && !crc_out_dev && plan->counts.nsegs) return -EINVAL;
     DeviceGuard dg(plan->device);
     if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
-    return pack_batch_launch(plan->device, plan->lay, plan->dev_block, plan->counts, plan->flags, crc_out_dev, (cudaStream_t)stream, nullptr);
+    return pack_batch_launch(plan->device, plan->lay, plan->dev_block, plan->counts, plan->flags, crc_out_dev, (cudaStream_t)stream, nullptr, 0);
 }
 
 uint64_t lsio_cuda_pack_plan_algorithmic_bytes(const lsio_cuda_pack_plan* plan) {

@@ -4,6 +4,7 @@ PyTorch is used only as plumbing here (device memory and streams); the kernels a
 hand-written sm_100a ones in csrc/pack_crc.cu and csrc/misc_kernels.cu.
 """
 import ctypes
+import sys
 
 import numpy as np
 
@@ -56,6 +57,8 @@ class PackPlan:
             self._h = ctypes.c_void_p()
 
     def __del__(self):
+        if sys.is_finalizing():
+            return  # interpreter exit: no native (CUDA) calls from the garbage collector; the process is going away
         try:
             self.close()
         except Exception:

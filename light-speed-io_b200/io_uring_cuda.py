@@ -10,6 +10,7 @@
     Err(anyhow::Error)               operation.rs:82-100     IoError item (returned, not raised -- it is a channel item)
 """
 import ctypes
+import sys
 import os
 
 import numpy as np
@@ -133,6 +134,8 @@ class Receiver:
             self._h = None
 
     def __del__(self):
+        if sys.is_finalizing():
+            return  # interpreter exit: no native (CUDA) calls from the garbage collector; the process is going away
         try:
             self.drop()
         except Exception:
@@ -255,6 +258,8 @@ class IoUringCuda:
         self.drop()
 
     def __del__(self):
+        if sys.is_finalizing():
+            return  # interpreter exit: no native (CUDA) calls from the garbage collector; the process is going away
         try:
             self.drop()
         except Exception:

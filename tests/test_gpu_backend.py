@@ -509,12 +509,13 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                 sq_entries=int(rng.choice([8, 64])), completion_bound=int(rng.choice([4, 1024])), statx_via_ring=int(rng.integers(0, 2)),
                 o_direct=int(rng.integers(0, 2)), poll_sleep_us=int(rng.choice([0, 50])), arena_bytes=96 << 20, staging_bytes=32 << 20,
                 min_copy_bytes=int(rng.choice([1 << 20, 8 << 20, 64 << 20])), flush_us=int(rng.choice([50, 200, 2000])),
+                pack_threads=int(rng.choice([0, 32, 256, 512, 1024])),
             )
             expect, group_of = {}, {}
             with lsio.IoUringCuda(int(rng.integers(1, 5)), **cfg) as u:
                 ud = 0
                 for fn, size in [files[int(k)] for k in rng.integers(0, len(files), 10)]:
-                    rs = []
+                    rs, req_bytes = [], 0
                     for _ in range(int(rng.integers(1, 40))):
                         kind = rng.integers(0, 10)
                         if kind == 0:
@@ -528,6 +529,11 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                             n = int(rng.integers(1, min(size, 2_000_000) + 1))
                             s = int(rng.integers(0, size - n + 1))
                             r = (s, s + n)
+                        rc, rr = oracle.resolve_range(size, r[0], r[1])
+                        if rc == 0 and rr.end_off <= size and rr.end_off > rr.start_off:
+                            if req_bytes + rr.end_off - rr.start_off > (40 << 20):
+                                continue  # one request's buffer must fit the 96 MiB arena (larger ones are in-band ENOMEM errors)
+                            req_bytes += rr.end_off - rr.start_off
                         rs.append(r)
                     ids = list(range(ud, ud + len(rs)))
                     for k, r in zip(ids, rs):
@@ -550,7 +556,7 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                     fn, size, (s, e) = expect[c.user_data]
                     rc, rr = oracle.resolve_range(size, s, e)
                     valid = rc == 0 and rr.end_off <= size and rr.end_off > rr.start_off
-                    assert c.is_ok() == valid, (cfg, (s, e), size, c)
+                    assert c.is_ok() == valid, (it, cfg, (s, e), size, c)
                     if valid:
                         want = oracle.pread_range(fn, s, e)
                         assert np.array_equal(c.buffer.as_slice(), want), (cfg, fn, (s, e))

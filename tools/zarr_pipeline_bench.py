@@ -190,8 +190,11 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--min-copy-mib", type=int, default=0, help="backend knob: pack launches are batched up to at least this much")
     ap.add_argument("--flush-us", type=int, default=0, help="backend knob: ...or until the oldest landed extent has waited this long")
+    ap.add_argument("--pack-threads", type=int, default=0)
     a = ap.parse_args()
     cfg = {}
+    if a.pack_threads:
+        cfg["pack_threads"] = a.pack_threads
     if a.min_copy_mib:
         cfg["min_copy_bytes"] = a.min_copy_mib << 20
     if a.flush_us:
