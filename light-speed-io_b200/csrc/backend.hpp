@@ -15,7 +15,6 @@
 #include <cstdarg>
 #include <deque>
 #include <fstream>
-#include <map>
 #include <sstream>
 #include <thread>
 
@@ -24,6 +23,7 @@
 #include "common.hpp"
 #include "gf2.hpp"
 #include "lsio_uring_cuda.h"
+#include "op_groups.hpp"
 #include "pack_batch.hpp"
 #include "staging.hpp"
 #include "threadpool.hpp"
@@ -180,16 +180,9 @@ struct Group {
 
 using OutChannel = Channel<lsio_output>;
 
-// Ordered groups of operations: planned in the reference (lsio_io/src/lib.rs:6-8, planned_design.md:71-72),
-// built here.  A request counts as finished when the last reference to it is released, which the
-// device stage does only after the request's items are in the completion channel.
-struct OpGroups {
-    std::mutex mu;
-    uint64_t current = 0;                 // group that new submissions join
-    uint64_t running = 0;                 // oldest group that may issue I/O
-    std::map<uint64_t, uint64_t> alive;   // unfinished requests per group
-    std::deque<std::pair<size_t, Op>> held;  // requests of groups > running, in submission order (device group, op)
-};
+// Ordered groups of operations (op_groups.hpp).  A request counts as finished when the last reference to it is
+// released, which the device stage does only after the request's items are in the completion channel.
+using OpGroups = OrderedGroups<std::pair<size_t, Op>>;  // (device group, op)
 
 struct Backend {
     lsio_uring_cuda_config cfg;

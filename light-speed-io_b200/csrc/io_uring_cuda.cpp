@@ -34,35 +34,12 @@ static void set_error(const char* fmt, ...) {
     va_end(ap);
     g_last_error = buf;
 }
-// ---- ordered groups (lsio_io/src/lib.rs:6-8) --------------------------------------------------------
-// Pops the held requests that `running` now admits. Caller holds og.mu; the ops are pushed after unlocking.
-static void release_held(OpGroups& og, std::vector<std::pair<size_t, Op>>& out) {
-    while (true) {
-        // running = the oldest group with unfinished requests, else the current group
-        og.running = og.alive.empty() ? og.current : std::min(og.alive.begin()->first, og.current);
-        bool any = false;
-        while (!og.held.empty() && og.held.front().second.req->op_group <= og.running) {
-            out.push_back(std::move(og.held.front()));
-            og.held.pop_front();
-            any = true;
-        }
-        if (!any) break;
-    }
-}
-
+// ---- ordered groups (lsio_io/src/lib.rs:6-8; bookkeeping in op_groups.hpp) --------------------------------
 Request::~Request() {
     if (fd >= 0) close(fd);  // only reached when the backend is torn down with reads still queued
     if (!be) return;
     std::vector<std::pair<size_t, Op>> go;
-    {
-        OpGroups& og = be->op_groups;
-        std::lock_guard<std::mutex> lk(og.mu);
-        auto it = og.alive.find(op_group);
-        if (it != og.alive.end() && --it->second == 0) {
-            og.alive.erase(it);
-            if (!be->closing.load()) release_held(og, go);
-        }
-    }
+    be->op_groups.finished(op_group, !be->closing.load(), &go);
     for (auto& [gi, op] : go) be->groups[gi]->pool->push(std::move(op));
 }
 
@@ -333,39 +310,19 @@ static int submit(lsio_uring_cuda* self, int group, const char* location, const 
     const size_t gi = group >= 0 ? (size_t)group : (size_t)(be->rr.fetch_add(1) % be->groups.size());
     if (gi >= be->groups.size()) return -EINVAL;
     r->grp = be->groups[gi].get();
-    Op op;
-    op.kind = Op::GetRanges;
-    op.req = r;
-    {
-        OpGroups& og = be->op_groups;
-        std::lock_guard<std::mutex> lk(og.mu);
-        r->op_group = og.current;
-        r->be = be;
-        og.alive[og.current]++;
-        if (og.current > og.running) {  // an earlier group is still in flight: hold the request back, unopened
-            og.held.emplace_back(gi, std::move(op));
-            return 0;
-        }
-    }
+    std::pair<size_t, Op> item;
+    item.first = gi;
+    item.second.kind = Op::GetRanges;
+    item.second.req = r;
+    r->be = be;  // from here on ~Request reports to the group bookkeeping
+    if (!be->op_groups.submit(item, &r->op_group)) return 0;  // an earlier group is still in flight: held back, unopened
     r.reset();
-    be->groups[gi]->pool->push(std::move(op));  // threadpool.rs:134-137
+    be->groups[gi]->pool->push(std::move(item.second));  // threadpool.rs:134-137
     return 0;
 }
 
-uint64_t lsio_uring_cuda_next_group(lsio_uring_cuda* self) {
-    if (!self) return 0;
-    OpGroups& og = self->be->op_groups;
-    std::lock_guard<std::mutex> lk(og.mu);
-    og.current++;
-    if (og.alive.empty()) og.running = og.current;  // nothing in flight: the new group may start at once
-    return og.current;
-}
-uint64_t lsio_uring_cuda_current_group(const lsio_uring_cuda* self) {
-    if (!self) return 0;
-    OpGroups& og = self->be->op_groups;
-    std::lock_guard<std::mutex> lk(og.mu);
-    return og.current;
-}
+uint64_t lsio_uring_cuda_next_group(lsio_uring_cuda* self) { return self ? self->be->op_groups.next_group() : 0; }
+uint64_t lsio_uring_cuda_current_group(const lsio_uring_cuda* self) { return self ? self->be->op_groups.current() : 0; }
 
 int lsio_uring_cuda_get_ranges(lsio_uring_cuda* self, const char* location, const int64_t* range_start, const int64_t* range_end, size_t n_ranges,
                                const uint64_t* user_data, size_t n_user_data) {
@@ -418,13 +375,7 @@ void lsio_uring_cuda_free(lsio_uring_cuda* self) {
     }
     joined.store(true);
     drainer.join();
-    {  // requests of later groups that were never admitted: dropped unopened
-        std::deque<std::pair<size_t, Op>> held;
-        {
-            std::lock_guard<std::mutex> lk(be->op_groups.mu);
-            held.swap(be->op_groups.held);
-        }
-    }
+    be->op_groups.take_held();  // requests of later groups that were never admitted: dropped unopened (outside the lock)
     for (auto& g : be->groups) free_group_cuda(*g);
     delete self;  // chunks already handed out keep the arena alive through their InnerBuffer
 }

@@ -7,10 +7,14 @@
 //   4 staging    the pinned ring run as a log: contiguity, wrap, registration boundary, in-order retire
 //   5 arena      first-fit + coalescing of the per-request HBM buffers
 //   6 gf2        crc32c_combine against a direct bitwise CRC
+//   7 groups     ordered groups of operations (planned: lsio_io/src/lib.rs:6-8): admission order, held submissions,
+//                empty groups, teardown, and a multi-threaded run checked for "group n finishes before n+1 starts"
 // Returns 0 on success, or (case * 100 + failed check).
 #include <linux/io_uring.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -19,6 +23,7 @@
 #include "channel.hpp"
 #include "gf2.hpp"
 #include "lsio_uring_cuda.h"
+#include "op_groups.hpp"
 #include "staging.hpp"
 #include "tracker.hpp"
 #include "uring.hpp"
@@ -186,6 +191,108 @@ extern "C" int lsio_uring_cuda_selftest(int which) {
         }
         CHECK(2, crc_bitwise((const uint8_t*)"123456789", 9) == 0xE3069283u);
         CHECK(3, gf2::multmodp(gf2::xpow(100), gf2::xpow(-100)) == 0x80000000u);  // x^100 * x^-100 == 1
+        return 0;
+    }
+    case 7: {
+        OrderedGroups<int> og;
+        uint64_t g = 99;
+        int a = 1, b = 2, c = 3, d = 4, e = 5;
+        std::vector<int> out;
+        CHECK(1, og.current() == 0 && og.submit(a, &g) && g == 0);  // group 0 starts at once
+        CHECK(2, og.submit(b, &g) && g == 0);
+        CHECK(3, og.next_group() == 1);
+        CHECK(4, !og.submit(c, &g) && g == 1 && og.held_count() == 1);  // group 1 waits for group 0
+        CHECK(5, og.next_group() == 2 && og.next_group() == 3);        // group 2 stays empty
+        CHECK(6, !og.submit(d, &g) && g == 3 && !og.submit(e, &g) && og.held_count() == 3);
+        og.finished(0, true, &out);
+        CHECK(7, out.empty());  // one submission of group 0 is still running
+        og.finished(0, true, &out);
+        CHECK(8, out.size() == 1 && out[0] == 3);  // group 1 admitted, group 3 not yet
+        out.clear();
+        og.finished(1, true, &out);
+        CHECK(9, out.size() == 2 && out[0] == 4 && out[1] == 5);  // the empty group 2 is skipped, order kept
+        out.clear();
+        og.finished(3, true, &out);
+        og.finished(3, true, &out);
+        int f = 6;
+        CHECK(10, out.empty() && og.submit(f, &g) && g == 3);  // nothing in flight: the current group runs at once
+        CHECK(11, og.next_group() == 4);
+        int h = 7;
+        CHECK(12, !og.submit(h, &g) && g == 4);
+        og.finished(3, false, &out);  // teardown: accounting only, nothing is released
+        CHECK(13, out.empty() && og.held_count() == 1 && og.take_held().size() == 1 && og.held_count() == 0);
+        // next_group with nothing in flight admits the new group immediately
+        OrderedGroups<int> og2;
+        CHECK(14, og2.next_group() == 1 && og2.submit(a, &g) && g == 1);
+        // concurrent: 4 submitters x 200 submissions with group changes, 4 finisher threads; every submission of
+        // group n must finish before any of group n+1 starts
+        struct Sub {
+            uint64_t group;
+        };
+        OrderedGroups<int> og3;
+        std::mutex mu;
+        std::vector<int> runnable;  // ids that may start
+        std::vector<uint64_t> group_of(800);
+        std::atomic<int> started{0}, finished{0}, violations{0};
+        std::map<uint64_t, int> running_per_group;
+        uint64_t max_started_group = 0;
+        std::atomic<bool> submit_done{false};
+        auto start = [&](int id) {  // caller holds mu
+            const uint64_t gg = group_of[id];
+            for (auto& kv : running_per_group)
+                if (kv.first < gg && kv.second > 0) violations++;  // an older group still has running work
+            if (gg < max_started_group) violations++;
+            max_started_group = std::max(max_started_group, gg);
+            running_per_group[gg]++;
+            runnable.push_back(id);
+            started++;
+        };
+        std::thread submitter([&] {
+            for (int id = 0; id < 800; id++) {
+                int item = id;
+                uint64_t gg;
+                {
+                    // group_of must be known before the item can be released by a finisher: submit under mu
+                    std::lock_guard<std::mutex> lk(mu);
+                    const bool now = og3.submit(item, &gg);
+                    group_of[id] = gg;
+                    if (now) start(id);
+                }
+                if (id % 7 == 6) og3.next_group();
+            }
+            submit_done = true;
+        });
+        std::vector<std::thread> finishers;
+        for (int t = 0; t < 4; t++)
+            finishers.emplace_back([&] {
+                while (finished.load() < 800) {
+                    int id = -1;
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (!runnable.empty()) {
+                            id = runnable.back();
+                            runnable.pop_back();
+                        }
+                    }
+                    if (id < 0) {
+                        std::this_thread::yield();
+                        continue;
+                    }
+                    std::vector<int> rel;
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        running_per_group[group_of[id]]--;
+                        og3.finished(group_of[id], true, &rel);
+                        for (int r : rel) start(r);
+                    }
+                    finished++;
+                }
+            });
+        submitter.join();
+        for (auto& t : finishers) t.join();
+        CHECK(15, started.load() == 800 && finished.load() == 800);
+        CHECK(16, violations.load() == 0);
+        CHECK(17, og3.held_count() == 0);
         return 0;
     }
     default:

@@ -221,7 +221,8 @@ def test_files_for_rank_is_a_partition(lsio):
 @pytest.mark.parametrize("which,name", [(1, "tracker (tracker.rs:74-114)"), (2, "user_data (user_data.rs:47-56)"),
                                         (3, "bounded channel: back-pressure, batch receive, disconnect"),
                                         (4, "staging ring as a log: wrap, no-straddle, in-order retire"),
-                                        (5, "HBM arena: first fit + coalescing"), (6, "crc32c_combine / GF(2) inverse")])
+                                        (5, "HBM arena: first fit + coalescing"), (6, "crc32c_combine / GF(2) inverse"),
+                                        (7, "ordered groups of operations (lsio_io lib.rs:6-8): admission, hold, teardown, threads")])
 def test_native_host_components(lsio, which, name):
     rc = lsio._native.lib.lsio_uring_cuda_selftest(which)
     assert rc == 0, f"{name}: check {rc % 100} failed"
