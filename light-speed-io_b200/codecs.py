@@ -147,7 +147,9 @@ class CodecPipeline:
                     raise TypeError(f"unknown codec {c!r}")
             arr = np.array(stages, dtype=np.uint32).reshape(-1, 2)
             h = ctypes.c_void_p()
-            self._max_batch = max(int(n), 16384)
+            # room for this batch, rounded up to a power of two (later, slightly larger batches reuse it); the scratch
+            # buffer is max_batch x decoded_nbytes of HBM, so it must follow the batch size, not a fixed count
+            self._max_batch = max(64, 1 << (max(int(n), 1) - 1).bit_length())
             N.check(N.lib.lsio_codec_pipeline_create(self.device, arr.ctypes.data, len(stages), self.decoded_nbytes, self._max_batch, ctypes.byref(h)),
                     "codec_pipeline_create (encode order must be Shuffle, LZ4, Crc32c)")
             self._h = h

@@ -660,3 +660,58 @@ def test_chunks_as_torch_tensors_through_dlpack(lsio, oracle, cuda_dev, data_dir
         assert torch.equal(rows.cpu(), torch.from_numpy(a[3:5]))
         assert bytes(raw.cpu().numpy()) == (b"\x00" * 1024 + a.tobytes())[1:1001]
         assert float(full.sum()) == pytest.approx(float(a.sum()), rel=1e-4)
+
+
+@pytest.mark.timeout(180)
+def test_abandoning_a_backend_mid_stream_never_hangs(lsio, oracle, cuda_dev, data_dir):
+    """A consumer that gives up early (an exception in its loop): the backend is dropped with requests in flight,
+    later groups still held back, unread items in a small channel, chunks and receiver clones still alive and
+    released afterwards in arbitrary order.  Every combination must tear down promptly."""
+    import gc
+
+    fn = os.path.join(data_dir, "ab")
+    oracle.write_file(fn, 9, 12 * MIB + 5)
+    rng = np.random.default_rng(77)
+    for it in range(40):
+        cfg = dict(staging_mode=int(rng.integers(0, 2)), completion_bound=int(rng.choice([2, 16, 1024])), arena_bytes=int(rng.choice([24, 96])) << 20,
+                   staging_bytes=16 << 20, checksum=int(rng.integers(0, 4)), max_read_bytes=int(rng.choice([65536, 524288])),
+                   min_copy_bytes=int(rng.choice([1, 64])) << 20, flush_us=int(rng.choice([50, 2000])), pack_threads=int(rng.choice([0, 256])))
+        u = lsio.IoUringCuda(int(rng.integers(1, 4)), **cfg)
+        rx = u.completion()
+        n_items = 0
+        for g in range(int(rng.integers(1, 5))):
+            for _ in range(int(rng.integers(1, 4))):
+                rs = []
+                for _ in range(int(rng.integers(1, 30))):
+                    n = int(rng.integers(1, 3 * MIB))
+                    s = int(rng.integers(0, 12 * MIB - n))
+                    rs.append((s, s + n))
+                if rng.integers(0, 6) == 0:
+                    rs.append((0, -1))  # 12 MiB more: sometimes larger than the small arena (in-band ENOMEM errors)
+                u.get_ranges(fn, rs, range(n_items, n_items + len(rs)))
+                n_items += len(rs)
+            if rng.integers(0, 2):
+                u.next_group()
+        kept = []
+        for _ in range(int(rng.integers(0, min(n_items, 12) + 1))):  # read a few items, keep some chunks alive
+            try:
+                c = rx.recv_timeout(20.0)
+            except lsio.RecvTimeoutError:  # everything left is stalled behind chunks we are holding: that is allowed
+                break
+            if c.is_ok() and rng.integers(0, 2):
+                kept.append(c)
+        order = int(rng.integers(0, 3))
+        t0 = time.time()
+        if order == 0:
+            u.drop()
+            rx.drop()
+        elif order == 1:
+            rx2 = rx.clone()
+            rx.drop()
+            u.drop()
+            rx2.drop()
+        else:
+            u.drop()  # the receiver and the chunks outlive the backend and go with the garbage collector
+        assert time.time() - t0 < 30, (it, cfg)
+        del kept, rx, u
+        gc.collect()
