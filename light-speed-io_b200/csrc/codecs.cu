@@ -215,6 +215,185 @@ __global__ void __launch_bounds__(kLzThreads, kMinCtas) lz4_kernel(const lsio_co
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// LZ4, launches with few blocks: parse first, copy in parallel
+// ---------------------------------------------------------------------------------------------------------
+// With few blocks in flight the kernel above is bound by the latency of ONE block: ~900 cycles per sequence,
+// because every sequence waits for its own copies (a store, a team sync, a load of bytes that were just written
+// and therefore come from L2, a store, a sync).  Parsing alone is cheap and is the only truly serial part, so this
+// kernel separates the two.  A warp owns a block and works in batches of 32 sequences:
+//   phase 1  every lane parses the same 32 sequences from the shared-memory window (tokens and lengths only);
+//            lane j keeps sequence j: where its literals come from and go to, its match offset and length;
+//   phase 2  lane j copies its own literals and its own match, 16 bytes per round trip (all loads first, then all
+//            stores), so the whole batch pays one memory latency instead of 32.  A match may read bytes that
+//            another match of the same batch produces; matches therefore retire in rounds: in each round every
+//            pending match whose source ends at or below the destination of the FIRST pending one is ready (all
+//            bytes below that point are final), the rest wait for the next round.  Runs longer than 16 bytes are
+//            copied by the whole warp.
+// Measured: +17-19 % per block only (19 MB/s instead of 16): on one warp the parse alone costs ~350 cycles per
+// sequence (a chain of ~50 dependent instructions and two shared-memory reads), which bounds any design that keeps
+// LZ4's token stream serial per block.  Used for launches of up to ~1.5k blocks.
+constexpr int kWideBytes = 16;  // bytes one lane moves per round trip
+
+// Lane-private copy of n <= 16 bytes: every load is issued before the first store.  period > 0: the source is the
+// `period` bytes at s repeated (a match overlapping its own output).
+__device__ __forceinline__ void lane_copy16(uint8_t* d, const uint8_t* s, uint32_t n, uint32_t period) {
+    uint32_t v[kWideBytes];
+#pragma unroll
+    for (int i = 0; i < kWideBytes; i++) {
+        v[i] = 0;
+        if ((uint32_t)i < n) v[i] = s[period ? (uint32_t)i % period : (uint32_t)i];
+    }
+#pragma unroll
+    for (int i = 0; i < kWideBytes; i++)
+        if ((uint32_t)i < n) d[i] = (uint8_t)v[i];
+}
+// Whole-warp copy of one long run (uniform arguments).
+__device__ __forceinline__ void warp_copy(uint8_t* d, const uint8_t* s, uint32_t n, uint32_t period, int lane) {
+    if (period) {
+        for (uint32_t i = lane; i < n; i += 32) d[i] = s[i % period];
+    } else if (n >= 64) {
+        lz_copy_long<32>(d, s, n, lane);
+    } else {
+        for (uint32_t i = lane; i < n; i += 32) d[i] = s[i];
+    }
+}
+
+__global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
+                                                              lsio_codec_result* __restrict__ results) {
+    constexpr int T = 32, kTeams = kLzThreads / T;
+    __shared__ __align__(16) uint8_t s_lz[kTeams * kLzWin];
+    const int team = threadIdx.x / T, lane = threadIdx.x % T;
+    const uint32_t idx = blockIdx.x * kTeams + team;
+    if (idx >= n_items) return;
+    const lsio_codec_item it = items[idx];
+    LzIn<T> in;
+    in.src = reinterpret_cast<const uint8_t*>(it.src);
+    in.n = it.src_len;
+    in.lead = (uint32_t)(it.src & 15);
+    in.win = s_lz + team * kLzWin;
+    in.ws = 0;
+    in.mask = 0xFFFFFFFFu;
+    in.l = lane;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(it.dst);
+    __builtin_assume(__isGlobal(dst));
+    __builtin_assume(__isGlobal(in.src));
+    const uint32_t n = it.src_len, cap = it.dst_cap;
+    uint32_t ip = 0, op = 0;
+    int status = LSIO_CODEC_OK;
+    bool done = false;
+    if (n == 0) status = LSIO_CODEC_ERR_INPUT;
+    else lz_fill(in);
+    while (status == LSIO_CODEC_OK && !done) {
+        // ---- phase 1: parse up to 32 sequences; lane j keeps sequence j ----
+        uint32_t my_lit_ip = 0, my_lit = 0, my_lop = 0, my_off = 0, my_ml = 0;
+        int nseq = 0;
+        for (; nseq < 32; nseq++) {
+            if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
+            uint32_t q = ip + in.lead - in.ws;
+            if (q + 20 > (uint32_t)kLzWin) {
+                in.ws = (ip + in.lead) & ~15u;
+                lz_fill(in);
+                q = ip + in.lead - in.ws;
+            }
+            const uint8_t* w = in.win + q;
+            const uint32_t token = w[0];
+            uint32_t lit = token >> 4, ml = token & 15, offset = 0, lit_ip;
+            bool last = false;
+            if (lit < 15) {  // the common case: everything up to the offset sits in the window
+                if (lit > n - ip - 1) { status = LSIO_CODEC_ERR_INPUT; break; }
+                if (lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
+                lit_ip = ip + 1;
+                ip += 1 + lit;
+                if (ip == n) last = true;
+                else if (n - ip < 2) status = LSIO_CODEC_ERR_INPUT;  // the literals are still valid output
+                else {
+                    offset = w[1 + lit] | (uint32_t)w[2 + lit] << 8;
+                    ip += 2;
+                }
+            } else {
+                ip++;
+                uint32_t b;
+                do {
+                    if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
+                    b = lz_byte(in, ip++);
+                    lit += b;
+                } while (b == 255);
+                if (status) break;
+                if (lit > n - ip) { status = LSIO_CODEC_ERR_INPUT; break; }
+                if (lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
+                lit_ip = ip;
+                ip += lit;
+                if (ip == n) last = true;
+                else if (n - ip < 2) status = LSIO_CODEC_ERR_INPUT;
+                else {
+                    offset = lz_byte(in, ip);
+                    offset |= lz_byte(in, ip + 1) << 8;
+                    ip += 2;
+                }
+            }
+            const uint32_t lop = op;
+            op += lit;
+            if (!last && status == LSIO_CODEC_OK) {
+                if (ml == 15) {
+                    uint32_t b;
+                    do {
+                        if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
+                        b = lz_byte(in, ip++);
+                        ml += b;
+                    } while (b == 255);
+                }
+                ml += 4;
+                if (status == LSIO_CODEC_OK && (offset == 0 || offset > op)) status = LSIO_CODEC_ERR_OFFSET;
+                if (status == LSIO_CODEC_OK && ml > cap - op) status = LSIO_CODEC_ERR_OUTPUT;
+            }
+            if (last || status != LSIO_CODEC_OK) ml = 0;  // literals only: the end of the block, or a match that cannot be used
+            if (lane == nseq) {
+                my_lit_ip = lit_ip;
+                my_lit = lit;
+                my_lop = lop;
+                my_off = offset;
+                my_ml = ml;
+            }
+            op += ml;
+            if (last) done = true;
+            if (last || status != LSIO_CODEC_OK) {
+                nseq++;
+                break;
+            }
+        }
+        // ---- phase 2: literals (no dependencies), then matches in rounds ----
+        const bool active = lane < nseq;
+        if (active && my_lit && my_lit <= (uint32_t)kWideBytes) lane_copy16(dst + my_lop, in.src + my_lit_ip, my_lit, 0);
+        for (unsigned m = __ballot_sync(0xFFFFFFFFu, active && my_lit > (uint32_t)kWideBytes); m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            warp_copy(dst + __shfl_sync(0xFFFFFFFFu, my_lop, j), in.src + __shfl_sync(0xFFFFFFFFu, my_lit_ip, j), __shfl_sync(0xFFFFFFFFu, my_lit, j), 0, lane);
+        }
+        __syncwarp();
+        const uint32_t my_mop = my_lop + my_lit;  // where this lane's match goes
+        const uint32_t my_src_hi = my_mop - my_off + (my_ml < my_off ? my_ml : my_off);
+        unsigned pending = __ballot_sync(0xFFFFFFFFu, active && my_ml != 0);
+        while (pending) {
+            // every byte below the destination of the first pending match is final
+            const uint32_t floor_op = __shfl_sync(0xFFFFFFFFu, my_mop, __ffs(pending) - 1);
+            const bool ready = ((pending >> lane) & 1u) && my_src_hi <= floor_op;
+            const uint32_t period = my_off < my_ml ? my_off : 0;
+            if (ready && my_ml <= (uint32_t)kWideBytes) lane_copy16(dst + my_mop, dst + my_mop - my_off, my_ml, period);
+            for (unsigned m = __ballot_sync(0xFFFFFFFFu, ready && my_ml > (uint32_t)kWideBytes); m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                const uint32_t mop = __shfl_sync(0xFFFFFFFFu, my_mop, j), off = __shfl_sync(0xFFFFFFFFu, my_off, j), ml = __shfl_sync(0xFFFFFFFFu, my_ml, j);
+                warp_copy(dst + mop, dst + mop - off, ml, off < ml ? off : 0, lane);
+            }
+            __syncwarp();
+            pending &= ~__ballot_sync(0xFFFFFFFFu, ready);
+        }
+    }
+    if (lane == 0) {
+        results[idx].out_len = op;
+        results[idx].status = status;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // byte shuffle / unshuffle
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t kShufTile = 16384;  // bytes of one buffer handled by one CTA
@@ -357,11 +536,14 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     // 4096 and 8192 blocks of 64 KiB (tools/codec_bench.py).
     // Measured on shuffled float32 chunks of 64 KiB (GB/s decoded): 16,384 blocks 122 (5 CTAs/SM) vs 116 (8 CTAs/SM);
     // 32,768 blocks 174 with 8; 65,536 blocks of 16 KiB 167 vs 193.
-    int variant = n > 24576 ? 88 : n > 6144 ? 8 : 32;  // 88: teams of 8, 8 CTAs/SM; 8: teams of 8, 5 CTAs/SM; 32: a warp per block
+    // Up to ~1.5k blocks the parse-then-copy kernel is ahead of a warp per block (4.9 vs 4.2 GB/s at 256 x 1 MiB, 19.4 vs 16.3
+    // at 1,024; 33 vs 32 at 2,048 x 64 KiB; behind from 4,096 on).
+    int variant = n > 24576 ? 88 : n > 6144 ? 8 : n > 1536 ? 32 : 1;  // 88 / 8: teams of 8 at 8 / 5 CTAs per SM; 32: a warp per block; 1: parse-then-copy
     if (const char* e = getenv("LSIO_LZ4_VARIANT")) variant = atoi(e);  // measurement knob (tools/codec_bench.py)
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 88) lz4_kernel<8, 8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     else if (variant == 8) lz4_kernel<8, 5><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else if (variant == 1) lz4_wide_kernel<<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     else lz4_kernel<32, 1><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());

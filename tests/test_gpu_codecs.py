@@ -38,8 +38,12 @@ def _lz4_batch(lsio, torch, blocks, caps, src_lead=0, dst_lead=0, replicate=1):
     return res, [o.cpu().numpy() for o in outs]
 
 
-def test_lz4_golden_vectors_from_liblz4(lsio, oracle, cuda_dev):
+@pytest.mark.parametrize("variant", [None, "1"])
+def test_lz4_golden_vectors_from_liblz4(lsio, oracle, cuda_dev, monkeypatch, variant):
     import torch
+
+    if variant:
+        monkeypatch.setenv("LSIO_LZ4_VARIANT", variant)
 
     vs = json.load(open(os.path.join(HERE, "golden", "codecs.json")))["vectors"]
     blocks = [bytes.fromhex(v["lz4_hex"]) for v in vs]
@@ -55,10 +59,11 @@ def test_lz4_golden_vectors_from_liblz4(lsio, oracle, cuda_dev):
             assert np.all(o[:32 + dst_lead] == 0xAB) and np.all(o[32 + dst_lead + len(want):] == 0xAB)  # nothing outside dst
 
 
-@pytest.mark.parametrize("variant", [None, "8", "88", "32"])
+@pytest.mark.parametrize("variant", [None, "8", "88", "32", "1"])
 def test_lz4_random_blocks_match_the_oracle(lsio, oracle, cuda_dev, monkeypatch, variant):
     """Many blocks per launch, both compressors (oracle's greedy one and liblz4), ragged sizes, misaligned.
-    Every kernel variant (LSIO_LZ4_VARIANT: teams of 8 lanes at 5 or 8 CTAs per SM, or a warp per block) must give the same bytes;
+    Every kernel variant (LSIO_LZ4_VARIANT: teams of 8 lanes at 5 or 8 CTAs per SM, a warp per block, or the parse-then-copy
+    kernel) must give the same bytes;
     None = the library's own choice by launch size."""
     import pyarrow as pa
     import torch
@@ -96,7 +101,7 @@ def test_lz4_random_blocks_match_the_oracle(lsio, oracle, cuda_dev, monkeypatch,
             assert np.all(o[:39] == 0xAB) and np.all(o[39 + len(d):] == 0xAB), i
 
 
-@pytest.mark.parametrize("variant", ["8", "88", "32"])
+@pytest.mark.parametrize("variant", ["8", "88", "32", "1"])
 def test_lz4_large_block_and_long_runs(lsio, oracle, cuda_dev, monkeypatch, variant):
     import torch
 
@@ -112,8 +117,12 @@ def test_lz4_large_block_and_long_runs(lsio, oracle, cuda_dev, monkeypatch, vari
         assert o[:len(d)].tobytes() == d and np.all(o[len(d):] == 0xAB)
 
 
-def test_lz4_malformed_blocks_report_their_own_status(lsio, oracle, cuda_dev):
+@pytest.mark.parametrize("variant", [None, "1"])
+def test_lz4_malformed_blocks_report_their_own_status(lsio, oracle, cuda_dev, monkeypatch, variant):
     import torch
+
+    if variant:
+        monkeypatch.setenv("LSIO_LZ4_VARIANT", variant)
 
     C = lsio.codecs
     good = recipe_bytes({"kind": "lowent", "n": 3000, "seed": 2, "alphabet": 4})
