@@ -164,12 +164,13 @@ class CodecPipeline:
 
         records = np.ascontiguousarray(records)
         n = len(records)
+        h = self._native(n)  # first: without a usable device this fails loudly here (no CPU fallback)
         if out is None:
             out = torch.empty((n, self.decoded_nbytes), dtype=torch.uint8, device=torch.device("cuda", self.device))
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         self._pending = (records, out)
-        N.check(N.lib.lsio_codec_pipeline_decode(self._native(n), records.ctypes.data, n, out.data_ptr(), _stream_ptr(stream)), "codec_pipeline_decode")
+        N.check(N.lib.lsio_codec_pipeline_decode(h, records.ctypes.data, n, out.data_ptr(), _stream_ptr(stream)), "codec_pipeline_decode")
         return out
 
     def finish(self):

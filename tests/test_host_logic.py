@@ -261,3 +261,60 @@ def test_dlpack_export_of_host_views(lsio):
     del cap
     a.drop()  # tensors keep the buffer alive after the view is gone
     assert int(t[4097]) == src[4097] and np.array_equal(f.numpy().view(np.uint8).ravel(), src)
+
+
+def test_codec_layer_host_side_without_a_gpu(lsio):
+    """The parts of the codec layer that are pure host code, and its loud failure without a device."""
+    import torch
+
+    C = lsio.codecs
+    # tile map: one {item, tile} pair per 16 KiB tile, in launch order; empty buffers take no tile
+    tm = C.shuffle_tile_map([0, 1, 16384, 16385, 50000])
+    assert tm.tolist() == [[1, 0], [2, 0], [3, 0], [3, 1], [4, 0], [4, 1], [4, 2], [4, 3]]
+    assert lsio._native.lib.lsio_codecs_shuffle_tiles(0) == 0 and lsio._native.lib.lsio_codecs_shuffle_tiles(16384 * 3) == 3
+    assert C.ITEM_DTYPE.itemsize == 24 and C.RESULT_DTYPE.itemsize == 8  # lsio_codec_item / lsio_codec_result layouts
+    assert C.crc32c_trailer_ok(C.CRC32C_RESIDUE) and not C.crc32c_trailer_ok(0)
+    items = C.make_items([16], [32], [4], [8])
+    assert items["src"][0] == 16 and items["dst"][0] == 32 and items["src_len"][0] == 4 and items["dst_cap"][0] == 8
+    with pytest.raises(ValueError):
+        C.CodecPipeline([C.LZ4()], 1000)  # rows are addressed as 16-byte vectors
+    if not torch.cuda.is_available():
+        with pytest.raises(lsio._native.LsioCudaError):  # no CPU fallback: the kernels are the product
+            C.lz4_decompress(items)
+        with pytest.raises(lsio._native.LsioCudaError):
+            C.unshuffle(items, 4)
+        with pytest.raises(lsio._native.LsioCudaError):
+            C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], 4096).decode_records(np.zeros(0, dtype=np.dtype(lsio._native.COutput)))
+
+
+def test_zarr_shard_index_parsing(lsio, oracle):
+    """lsio_b200.zarr_shard: the index range in get_ranges terms and the index parser (Zarr v3 sharding codec), on a
+    host view standing in for the landed chunk."""
+    import struct
+
+    Z = lsio.zarr_shard
+    assert Z.index_nbytes(10) == 164 and Z.index_nbytes(10, crc32c=False) == 160
+    assert Z.index_range(10) == (-164, -1) and Z.index_range(10, location="start") == (0, 164)
+    table = np.array([[100, 40], [0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF], [140, 7]], dtype="<u8")
+    raw = table.tobytes() + struct.pack("<I", oracle.crc32c(table.tobytes()))
+
+    class FakeChunk:  # what Receiver.recv returns, over host memory
+        def __init__(self, data, crc):
+            m = lsio.AlignedBytesMut(len(data), 512)
+            ctypes.memmove(m.as_mut_ptr(), data, len(data))
+            self.buffer = m.freeze().set_slice(0, len(data))
+            self.crc32c, self.user_data = crc, 0
+
+        def is_ok(self):
+            return True
+
+    off, nb = Z.parse_index(FakeChunk(raw, oracle.crc32c(raw)), 3)
+    assert off.tolist() == [100, 0xFFFFFFFFFFFFFFFF, 140] and nb.tolist() == [40, 0xFFFFFFFFFFFFFFFF, 7]
+    bad = bytearray(raw)
+    bad[5] ^= 1
+    with pytest.raises(Z.ShardIndexError, match="crc32c"):
+        Z.parse_index(FakeChunk(bytes(bad), oracle.crc32c(bytes(bad))), 3)
+    with pytest.raises(Z.ShardIndexError, match="bytes, expected"):
+        Z.parse_index(FakeChunk(raw, oracle.crc32c(raw)), 4)
+    off, nb = Z.parse_index(FakeChunk(table.tobytes(), None), 3, crc32c=False)
+    assert off.tolist()[0] == 100
