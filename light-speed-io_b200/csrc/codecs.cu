@@ -215,33 +215,48 @@ __global__ void __launch_bounds__(kLzThreads, kMinCtas) lz4_kernel(const lsio_co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// LZ4, launches with few blocks: parse first, copy in parallel
+// LZ4, launches with few blocks: parse in parallel, copy in parallel
 // ---------------------------------------------------------------------------------------------------------
 // With few blocks in flight the kernel above is bound by the latency of ONE block: ~900 cycles per sequence,
 // because every sequence waits for its own copies (a store, a team sync, a load of bytes that were just written
-// and therefore come from L2, a store, a sync).  Parsing alone is cheap and is the only truly serial part, so this
-// kernel separates the two.  A warp owns a block and works in batches of 32 sequences:
-//   phase 1  every lane parses the same 32 sequences from the shared-memory window (tokens and lengths only);
-//            lane j keeps sequence j: where its literals come from and go to, its match offset and length;
-//   phase 2  lane j copies its own literals and its own match, 16 bytes per round trip (all loads first, then all
-//            stores), so the whole batch pays one memory latency instead of 32.  A match may read bytes that
-//            another match of the same batch produces; matches therefore retire in rounds: in each round every
-//            pending match whose source ends at or below the destination of the FIRST pending one is ready (all
-//            bytes below that point are final), the rest wait for the next round.  Runs longer than 16 bytes are
-//            copied by the whole warp.
-// Measured: +17-19 % per block only (19 MB/s instead of 16): on one warp the parse alone costs ~350 cycles per
-// sequence (a chain of ~50 dependent instructions and two shared-memory reads), which bounds any design that keeps
-// LZ4's token stream serial per block.  Used for launches of up to ~1.5k blocks.
-constexpr int kWideBytes = 16;  // bytes one lane moves per round trip
+// and therefore come from L2, a store, a sync) and because a single warp retires a dependent instruction only
+// every few cycles (a plain serial parse alone measured ~350 cycles per sequence).  This kernel gives a warp one
+// block and works on the next 32 bytes of the compressed stream at a time:
+//   parse   lane j assumes a token at byte ip + j and decodes it in parallel with the others (literal length,
+//           match length, offset, where the next token would be); the real tokens are then found by following the
+//           "next" links from lane 0 with one warp shuffle per sequence, and a warp prefix sum over the real lanes
+//           gives every sequence its output position.  Tokens with length extensions, the end of the block and
+//           anything invalid fall back to a fully checked serial parse of one sequence.
+//   copy    every real lane copies its own literals and its own match, all loads before all stores, so the batch
+//           pays one memory latency instead of one per sequence.  A match may read bytes that another match of the
+//           same batch produces; matches therefore retire in rounds: in each round every pending match whose source
+//           ends at or below the destination of the FIRST pending one is ready (all bytes below that point are
+//           final), the rest wait for the next round.  Runs longer than kWideBytes are copied by the whole warp.
+constexpr int kWideBytes = 20;  // bytes one lane moves per round trip (a match without length extension is <= 18)
+constexpr int kWideSpan = 32;   // token positions examined per batch (one per lane)
+constexpr int kWideNeed = kWideSpan + 20;  // compressed bytes a batch may look at: the last position's token, 14 literals, offset
 
-// Lane-private copy of n <= 16 bytes: every load is issued before the first store.  period > 0: the source is the
-// `period` bytes at s repeated (a match overlapping its own output).
-__device__ __forceinline__ void lane_copy16(uint8_t* d, const uint8_t* s, uint32_t n, uint32_t period) {
+// Lane-private copy of n <= kWideBytes bytes: every load is issued before the first store.
+__device__ __forceinline__ void lane_copy(uint8_t* d, const uint8_t* s, uint32_t n) {
     uint32_t v[kWideBytes];
 #pragma unroll
     for (int i = 0; i < kWideBytes; i++) {
         v[i] = 0;
-        if ((uint32_t)i < n) v[i] = s[period ? (uint32_t)i % period : (uint32_t)i];
+        if ((uint32_t)i < n) v[i] = s[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kWideBytes; i++)
+        if ((uint32_t)i < n) d[i] = (uint8_t)v[i];
+}
+// The same for a match that overlaps its own output: the source is the `period` bytes at s, repeated.
+__device__ __forceinline__ void lane_copy_periodic(uint8_t* d, const uint8_t* s, uint32_t n, uint32_t period) {
+    uint32_t v[kWideBytes];
+    uint32_t j = 0;
+#pragma unroll
+    for (int i = 0; i < kWideBytes; i++) {
+        v[i] = 0;
+        if ((uint32_t)i < n) v[i] = s[j];
+        if (++j == period) j = 0;
     }
 #pragma unroll
     for (int i = 0; i < kWideBytes; i++)
@@ -261,6 +276,7 @@ __device__ __forceinline__ void warp_copy(uint8_t* d, const uint8_t* s, uint32_t
 __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
                                                               lsio_codec_result* __restrict__ results) {
     constexpr int T = 32, kTeams = kLzThreads / T;
+    constexpr unsigned kAll = 0xFFFFFFFFu;
     __shared__ __align__(16) uint8_t s_lz[kTeams * kLzWin];
     const int team = threadIdx.x / T, lane = threadIdx.x % T;
     const uint32_t idx = blockIdx.x * kTeams + team;
@@ -272,7 +288,7 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
     in.lead = (uint32_t)(it.src & 15);
     in.win = s_lz + team * kLzWin;
     in.ws = 0;
-    in.mask = 0xFFFFFFFFu;
+    in.mask = kAll;
     in.l = lane;
     uint8_t* dst = reinterpret_cast<uint8_t*>(it.dst);
     __builtin_assume(__isGlobal(dst));
@@ -284,10 +300,64 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
     if (n == 0) status = LSIO_CODEC_ERR_INPUT;
     else lz_fill(in);
     while (status == LSIO_CODEC_OK && !done) {
-        // ---- phase 1: parse up to 32 sequences; lane j keeps sequence j ----
+        // what this lane copies in this batch: literals [my_lit_ip, +my_lit) -> dst + my_lop, then a match of my_ml bytes
         uint32_t my_lit_ip = 0, my_lit = 0, my_lop = 0, my_off = 0, my_ml = 0;
-        int nseq = 0;
-        for (; nseq < 32; nseq++) {
+        unsigned real = 0;  // lanes that hold a sequence
+        // ---- parse, in parallel: lane j decodes the token that would start at ip + j ----
+        if (n - ip >= (uint32_t)kWideNeed) {  // far enough from the end: every field looked at is inside the block
+            uint32_t q = ip + in.lead - in.ws;
+            if (q + kWideNeed > (uint32_t)kLzWin) {
+                in.ws = (ip + in.lead) & ~15u;
+                lz_fill(in);
+                q = ip + in.lead - in.ws;
+            }
+            const uint8_t* w = in.win + q + lane;
+            const uint32_t token = w[0];
+            const uint32_t lit = token >> 4, mlc = token & 15;
+            const bool simple = lit < 15 && mlc < 15;  // no length extensions
+            const uint32_t offset = w[1 + lit] | (uint32_t)w[2 + lit] << 8;
+            const uint32_t nxt = simple ? (uint32_t)lane + 3 + lit : 0;  // where the next token would start; 0: not handled here
+            uint32_t cur = 0;
+            while (cur < (uint32_t)kWideSpan) {  // follow the links from the token at ip
+                const uint32_t nx = __shfl_sync(kAll, nxt, cur);
+                if (nx == 0) break;
+                real |= 1u << cur;
+                cur = nx;
+            }
+            if (real) {
+                const bool mine = (real >> lane) & 1u;
+                const uint32_t v = mine ? lit + mlc + 4 : 0;
+                uint32_t incl = v;  // inclusive prefix sum of the output bytes of the real sequences
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t up = __shfl_up_sync(kAll, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const uint32_t lop = op + (incl - v), mop = lop + lit;
+                // a sequence that does not fit the output or whose offset reaches before the output ends the batch:
+                // the checked parse below takes it (and reports the error if it is one)
+                const bool bad = mine && (incl > cap - op || offset == 0 || offset > mop);
+                const unsigned badmask = __ballot_sync(kAll, bad);
+                if (badmask) {
+                    cur = (uint32_t)__ffs(badmask) - 1;
+                    real &= (1u << cur) - 1u;
+                }
+                if (real) {
+                    if ((real >> lane) & 1u) {
+                        my_lit_ip = ip + lane + 1;
+                        my_lit = lit;
+                        my_lop = lop;
+                        my_off = offset;
+                        my_ml = mlc + 4;
+                    }
+                    const int lastl = 31 - __clz(real);  // the batch ends after the last real sequence
+                    op += __shfl_sync(kAll, incl, lastl);
+                    ip += cur;  // the first token not taken: the bad one, or where the last link points
+                }
+            }
+        }
+        if (!real) {
+            // ---- parse, serially: ONE sequence, fully checked (length extensions, the end of the block, errors) ----
             if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
             uint32_t q = ip + in.lead - in.ws;
             if (q + 20 > (uint32_t)kLzWin) {
@@ -297,9 +367,9 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
             }
             const uint8_t* w = in.win + q;
             const uint32_t token = w[0];
-            uint32_t lit = token >> 4, ml = token & 15, offset = 0, lit_ip;
-            bool last = false;
-            if (lit < 15) {  // the common case: everything up to the offset sits in the window
+            uint32_t lit = token >> 4, ml = token & 15, offset = 0, lit_ip = 0;
+            bool last = false, have = true;
+            if (lit < 15) {  // everything up to the offset sits in the window
                 if (lit > n - ip - 1) { status = LSIO_CODEC_ERR_INPUT; break; }
                 if (lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
                 lit_ip = ip + 1;
@@ -312,25 +382,27 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
                 }
             } else {
                 ip++;
-                uint32_t b;
+                uint32_t b = 0;
                 do {
-                    if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
+                    if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; have = false; break; }
                     b = lz_byte(in, ip++);
                     lit += b;
                 } while (b == 255);
-                if (status) break;
-                if (lit > n - ip) { status = LSIO_CODEC_ERR_INPUT; break; }
-                if (lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; break; }
-                lit_ip = ip;
-                ip += lit;
-                if (ip == n) last = true;
-                else if (n - ip < 2) status = LSIO_CODEC_ERR_INPUT;
-                else {
-                    offset = lz_byte(in, ip);
-                    offset |= lz_byte(in, ip + 1) << 8;
-                    ip += 2;
+                if (have && lit > n - ip) { status = LSIO_CODEC_ERR_INPUT; have = false; }
+                if (have && lit > cap - op) { status = LSIO_CODEC_ERR_OUTPUT; have = false; }
+                if (have) {
+                    lit_ip = ip;
+                    ip += lit;
+                    if (ip == n) last = true;
+                    else if (n - ip < 2) status = LSIO_CODEC_ERR_INPUT;
+                    else {
+                        offset = lz_byte(in, ip);
+                        offset |= lz_byte(in, ip + 1) << 8;
+                        ip += 2;
+                    }
                 }
             }
+            if (!have) break;
             const uint32_t lop = op;
             op += lit;
             if (!last && status == LSIO_CODEC_OK) {
@@ -347,44 +419,44 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
                 if (status == LSIO_CODEC_OK && ml > cap - op) status = LSIO_CODEC_ERR_OUTPUT;
             }
             if (last || status != LSIO_CODEC_OK) ml = 0;  // literals only: the end of the block, or a match that cannot be used
-            if (lane == nseq) {
+            if (lane == 0) {
                 my_lit_ip = lit_ip;
                 my_lit = lit;
                 my_lop = lop;
                 my_off = offset;
                 my_ml = ml;
             }
+            real = 1;
             op += ml;
             if (last) done = true;
-            if (last || status != LSIO_CODEC_OK) {
-                nseq++;
-                break;
-            }
         }
-        // ---- phase 2: literals (no dependencies), then matches in rounds ----
-        const bool active = lane < nseq;
-        if (active && my_lit && my_lit <= (uint32_t)kWideBytes) lane_copy16(dst + my_lop, in.src + my_lit_ip, my_lit, 0);
-        for (unsigned m = __ballot_sync(0xFFFFFFFFu, active && my_lit > (uint32_t)kWideBytes); m; m &= m - 1) {
+        // ---- copy: literals (no dependencies), then matches in rounds ----
+        const bool active = (real >> lane) & 1u;
+        if (active && my_lit && my_lit <= (uint32_t)kWideBytes) lane_copy(dst + my_lop, in.src + my_lit_ip, my_lit);
+        for (unsigned m = __ballot_sync(kAll, active && my_lit > (uint32_t)kWideBytes); m; m &= m - 1) {
             const int j = __ffs(m) - 1;
-            warp_copy(dst + __shfl_sync(0xFFFFFFFFu, my_lop, j), in.src + __shfl_sync(0xFFFFFFFFu, my_lit_ip, j), __shfl_sync(0xFFFFFFFFu, my_lit, j), 0, lane);
+            warp_copy(dst + __shfl_sync(kAll, my_lop, j), in.src + __shfl_sync(kAll, my_lit_ip, j), __shfl_sync(kAll, my_lit, j), 0, lane);
         }
         __syncwarp();
         const uint32_t my_mop = my_lop + my_lit;  // where this lane's match goes
         const uint32_t my_src_hi = my_mop - my_off + (my_ml < my_off ? my_ml : my_off);
-        unsigned pending = __ballot_sync(0xFFFFFFFFu, active && my_ml != 0);
+        unsigned pending = __ballot_sync(kAll, active && my_ml != 0);
         while (pending) {
             // every byte below the destination of the first pending match is final
-            const uint32_t floor_op = __shfl_sync(0xFFFFFFFFu, my_mop, __ffs(pending) - 1);
+            const uint32_t floor_op = __shfl_sync(kAll, my_mop, __ffs(pending) - 1);
             const bool ready = ((pending >> lane) & 1u) && my_src_hi <= floor_op;
             const uint32_t period = my_off < my_ml ? my_off : 0;
-            if (ready && my_ml <= (uint32_t)kWideBytes) lane_copy16(dst + my_mop, dst + my_mop - my_off, my_ml, period);
-            for (unsigned m = __ballot_sync(0xFFFFFFFFu, ready && my_ml > (uint32_t)kWideBytes); m; m &= m - 1) {
+            if (ready && my_ml <= (uint32_t)kWideBytes) {
+                if (period) lane_copy_periodic(dst + my_mop, dst + my_mop - my_off, my_ml, period);
+                else lane_copy(dst + my_mop, dst + my_mop - my_off, my_ml);
+            }
+            for (unsigned m = __ballot_sync(kAll, ready && my_ml > (uint32_t)kWideBytes); m; m &= m - 1) {
                 const int j = __ffs(m) - 1;
-                const uint32_t mop = __shfl_sync(0xFFFFFFFFu, my_mop, j), off = __shfl_sync(0xFFFFFFFFu, my_off, j), ml = __shfl_sync(0xFFFFFFFFu, my_ml, j);
+                const uint32_t mop = __shfl_sync(kAll, my_mop, j), off = __shfl_sync(kAll, my_off, j), ml = __shfl_sync(kAll, my_ml, j);
                 warp_copy(dst + mop, dst + mop - off, ml, off < ml ? off : 0, lane);
             }
             __syncwarp();
-            pending &= ~__ballot_sync(0xFFFFFFFFu, ready);
+            pending &= ~__ballot_sync(kAll, ready);
         }
     }
     if (lane == 0) {
