@@ -232,25 +232,12 @@ __global__ void __launch_bounds__(kLzThreads, kMinCtas) lz4_kernel(const lsio_co
 //           same batch produces; matches therefore retire in rounds: in each round every pending match whose source
 //           ends at or below the destination of the FIRST pending one is ready (all bytes below that point are
 //           final), the rest wait for the next round.  Runs longer than kWideBytes are copied by the whole warp.
-constexpr int kWideBytes = 20;  // bytes one lane moves per round trip (a match without length extension is <= 18)
-constexpr int kWideSpan = 32;   // token positions examined per batch (one per lane)
-constexpr int kWideNeed = kWideSpan + 20;  // compressed bytes a batch may look at: the last position's token, 14 literals, offset
+constexpr int kWideBytes = 20;  // bytes one lane moves per sequence and round trip (a match without length extension is <= 18)
 
-// Lane-private copy of n <= kWideBytes bytes: every load is issued before the first store.
-__device__ __forceinline__ void lane_copy(uint8_t* d, const uint8_t* s, uint32_t n) {
-    uint32_t v[kWideBytes];
-#pragma unroll
-    for (int i = 0; i < kWideBytes; i++) {
-        v[i] = 0;
-        if ((uint32_t)i < n) v[i] = s[i];
-    }
-#pragma unroll
-    for (int i = 0; i < kWideBytes; i++)
-        if ((uint32_t)i < n) d[i] = (uint8_t)v[i];
-}
-// The same for a match that overlaps its own output: the source is the `period` bytes at s, repeated.
-__device__ __forceinline__ void lane_copy_periodic(uint8_t* d, const uint8_t* s, uint32_t n, uint32_t period) {
-    uint32_t v[kWideBytes];
+// Lane-private copy of n <= kWideBytes bytes in two steps, so that a lane can issue the loads of several sequences
+// before the first store.  period > 0: the source is the `period` bytes at s repeated (a match overlapping its own
+// output); period == 0 never wraps.
+__device__ __forceinline__ void lane_load(uint32_t (&v)[kWideBytes], const uint8_t* s, uint32_t n, uint32_t period) {
     uint32_t j = 0;
 #pragma unroll
     for (int i = 0; i < kWideBytes; i++) {
@@ -258,6 +245,8 @@ __device__ __forceinline__ void lane_copy_periodic(uint8_t* d, const uint8_t* s,
         if ((uint32_t)i < n) v[i] = s[j];
         if (++j == period) j = 0;
     }
+}
+__device__ __forceinline__ void lane_store(uint8_t* d, const uint32_t (&v)[kWideBytes], uint32_t n) {
 #pragma unroll
     for (int i = 0; i < kWideBytes; i++)
         if ((uint32_t)i < n) d[i] = (uint8_t)v[i];
@@ -273,10 +262,15 @@ __device__ __forceinline__ void warp_copy(uint8_t* d, const uint8_t* s, uint32_t
     }
 }
 
+// H: token positions examined per batch = 32 * H (lane j looks at positions j, j + 32, ...): a larger batch spreads
+// the memory round trips of the copy phase over more sequences.
+template <int H>
 __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
                                                               lsio_codec_result* __restrict__ results) {
     constexpr int T = 32, kTeams = kLzThreads / T;
     constexpr unsigned kAll = 0xFFFFFFFFu;
+    constexpr uint32_t kSpan = 32 * H;       // token positions per batch
+    constexpr uint32_t kNeed = kSpan + 20;   // compressed bytes a batch may look at: the last position's token, 14 literals, offset
     __shared__ __align__(16) uint8_t s_lz[kTeams * kLzWin];
     const int team = threadIdx.x / T, lane = threadIdx.x % T;
     const uint32_t idx = blockIdx.x * kTeams + team;
@@ -300,63 +294,94 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
     if (n == 0) status = LSIO_CODEC_ERR_INPUT;
     else lz_fill(in);
     while (status == LSIO_CODEC_OK && !done) {
-        // what this lane copies in this batch: literals [my_lit_ip, +my_lit) -> dst + my_lop, then a match of my_ml bytes
-        uint32_t my_lit_ip = 0, my_lit = 0, my_lop = 0, my_off = 0, my_ml = 0;
-        unsigned real = 0;  // lanes that hold a sequence
-        // ---- parse, in parallel: lane j decodes the token that would start at ip + j ----
-        if (n - ip >= (uint32_t)kWideNeed) {  // far enough from the end: every field looked at is inside the block
+        // what this lane copies in this batch, per slot h: literals [lit_ip, +lit) -> dst + lop, then a match of ml bytes
+        uint32_t my_lit_ip[H], my_lit[H], my_lop[H], my_off[H], my_ml[H];
+        unsigned real[H];  // real[h] bit j: slot h of lane j holds a sequence
+#pragma unroll
+        for (int h = 0; h < H; h++) my_lit_ip[h] = my_lit[h] = my_lop[h] = my_off[h] = my_ml[h] = 0, real[h] = 0;
+        bool any = false;
+        // ---- parse, in parallel: slot h of lane j decodes the token that would start at ip + 32 h + j ----
+        if (n - ip >= kNeed) {  // far enough from the end: every field looked at is inside the block
             uint32_t q = ip + in.lead - in.ws;
-            if (q + kWideNeed > (uint32_t)kLzWin) {
+            if (q + kNeed > (uint32_t)kLzWin) {
                 in.ws = (ip + in.lead) & ~15u;
                 lz_fill(in);
                 q = ip + in.lead - in.ws;
             }
-            const uint8_t* w = in.win + q + lane;
-            const uint32_t token = w[0];
-            const uint32_t lit = token >> 4, mlc = token & 15;
-            const bool simple = lit < 15 && mlc < 15;  // no length extensions
-            const uint32_t offset = w[1 + lit] | (uint32_t)w[2 + lit] << 8;
-            const uint32_t nxt = simple ? (uint32_t)lane + 3 + lit : 0;  // where the next token would start; 0: not handled here
+            uint32_t lit[H], mlc[H], offset[H], nxt[H];
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                const uint8_t* w = in.win + q + 32 * h + lane;
+                const uint32_t token = w[0];
+                lit[h] = token >> 4;
+                mlc[h] = token & 15;
+                offset[h] = w[1 + lit[h]] | (uint32_t)w[2 + lit[h]] << 8;
+                // where the next token would start; 0: length extensions, not handled here
+                nxt[h] = (lit[h] < 15 && mlc[h] < 15) ? 32u * h + (uint32_t)lane + 3 + lit[h] : 0;
+            }
             uint32_t cur = 0;
-            while (cur < (uint32_t)kWideSpan) {  // follow the links from the token at ip
-                const uint32_t nx = __shfl_sync(kAll, nxt, cur);
+            while (cur < kSpan) {  // follow the links from the token at ip (cur is uniform)
+                uint32_t nx = 0;
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    if ((cur >> 5) == (uint32_t)h) nx = __shfl_sync(kAll, nxt[h], cur & 31);
                 if (nx == 0) break;
-                real |= 1u << cur;
+#pragma unroll
+                for (int h = 0; h < H; h++)
+                    if ((cur >> 5) == (uint32_t)h) real[h] |= 1u << (cur & 31);
                 cur = nx;
             }
-            if (real) {
-                const bool mine = (real >> lane) & 1u;
-                const uint32_t v = mine ? lit + mlc + 4 : 0;
-                uint32_t incl = v;  // inclusive prefix sum of the output bytes of the real sequences
+            // output positions: prefix sum of the output bytes of the real sequences, in position order
+            uint32_t v[H], incl[H], carry = 0;
+            unsigned badmask[H];
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                v[h] = ((real[h] >> lane) & 1u) ? lit[h] + mlc[h] + 4 : 0;
+                uint32_t x = v[h];
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t up = __shfl_up_sync(kAll, incl, d);
-                    if (lane >= d) incl += up;
+                    const uint32_t up = __shfl_up_sync(kAll, x, d);
+                    if (lane >= d) x += up;
                 }
-                const uint32_t lop = op + (incl - v), mop = lop + lit;
+                incl[h] = x + carry;
+                carry = __shfl_sync(kAll, incl[h], 31);
+                const uint32_t mop = op + incl[h] - v[h] + lit[h];
                 // a sequence that does not fit the output or whose offset reaches before the output ends the batch:
                 // the checked parse below takes it (and reports the error if it is one)
-                const bool bad = mine && (incl > cap - op || offset == 0 || offset > mop);
-                const unsigned badmask = __ballot_sync(kAll, bad);
-                if (badmask) {
-                    cur = (uint32_t)__ffs(badmask) - 1;
-                    real &= (1u << cur) - 1u;
-                }
-                if (real) {
-                    if ((real >> lane) & 1u) {
-                        my_lit_ip = ip + lane + 1;
-                        my_lit = lit;
-                        my_lop = lop;
-                        my_off = offset;
-                        my_ml = mlc + 4;
-                    }
-                    const int lastl = 31 - __clz(real);  // the batch ends after the last real sequence
-                    op += __shfl_sync(kAll, incl, lastl);
-                    ip += cur;  // the first token not taken: the bad one, or where the last link points
+                badmask[h] = __ballot_sync(kAll, ((real[h] >> lane) & 1u) && (incl[h] > cap - op || offset[h] == 0 || offset[h] > mop));
+            }
+            bool cut = false;
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                if (cut) real[h] = 0;
+                else if (badmask[h]) {
+                    const uint32_t pos = (uint32_t)__ffs(badmask[h]) - 1;
+                    real[h] &= (1u << pos) - 1u;
+                    cur = 32u * h + pos;
+                    cut = true;
                 }
             }
+            uint32_t total = 0;
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                if (real[h]) {
+                    any = true;
+                    total = __shfl_sync(kAll, incl[h], 31 - __clz(real[h]));  // the batch ends after its last real sequence
+                    if ((real[h] >> lane) & 1u) {
+                        my_lit_ip[h] = ip + 32u * h + lane + 1;
+                        my_lit[h] = lit[h];
+                        my_lop[h] = op + incl[h] - v[h];
+                        my_off[h] = offset[h];
+                        my_ml[h] = mlc[h] + 4;
+                    }
+                }
+            }
+            if (any) {
+                op += total;
+                ip += cur;  // the first token not taken: the bad one, or where the last link points
+            }
         }
-        if (!real) {
+        if (!any) {
             // ---- parse, serially: ONE sequence, fully checked (length extensions, the end of the block, errors) ----
             if (ip >= n) { status = LSIO_CODEC_ERR_INPUT; break; }
             uint32_t q = ip + in.lead - in.ws;
@@ -420,43 +445,72 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
             }
             if (last || status != LSIO_CODEC_OK) ml = 0;  // literals only: the end of the block, or a match that cannot be used
             if (lane == 0) {
-                my_lit_ip = lit_ip;
-                my_lit = lit;
-                my_lop = lop;
-                my_off = offset;
-                my_ml = ml;
+                my_lit_ip[0] = lit_ip;
+                my_lit[0] = lit;
+                my_lop[0] = lop;
+                my_off[0] = offset;
+                my_ml[0] = ml;
             }
-            real = 1;
+            real[0] = 1;
             op += ml;
             if (last) done = true;
         }
         // ---- copy: literals (no dependencies), then matches in rounds ----
-        const bool active = (real >> lane) & 1u;
-        if (active && my_lit && my_lit <= (uint32_t)kWideBytes) lane_copy(dst + my_lop, in.src + my_lit_ip, my_lit);
-        for (unsigned m = __ballot_sync(kAll, active && my_lit > (uint32_t)kWideBytes); m; m &= m - 1) {
-            const int j = __ffs(m) - 1;
-            warp_copy(dst + __shfl_sync(kAll, my_lop, j), in.src + __shfl_sync(kAll, my_lit_ip, j), __shfl_sync(kAll, my_lit, j), 0, lane);
+        uint32_t buf[H][kWideBytes];
+        bool act[H];
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            act[h] = (real[h] >> lane) & 1u;
+            if (act[h] && my_lit[h] && my_lit[h] <= (uint32_t)kWideBytes) lane_load(buf[h], in.src + my_lit_ip[h], my_lit[h], 0);
+        }
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            if (act[h] && my_lit[h] && my_lit[h] <= (uint32_t)kWideBytes) lane_store(dst + my_lop[h], buf[h], my_lit[h]);
+            for (unsigned m = __ballot_sync(kAll, act[h] && my_lit[h] > (uint32_t)kWideBytes); m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                warp_copy(dst + __shfl_sync(kAll, my_lop[h], j), in.src + __shfl_sync(kAll, my_lit_ip[h], j), __shfl_sync(kAll, my_lit[h], j), 0, lane);
+            }
         }
         __syncwarp();
-        const uint32_t my_mop = my_lop + my_lit;  // where this lane's match goes
-        const uint32_t my_src_hi = my_mop - my_off + (my_ml < my_off ? my_ml : my_off);
-        unsigned pending = __ballot_sync(kAll, active && my_ml != 0);
-        while (pending) {
-            // every byte below the destination of the first pending match is final
-            const uint32_t floor_op = __shfl_sync(kAll, my_mop, __ffs(pending) - 1);
-            const bool ready = ((pending >> lane) & 1u) && my_src_hi <= floor_op;
-            const uint32_t period = my_off < my_ml ? my_off : 0;
-            if (ready && my_ml <= (uint32_t)kWideBytes) {
-                if (period) lane_copy_periodic(dst + my_mop, dst + my_mop - my_off, my_ml, period);
-                else lane_copy(dst + my_mop, dst + my_mop - my_off, my_ml);
+        uint32_t my_mop[H], my_src_hi[H];
+        unsigned pending[H], any_pending = 0;
+#pragma unroll
+        for (int h = 0; h < H; h++) {
+            my_mop[h] = my_lop[h] + my_lit[h];  // where this slot's match goes
+            my_src_hi[h] = my_mop[h] - my_off[h] + (my_ml[h] < my_off[h] ? my_ml[h] : my_off[h]);
+            pending[h] = __ballot_sync(kAll, act[h] && my_ml[h] != 0);
+            any_pending |= pending[h];
+        }
+        while (any_pending) {
+            // every byte below the destination of the first pending match (in position order) is final
+            uint32_t floor_op = 0;
+            bool found = false;
+#pragma unroll
+            for (int h = 0; h < H; h++)
+                if (!found && pending[h]) {
+                    floor_op = __shfl_sync(kAll, my_mop[h], __ffs(pending[h]) - 1);
+                    found = true;
+                }
+            bool ready[H];
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                ready[h] = ((pending[h] >> lane) & 1u) && my_src_hi[h] <= floor_op;
+                if (ready[h] && my_ml[h] <= (uint32_t)kWideBytes)
+                    lane_load(buf[h], dst + my_mop[h] - my_off[h], my_ml[h], my_off[h] < my_ml[h] ? my_off[h] : 0);
             }
-            for (unsigned m = __ballot_sync(kAll, ready && my_ml > (uint32_t)kWideBytes); m; m &= m - 1) {
-                const int j = __ffs(m) - 1;
-                const uint32_t mop = __shfl_sync(kAll, my_mop, j), off = __shfl_sync(kAll, my_off, j), ml = __shfl_sync(kAll, my_ml, j);
-                warp_copy(dst + mop, dst + mop - off, ml, off < ml ? off : 0, lane);
+            any_pending = 0;
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                if (ready[h] && my_ml[h] <= (uint32_t)kWideBytes) lane_store(dst + my_mop[h], buf[h], my_ml[h]);
+                for (unsigned m = __ballot_sync(kAll, ready[h] && my_ml[h] > (uint32_t)kWideBytes); m; m &= m - 1) {
+                    const int j = __ffs(m) - 1;
+                    const uint32_t mop = __shfl_sync(kAll, my_mop[h], j), off = __shfl_sync(kAll, my_off[h], j), ml = __shfl_sync(kAll, my_ml[h], j);
+                    warp_copy(dst + mop, dst + mop - off, ml, off < ml ? off : 0, lane);
+                }
+                pending[h] &= ~__ballot_sync(kAll, ready[h]);
+                any_pending |= pending[h];
             }
             __syncwarp();
-            pending &= ~__ballot_sync(kAll, ready);
         }
     }
     if (lane == 0) {
@@ -615,7 +669,8 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 88) lz4_kernel<8, 8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     else if (variant == 8) lz4_kernel<8, 5><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
-    else if (variant == 1) lz4_wide_kernel<<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else if (variant == 1) lz4_wide_kernel<2><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else if (variant == 11) lz4_wide_kernel<1><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     else lz4_kernel<32, 1><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());
