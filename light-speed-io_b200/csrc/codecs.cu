@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(kLzThreads, kMinCtas) lz4_kernel(const lsio_co
 //           same batch produces; matches therefore retire in rounds: in each round every pending match whose source
 //           ends at or below the destination of the FIRST pending one is ready (all bytes below that point are
 //           final), the rest wait for the next round.  Runs longer than kWideBytes are copied by the whole warp.
+// Measured: 2x per block (32 instead of 16 MB/s; 1,024 blocks of 1 MiB decode at 32 GB/s); what remains is the copy
+// phase's two to three dependent L2 round trips per batch of ~7 sequences.
 constexpr int kWideBytes = 20;  // bytes one lane moves per sequence and round trip (a match without length extension is <= 18)
 
 // Lane-private copy of n <= kWideBytes bytes in two steps, so that a lane can issue the loads of several sequences
@@ -262,8 +264,9 @@ __device__ __forceinline__ void warp_copy(uint8_t* d, const uint8_t* s, uint32_t
     }
 }
 
-// H: token positions examined per batch = 32 * H (lane j looks at positions j, j + 32, ...): a larger batch spreads
-// the memory round trips of the copy phase over more sequences.
+// H: token positions examined per batch = 32 * H (lane j looks at positions j, j + 32, ...).  H = 2 spreads the memory
+// round trips of the copy phase over twice the sequences but needs more rounds per batch (longer dependence chains):
+// measured slower (24.6 vs 31.6 GB/s at 1,024 blocks of 1 MiB), so H = 1 is what launches use.
 template <int H>
 __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_item* __restrict__ items, uint32_t n_items,
                                                               lsio_codec_result* __restrict__ results) {
@@ -662,15 +665,15 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     // 4096 and 8192 blocks of 64 KiB (tools/codec_bench.py).
     // Measured on shuffled float32 chunks of 64 KiB (GB/s decoded): 16,384 blocks 122 (5 CTAs/SM) vs 116 (8 CTAs/SM);
     // 32,768 blocks 174 with 8; 65,536 blocks of 16 KiB 167 vs 193.
-    // Up to ~1.5k blocks the parse-then-copy kernel is ahead of a warp per block (4.9 vs 4.2 GB/s at 256 x 1 MiB, 19.4 vs 16.3
-    // at 1,024; 33 vs 32 at 2,048 x 64 KiB; behind from 4,096 on).
-    int variant = n > 24576 ? 88 : n > 6144 ? 8 : n > 1536 ? 32 : 1;  // 88 / 8: teams of 8 at 8 / 5 CTAs per SM; 32: a warp per block; 1: parse-then-copy
+    // Up to ~3k blocks the parallel-parse kernel is ahead of a warp per block (GB/s decoded, shuffled float32: 8.2 vs 4.2 at
+    // 256 x 1 MiB, 32.3 vs 16.3 at 1,024 x 1 MiB; 50.8 vs 53.1 at 4,096 x 64 KiB).
+    int variant = n > 24576 ? 88 : n > 6144 ? 8 : n > 3072 ? 32 : 1;  // 88 / 8: teams of 8 at 8 / 5 CTAs per SM; 32: a warp per block; 1 (2): parallel parse, 32 (64) positions per batch
     if (const char* e = getenv("LSIO_LZ4_VARIANT")) variant = atoi(e);  // measurement knob (tools/codec_bench.py)
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 88) lz4_kernel<8, 8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     else if (variant == 8) lz4_kernel<8, 5><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
-    else if (variant == 1) lz4_wide_kernel<2><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
-    else if (variant == 11) lz4_wide_kernel<1><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else if (variant == 1) lz4_wide_kernel<1><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
+    else if (variant == 2) lz4_wide_kernel<2><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     else lz4_kernel<32, 1><<<(unsigned)((n + 7) / 8), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());

@@ -87,7 +87,7 @@ def main():
                (1 << 20, 256), (4 << 20, 256)]
     if args.quick:
         configs = [(64 << 10, 4096)]
-    variants = ("auto", "8", "88", "32", "1")
+    variants = ("auto", "8", "88", "32", "1", "2")
     if args.single:
         k, bb, nb, var = args.single.split(":")
         kinds = {k: kinds[k]}
