@@ -665,9 +665,10 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     // 4096 and 8192 blocks of 64 KiB (tools/codec_bench.py).
     // Measured on shuffled float32 chunks of 64 KiB (GB/s decoded): 16,384 blocks 122 (5 CTAs/SM) vs 116 (8 CTAs/SM);
     // 32,768 blocks 174 with 8; 65,536 blocks of 16 KiB 167 vs 193.
-    // Up to ~3k blocks the parallel-parse kernel is ahead of a warp per block (GB/s decoded, shuffled float32: 8.2 vs 4.2 at
-    // 256 x 1 MiB, 32.3 vs 16.3 at 1,024 x 1 MiB; 50.8 vs 53.1 at 4,096 x 64 KiB).
-    int variant = n > 24576 ? 88 : n > 6144 ? 8 : n > 3072 ? 32 : 1;  // 88 / 8: teams of 8 at 8 / 5 CTAs per SM; 32: a warp per block; 1 (2): parallel parse, 32 (64) positions per batch
+    // Below ~6k blocks the parallel-parse kernel replaces a warp per block (GB/s decoded, shuffled float32 / 2-bit noise:
+    // 7.9 vs 4.2 at 256 x 1 MiB, 31.5 vs 16.4 at 1,024 x 1 MiB, 55.4 vs 47.0 at 4,096 x 1 MiB, 44.6 vs 31.8 at 2,048 x 64 KiB,
+    // 50.4 vs 34.9 (noise) but 47.2 vs 53.1 (float32) at 4,096 x 64 KiB); the warp-per-block variant stays selectable (32).
+    int variant = n > 24576 ? 88 : n > 6144 ? 8 : 1;  // 88 / 8: teams of 8 at 8 / 5 CTAs per SM; 1 (2): parallel parse, 32 (64) positions per batch; 32: a warp per block
     if (const char* e = getenv("LSIO_LZ4_VARIANT")) variant = atoi(e);  // measurement knob (tools/codec_bench.py)
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 88) lz4_kernel<8, 8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
