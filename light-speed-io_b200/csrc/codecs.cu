@@ -234,23 +234,32 @@ __global__ void __launch_bounds__(kLzThreads, kMinCtas) lz4_kernel(const lsio_co
 //           final), the rest wait for the next round.  Runs longer than kWideBytes are copied by the whole warp.
 // Measured: 2x per block (32 instead of 16 MB/s; 1,024 blocks of 1 MiB decode at 32 GB/s); what remains is the copy
 // phase's two to three dependent L2 round trips per batch of ~7 sequences.
-constexpr int kWideBytes = 20;  // bytes one lane moves per sequence and round trip (a match without length extension is <= 18)
+constexpr int kWideBytes = 18;  // bytes one lane moves per sequence and round trip (a match without length extension is <= 18)
+constexpr int kWideLits = 14;   // literals of a token without length extension
 
-// Lane-private copy of n <= kWideBytes bytes in two steps, so that a lane can issue the loads of several sequences
-// before the first store.  period > 0: the source is the `period` bytes at s repeated (a match overlapping its own
-// output); period == 0 never wraps.
-__device__ __forceinline__ void lane_load(uint32_t (&v)[kWideBytes], const uint8_t* s, uint32_t n, uint32_t period) {
+// Lane-private copy of n <= N bytes in two steps, so that a lane can issue the loads of all its bytes (and of several
+// sequences) before the first store.  The copy phase is bound by the instructions of these unrolled loops (mirroring the
+// batch in shared memory to save L2 round trips halved the speed), so they are kept minimal: no wrap handling here,
+// N = 14 for literals.
+template <int N>
+__device__ __forceinline__ void lane_load(uint32_t (&v)[kWideBytes], const uint8_t* s, uint32_t n) {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        if ((uint32_t)i < n) v[i] = s[i];
+}
+// A match overlapping its own output: the source is the `period` bytes at s, repeated.
+__device__ __forceinline__ void lane_load_periodic(uint32_t (&v)[kWideBytes], const uint8_t* s, uint32_t n, uint32_t period) {
     uint32_t j = 0;
 #pragma unroll
     for (int i = 0; i < kWideBytes; i++) {
-        v[i] = 0;
         if ((uint32_t)i < n) v[i] = s[j];
         if (++j == period) j = 0;
     }
 }
+template <int N>
 __device__ __forceinline__ void lane_store(uint8_t* d, const uint32_t (&v)[kWideBytes], uint32_t n) {
 #pragma unroll
-    for (int i = 0; i < kWideBytes; i++)
+    for (int i = 0; i < N; i++)
         if ((uint32_t)i < n) d[i] = (uint8_t)v[i];
 }
 // Whole-warp copy of one long run (uniform arguments).
@@ -464,12 +473,12 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
 #pragma unroll
         for (int h = 0; h < H; h++) {
             act[h] = (real[h] >> lane) & 1u;
-            if (act[h] && my_lit[h] && my_lit[h] <= (uint32_t)kWideBytes) lane_load(buf[h], in.src + my_lit_ip[h], my_lit[h], 0);
+            if (act[h] && my_lit[h] && my_lit[h] <= (uint32_t)kWideLits) lane_load<kWideLits>(buf[h], in.src + my_lit_ip[h], my_lit[h]);
         }
 #pragma unroll
         for (int h = 0; h < H; h++) {
-            if (act[h] && my_lit[h] && my_lit[h] <= (uint32_t)kWideBytes) lane_store(dst + my_lop[h], buf[h], my_lit[h]);
-            for (unsigned m = __ballot_sync(kAll, act[h] && my_lit[h] > (uint32_t)kWideBytes); m; m &= m - 1) {
+            if (act[h] && my_lit[h] && my_lit[h] <= (uint32_t)kWideLits) lane_store<kWideLits>(dst + my_lop[h], buf[h], my_lit[h]);
+            for (unsigned m = __ballot_sync(kAll, act[h] && my_lit[h] > (uint32_t)kWideLits); m; m &= m - 1) {
                 const int j = __ffs(m) - 1;
                 warp_copy(dst + __shfl_sync(kAll, my_lop[h], j), in.src + __shfl_sync(kAll, my_lit_ip[h], j), __shfl_sync(kAll, my_lit[h], j), 0, lane);
             }
@@ -498,13 +507,15 @@ __global__ void __launch_bounds__(kLzThreads) lz4_wide_kernel(const lsio_codec_i
 #pragma unroll
             for (int h = 0; h < H; h++) {
                 ready[h] = ((pending[h] >> lane) & 1u) && my_src_hi[h] <= floor_op;
-                if (ready[h] && my_ml[h] <= (uint32_t)kWideBytes)
-                    lane_load(buf[h], dst + my_mop[h] - my_off[h], my_ml[h], my_off[h] < my_ml[h] ? my_off[h] : 0);
+                if (ready[h] && my_ml[h] <= (uint32_t)kWideBytes) {
+                    if (my_off[h] < my_ml[h]) lane_load_periodic(buf[h], dst + my_mop[h] - my_off[h], my_ml[h], my_off[h]);
+                    else lane_load<kWideBytes>(buf[h], dst + my_mop[h] - my_off[h], my_ml[h]);
+                }
             }
             any_pending = 0;
 #pragma unroll
             for (int h = 0; h < H; h++) {
-                if (ready[h] && my_ml[h] <= (uint32_t)kWideBytes) lane_store(dst + my_mop[h], buf[h], my_ml[h]);
+                if (ready[h] && my_ml[h] <= (uint32_t)kWideBytes) lane_store<kWideBytes>(dst + my_mop[h], buf[h], my_ml[h]);
                 for (unsigned m = __ballot_sync(kAll, ready[h] && my_ml[h] > (uint32_t)kWideBytes); m; m &= m - 1) {
                     const int j = __ffs(m) - 1;
                     const uint32_t mop = __shfl_sync(kAll, my_mop[h], j), off = __shfl_sync(kAll, my_off[h], j), ml = __shfl_sync(kAll, my_ml[h], j);
@@ -665,9 +676,9 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     // 4096 and 8192 blocks of 64 KiB (tools/codec_bench.py).
     // Measured on shuffled float32 chunks of 64 KiB (GB/s decoded): 16,384 blocks 122 (5 CTAs/SM) vs 116 (8 CTAs/SM);
     // 32,768 blocks 174 with 8; 65,536 blocks of 16 KiB 167 vs 193.
-    // Below ~6k blocks the parallel-parse kernel replaces a warp per block (GB/s decoded, shuffled float32 / 2-bit noise:
-    // 7.9 vs 4.2 at 256 x 1 MiB, 31.5 vs 16.4 at 1,024 x 1 MiB, 55.4 vs 47.0 at 4,096 x 1 MiB, 44.6 vs 31.8 at 2,048 x 64 KiB,
-    // 50.4 vs 34.9 (noise) but 47.2 vs 53.1 (float32) at 4,096 x 64 KiB); the warp-per-block variant stays selectable (32).
+    // Below ~6k blocks the parallel-parse kernel replaces a warp per block (GB/s decoded, shuffled float32: 8.9 vs 4.2 at
+    // 256 x 1 MiB, 34.6 vs 16.4 at 1,024 x 1 MiB, 53.4 vs 31.8 at 2,048 x 64 KiB, 56.0 vs 53.1 at 4,096 x 64 KiB); the
+    // warp-per-block variant stays selectable (32).
     int variant = n > 24576 ? 88 : n > 6144 ? 8 : 1;  // 88 / 8: teams of 8 at 8 / 5 CTAs per SM; 1 (2): parallel parse, 32 (64) positions per batch; 32: a warp per block
     if (const char* e = getenv("LSIO_LZ4_VARIANT")) variant = atoi(e);  // measurement knob (tools/codec_bench.py)
     cudaStream_t st = (cudaStream_t)stream;
