@@ -391,3 +391,18 @@ def test_zarr_v3_sharded_read(lsio, oracle, cuda_dev, data_dir):
             os.fsync(fh.fileno())
         with pytest.raises(Z.ShardIndexError, match="crc32c"):
             Z.read_shards(u, paths[:1], n_inner)
+
+
+def test_plain_c_consumer_of_groups_and_codec_pipeline(lsio, cuda_dev, data_dir, tmp_path):
+    """tests/c/codec_pipeline_test.c: ordered groups, recv_batch, lsio_codec_pipeline_* and device AlignedBytes from
+    plain C against liblsio_b200.so -- the layers above the path need no Python and no C++ on the caller's side."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(lsio._native.LIB_PATH)
+    exe = str(tmp_path / "codec_pipeline_test")
+    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Werror", f"-I{root}/include", f"{root}/tests/c/codec_pipeline_test.c", f"-L{libdir}", "-llsio_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    p = subprocess.run([exe, data_dir], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "200 chunks in 2 ordered groups decoded by the native pipeline and match" in p.stdout
