@@ -782,6 +782,14 @@ def main():
         cpu = {"value": b / s / GIB, "unit": "GiB/s", "cores": min(cores, workers * 2), "kind": "port",
                "sample": f"one pass over all {len(paths)} files ({b} B) from {source}, 8 worker threads + SQPOLL, into fresh host buffers; {errs} errors",
                "nproc": cores}
+        # the figure as lsio_bench itself prints it: filesize x n_files / elapsed, i.e. counting the 57,792-byte tail of
+        # every file that it never reads (crates/lsio_bench/src/main.rs:137, :181-183): +0.14 %
+        cpu["reference_style_gib_s"] = FILE_SIZE * len(paths) / s / GIB
+        try:  # also at one worker per core, without SQPOLL (workers + kernel pollers would oversubscribe the box)
+            s3, b3, _ = cpu_ref_pass(paths, cores, sqpoll=False)
+            cpu["nproc_workers_no_sqpoll_gib_s"] = b3 / s3 / GIB
+        except Exception as ex:
+            cpu["nproc_workers_no_sqpoll_gib_s"] = repr(ex)
         s2, b2, _ = cpu_ref_pass(paths, workers, mode=1)
         cpu["object_store_like_gib_s"] = b2 / s2 / GIB
 
