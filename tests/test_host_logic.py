@@ -318,3 +318,26 @@ def test_zarr_shard_index_parsing(lsio, oracle):
         Z.parse_index(FakeChunk(raw, oracle.crc32c(raw)), 4)
     off, nb = Z.parse_index(FakeChunk(table.tobytes(), None), 3, crc32c=False)
     assert off.tolist()[0] == 100
+
+
+def test_codec_pipeline_argument_checks(lsio):
+    """lsio_codec_pipeline_create refuses bad arguments before it touches the device."""
+    lib = lsio._native.lib
+    C = lsio.codecs
+
+    def create(stages, nbytes=4096, max_batch=16):
+        arr = np.array(stages, dtype=np.uint32).reshape(-1, 2)
+        h = ctypes.c_void_p()
+        rc = lib.lsio_codec_pipeline_create(0, arr.ctypes.data if len(stages) else None, len(stages), nbytes, max_batch, ctypes.byref(h))
+        if rc == 0:
+            lib.lsio_codec_pipeline_destroy(h)
+        return rc
+
+    assert create([(C.STAGE_SHUFFLE, 4), (C.STAGE_LZ4, 4)], nbytes=1000) == -22  # rows are 16-byte vectors
+    assert create([(C.STAGE_SHUFFLE, 4)], max_batch=0) == -22
+    assert create([(C.STAGE_SHUFFLE, 4)], nbytes=0) == -22
+    import torch
+
+    if not torch.cuda.is_available():  # valid arguments get as far as the device check, and stop there: no CPU fallback
+        assert create([(C.STAGE_SHUFFLE, 4), (C.STAGE_LZ4, 4), (C.STAGE_CRC32C, 0)]) > 0
+    # (stage order and the shuffle element size are checked after the device count: covered by the GPU tests)
