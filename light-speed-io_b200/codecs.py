@@ -116,8 +116,12 @@ class CodecPipeline:
     array's chunk shape is fixed), so the result is one (n_chunks, decoded_nbytes) uint8 tensor in HBM,
     chunk i in row i -- ready to be viewed as the array dtype and stacked into a training batch."""
 
-    def __init__(self, codecs, decoded_nbytes, device=0):
+    def __init__(self, codecs, decoded_nbytes, device=0, max_batch=None):
+        """`max_batch`: size the native pipeline (pinned descriptor arrays, HBM scratch of max_batch x decoded_nbytes) once,
+        up front; without it the pipeline is sized by the first batch and re-created -- tens to hundreds of milliseconds of
+        pinned and device allocation -- whenever a larger batch arrives."""
         self.codecs, self.decoded_nbytes, self.device = list(codecs), int(decoded_nbytes), int(device)
+        self._want_batch = int(max_batch) if max_batch else 0
         if self.decoded_nbytes % 16:
             raise ValueError("decoded_nbytes must be a multiple of 16 (rows are addressed as 16-byte vectors)")
 
@@ -149,7 +153,7 @@ class CodecPipeline:
             h = ctypes.c_void_p()
             # room for this batch, rounded up to a power of two (later, slightly larger batches reuse it); the scratch
             # buffer is max_batch x decoded_nbytes of HBM, so it must follow the batch size, not a fixed count
-            self._max_batch = max(64, 1 << (max(int(n), 1) - 1).bit_length())
+            self._max_batch = max(64, self._want_batch, 1 << (max(int(n), 1) - 1).bit_length())
             N.check(N.lib.lsio_codec_pipeline_create(self.device, arr.ctypes.data, len(stages), self.decoded_nbytes, self._max_batch, ctypes.byref(h)),
                     "codec_pipeline_create (encode order must be Shuffle, LZ4, Crc32c)")
             self._h = h

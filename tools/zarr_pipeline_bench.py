@@ -85,7 +85,7 @@ def run(chunk_kib=64, chunks=262144, files=256, batch=32768, workers=8, reps=3, 
         starts = [np.array([r[0] for r in rs], dtype=np.int64) for rs in ranges]
         ends = [np.array([r[1] for r in rs], dtype=np.int64) for rs in ranges]
         uds = [(np.uint64(f) << np.uint64(32)) | np.arange(per_file, dtype=np.uint64) for f in range(files)]
-        pipes = [C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], nbytes) for _ in range(2)]
+        pipes = [C.CodecPipeline([C.Shuffle(4), C.LZ4(), C.Crc32c()], nbytes, max_batch=batch) for _ in range(2)]
         streams = [torch.cuda.Stream(), torch.cuda.Stream()]
         expect = torch.from_numpy(np.stack([p[0] for p in pool])).cuda()
         results = []
@@ -102,13 +102,15 @@ def run(chunk_kib=64, chunks=262144, files=256, batch=32768, workers=8, reps=3, 
                         u.get_ranges_arrays(fns[f], starts[f][a:a + rpr], ends[f][a:a + rpr], uds[f][a:a + rpr])
                 got, t_decode, outs, trace = 0, 0.0, [], []
                 pending, inflight, k = [], [], 0  # two pipelines: batch k decodes while batch k+1 is received
+                n_pending = 0
                 while got < n:
-                    rec = rx.recv_batch(min(batch, n - got), timeout=30.0)  # numpy record array over lsio_output
+                    rec = rx.recv_batch(min(batch - n_pending, n - got), timeout=30.0)  # numpy record array over lsio_output
                     pending.append(rec)
                     got += len(rec)
-                    if sum(len(r) for r in pending) >= batch or got == n:
+                    n_pending += len(rec)
+                    if n_pending >= batch or got == n:  # never more than `batch`: the pipelines are sized once
                         rec = np.concatenate(pending)
-                        pending = []
+                        pending, n_pending = [], 0
                         if no_decode:
                             L.Receiver.drop_buffers(rec)
                             continue
