@@ -406,3 +406,66 @@ def test_plain_c_consumer_of_groups_and_codec_pipeline(lsio, cuda_dev, data_dir,
     p = subprocess.run([exe, data_dir], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "200 chunks in 2 ordered groups decoded by the native pipeline and match" in p.stdout
+
+
+def test_zarr_v3_sharded_array_by_chunk_coordinates(lsio, oracle, cuda_dev, data_dir):
+    """lsio_b200.zarr_v3.ShardedArray over a hand-written Zarr v3 store (zarr.json + shard files per the v3 spec and the
+    sharding codec): inner chunks addressed by grid coordinates come back as float32 tiles equal to the source array, with
+    the fill value for chunks never written and for a shard that does not exist; duplicates and arbitrary order allowed."""
+    import json
+    import torch
+
+    ZV = lsio.zarr_v3
+    rng = np.random.default_rng(5)
+    shape, shard_shape, inner = (64, 96), (32, 48), (8, 16)
+    fill = 7.5
+    full = (np.cumsum(rng.standard_normal(shape), axis=1) * 0.1).astype("<f4").round(1)
+    root = os.path.join(data_dir, "arr.zarr")
+    os.makedirs(os.path.join(root, "c", "0"))
+    os.makedirs(os.path.join(root, "c", "1"))
+    meta = {"zarr_format": 3, "node_type": "array", "shape": list(shape), "data_type": "float32", "fill_value": fill,
+            "chunk_grid": {"name": "regular", "configuration": {"chunk_shape": list(shard_shape)}},
+            "chunk_key_encoding": {"name": "default", "configuration": {"separator": "/"}},
+            "codecs": [{"name": "sharding_indexed", "configuration": {
+                "chunk_shape": list(inner), "index_location": "end",
+                "index_codecs": [{"name": "bytes", "configuration": {"endian": "little"}}, {"name": "crc32c"}],
+                "codecs": [{"name": "bytes", "configuration": {"endian": "little"}}, {"name": "numcodecs.shuffle", "configuration": {"elementsize": 4}},
+                           {"name": "numcodecs.lz4", "configuration": {"acceleration": 1}}, {"name": "crc32c"}]}}]}
+    with open(os.path.join(root, "zarr.json"), "w") as f:
+        json.dump(meta, f)
+    per = (shard_shape[0] // inner[0], shard_shape[1] // inner[1])  # 4 x 3 inner chunks per shard
+    expect = full.copy()
+    for si in range(2):
+        for sj in range(2):
+            if (si, sj) == (1, 0):  # this shard is never written
+                expect[32:64, 0:48] = fill
+                continue
+            table = np.full((per[0] * per[1], 2), 0xFFFFFFFFFFFFFFFF, dtype="<u8")
+            body = bytearray()
+            for k in rng.permutation(per[0] * per[1]):
+                a, b = divmod(int(k), per[1])
+                r0, c0 = si * 32 + a * 8, sj * 48 + b * 16
+                if rng.integers(0, 5) == 0:  # an inner chunk that was never written
+                    expect[r0:r0 + 8, c0:c0 + 16] = fill
+                    continue
+                tile = np.ascontiguousarray(full[r0:r0 + 8, c0:c0 + 16])
+                stored = struct.pack("<I", tile.nbytes) + oracle.lz4_compress(oracle.shuffle(tile.tobytes(), 4)).tobytes()
+                stored += struct.pack("<I", oracle.crc32c(stored))
+                table[k] = (len(body), len(stored))
+                body += stored
+            index = table.tobytes() + struct.pack("<I", oracle.crc32c(table.tobytes()))
+            with open(os.path.join(root, "c", str(si), str(sj)), "wb") as fh:
+                fh.write(bytes(body) + index)
+    arr = ZV.ShardedArray(root)
+    coords = [(i, j) for i in range(8) for j in range(6)]
+    order = rng.permutation(len(coords))
+    ask = [coords[k] for k in order] + [coords[5], coords[5], (7, 0)]  # duplicates, a chunk of the missing shard again
+    with lsio.IoUringCuda(3, arena_bytes=64 << 20, staging_bytes=16 << 20) as u:
+        tiles = arr.read_inner_chunks(u, ask)
+        assert tiles.shape == (len(ask), 8, 16) and tiles.dtype == torch.float32 and tiles.is_cuda
+        host = tiles.cpu().numpy()
+        for t, (i, j) in zip(host, ask):
+            assert np.array_equal(t, expect[i * 8:(i + 1) * 8, j * 16:(j + 1) * 16]), (i, j)
+        # a second read on the same backend (groups keep counting), a single chunk
+        one = arr.read_inner_chunks(u, [(0, 0)])
+        assert np.array_equal(one[0].cpu().numpy(), expect[0:8, 0:16])

@@ -341,3 +341,51 @@ def test_codec_pipeline_argument_checks(lsio):
     if not torch.cuda.is_available():  # valid arguments get as far as the device check, and stop there: no CPU fallback
         assert create([(C.STAGE_SHUFFLE, 4), (C.STAGE_LZ4, 4), (C.STAGE_CRC32C, 0)]) > 0
     # (stage order and the shuffle element size are checked after the device count: covered by the GPU tests)
+
+
+def _write_zarr_json(path, **over):
+    import json
+
+    meta = {"zarr_format": 3, "node_type": "array", "shape": [64, 96], "data_type": "float32", "fill_value": 7.5,
+            "chunk_grid": {"name": "regular", "configuration": {"chunk_shape": [32, 48]}},
+            "chunk_key_encoding": {"name": "default", "configuration": {"separator": "/"}},
+            "codecs": [{"name": "sharding_indexed", "configuration": {
+                "chunk_shape": [8, 16], "index_location": "end",
+                "index_codecs": [{"name": "bytes", "configuration": {"endian": "little"}}, {"name": "crc32c"}],
+                "codecs": [{"name": "bytes", "configuration": {"endian": "little"}}, {"name": "numcodecs.shuffle", "configuration": {"elementsize": 4}},
+                           {"name": "numcodecs.lz4", "configuration": {"acceleration": 1}}, {"name": "crc32c"}]}}]}
+    meta.update(over)
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "zarr.json"), "w") as f:
+        json.dump(meta, f)
+    return meta
+
+
+def test_zarr_v3_sharded_array_metadata(lsio, tmp_path):
+    """lsio_b200.zarr_v3.ShardedArray: zarr.json of a sharded array -> shapes, codec chain, coordinate arithmetic;
+    anything it cannot decode is refused by name."""
+    ZV, C = lsio.zarr_v3, lsio.codecs
+    d = str(tmp_path / "a.zarr")
+    _write_zarr_json(d)
+    a = ZV.ShardedArray(d)
+    assert a.shape == (64, 96) and a.shard_shape == (32, 48) and a.inner_shape == (8, 16) and a.dtype == np.dtype("<f4")
+    assert a.inner_per_shard == (4, 3) and a.n_inner == 12 and a.inner_nbytes == 8 * 16 * 4 and a.index_crc32c and a.fill_value == 7.5
+    assert [type(c) for c in a.pipeline_codecs] == [C.Shuffle, C.LZ4, C.Crc32c] and a.pipeline_codecs[0].elementsize == 4
+    shard, within = a.locate([(0, 0), (3, 2), (4, 3), (7, 5), (5, 1)])
+    assert shard.tolist() == [[0, 0], [0, 0], [1, 1], [1, 1], [1, 0]] and within.tolist() == [0, 11, 0, 11, 4]  # C order over the 4 x 3 inner grid
+    assert a.shard_path((1, 0)) == os.path.join(d, "c/1/0")
+    with pytest.raises(IndexError):
+        a.locate([(8, 0)])
+    _write_zarr_json(d, chunk_key_encoding={"name": "default", "configuration": {"separator": "."}}, fill_value="NaN")
+    b = ZV.ShardedArray(d)
+    assert b.shard_path((1, 2)) == os.path.join(d, "c.1.2") and np.isnan(b.fill_value)
+    for over, what in (({"codecs": [{"name": "bytes"}]}, "sharding_indexed"), ({"data_type": "complex64"}, "data_type"),
+                       ({"chunk_grid": {"name": "rectilinear", "configuration": {}}}, "chunk_grid"), ({"zarr_format": 2}, "Zarr v3")):
+        _write_zarr_json(d, **over)
+        with pytest.raises(ZV.UnsupportedZarr, match=what):
+            ZV.ShardedArray(d)
+    meta = _write_zarr_json(d)
+    meta["codecs"][0]["configuration"]["codecs"].insert(1, {"name": "zstd", "configuration": {"level": 3}})
+    _write_zarr_json(d, codecs=meta["codecs"])
+    with pytest.raises(ZV.UnsupportedZarr, match="zstd"):
+        ZV.ShardedArray(d)
