@@ -36,6 +36,11 @@ typedef struct {
 
 #define LSIO_CUDA_PACK_STORE 1u  /* write the packed bytes (strip + gather)            */
 #define LSIO_CUDA_PACK_CRC32C 2u /* fused per-segment CRC-32C of the bytes as landed   */
+#define LSIO_CUDA_PACK_LIGHT 4u  /* small-footprint variant for launches that share the GPU with other kernels or carry
+                                    little data: 256-thread CTAs, 4 KiB of shared memory, one launch (the fold is fused).
+                                    Same results; the default variant (one 1024-thread CTA per SM, 128 KiB of tables) is
+                                    the one that reaches the HBM roofline on large launches.
+                                    With STORE, a segment whose src == dst is checksummed in place (nothing is moved). */
 
 typedef struct lsio_cuda_pack_plan lsio_cuda_pack_plan;
 

@@ -46,7 +46,7 @@ typedef struct lsio_uring_cuda_config {
     uint32_t o_direct;          /* 1 = O_RDONLY|O_DIRECT as the reference (sqe.rs:25); 0 = buffered          */
     uint64_t staging_bytes;     /* pinned + io_uring-registered staging ring per device                      */
     uint64_t arena_bytes;       /* HBM arena per device that request buffers are carved from                 */
-    uint64_t max_read_bytes;    /* reads (merged or not) are cut at this size; default 1 MiB, <= 1 GiB        */
+    uint64_t max_read_bytes;    /* reads (merged or not) are cut at this size; default 512 KiB, <= 1 GiB      */
     uint64_t min_copy_bytes;    /* a pack launch (staging_mode 0: and its coalesced H2D copy) is batched up to at least this
                                    many landed bytes (default 64 MiB) ...                                                     */
     uint32_t flush_us;          /* ...or until the oldest landed extent has waited this long (default 2000), or the burst is
@@ -76,6 +76,32 @@ typedef struct lsio_uring_cuda_config {
                                    configuration the kernel reaches the HBM roofline with); 256 = small footprint for a GPU
                                    shared with the consumer's own kernels (a 1024-thread CTA waits for a whole SM to drain,
                                    a 256-thread one for a single slot); the pipeline is PCIe-bound either way              */
+    /* ---- round 2 ---- */
+    uint32_t inline_reads;      /* what a worker does with a file the kernel cannot read asynchronously (no FMODE_NOWAIT:
+                                   tmpfs, hugetlbfs, some FUSE -- probed once per filesystem with preadv2(RWF_NOWAIT)):
+                                   io_uring would hand every such read to an io-wq kernel thread (a thread hop per read and
+                                   twice the threads; measured 3.3 vs 4.6 GiB/s per thread on tmpfs).  1 (default) = read those
+                                   files with preadv2() on the worker itself, into the same registered slot; 0 = always through
+                                   the ring (the reference's behaviour); 2 = always inline.  Files that can be read
+                                   asynchronously (O_DIRECT on a block device) always go through READ_FIXED unless 2.        */
+    uint32_t force_align;       /* 0 (default) = per-file O_DIRECT alignment max(512, stx_dio_offset_align, stx_dio_mem_align)
+                                   from statx(STATX_DIOALIGN) on the opened file (reference: fetched, unused, 512 hard-coded:
+                                   open_file.rs:23-25, sqe.rs:12); n = use n instead (power of two >= 512; test knob for 4Kn)  */
+    uint32_t debug_short_read_every; /* test knob: every k-th read is issued with a truncated length so that the short-read
+                                   retry path (get_range.rs:66-68 TODO in the reference) runs; 0 = off                        */
+    uint32_t null_source;       /* diagnostic: 1 = workers skip the read itself (slots keep whatever they held; files are still
+                                   opened and sized): measures the device stage alone -- bytes delivered are NOT the files'   */
+    uint32_t direct_landing;    /* 1 (default) = an extent whose payload forms at most 4 runs that are contiguous both in the
+                                   slot and in the request buffers is copied by H2D DMA straight into the arena (no device
+                                   staging ring, no pack kernel copy: the kernel only checksums in place, HBM traffic L instead
+                                   of 3L); anything else (small unaligned ranges) goes ring -> pack kernel.  0 = always ring    */
+    uint32_t cpu_first;         /* with cpu_count > 0: this backend's threads (workers + device thread of every group) are     */
+    uint32_t cpu_count;         /* pinned to CPUs [cpu_first, cpu_first + cpu_count) instead of the GPU's NUMA node            */
+    uint32_t steal_batch;       /* reads a worker takes from a peer's deque in one steal (default 4 = one extent's worth;
+                                   the reference steals one, worker.rs:58-62)                                                 */
+    uint32_t pack_light_below_mib; /* pipeline launches over batches smaller than this use the light kernel variant
+                                   (256-thread CTAs, 5 KiB of shared memory, co-resident with a consumer's kernels, fold fused);
+                                   larger ones the roofline variant.  default 512; 0 = never light                          */
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {
@@ -83,7 +109,24 @@ typedef struct lsio_uring_cuda_stats {
     uint64_t h2d_copies, h2d_bytes, pack_launches, kernel_launches, payload_bytes;
     uint64_t chunks_ok, errors;
     uint64_t staging_stalls, arena_stalls;
+    /* ---- round 2 ---- */
+    uint64_t inline_reads;      /* reads done with preadv2 on the worker (see lsio_uring_cuda_config.inline_reads)  */
+    uint64_t direct_extents;    /* extents landed by H2D DMA straight into the arena                                 */
+    uint64_t direct_copies;     /* cudaMemcpyAsync calls of those extents (one per run)                              */
+    uint64_t read_ns;           /* ns workers spent inside inline reads (sum over workers)                           */
+    uint64_t copy_enqueue_ns;   /* ns workers spent enqueueing H2D copies                                            */
+    uint64_t worker_stall_ns;   /* ns workers slept because no slot / no log space was free                          */
+    uint64_t worker_busy_ns;    /* ns workers were not parked (sum over workers)                                     */
+    uint64_t pack_kernel_ns;    /* device time of the pipeline's pack/crc launches (cudaEvent pairs on the pack stream) */
+    uint64_t pack_kernel_bytes; /* algorithmic bytes of those launches (2L for ring segments, L for in-place ones)   */
+    uint64_t first_chunk_ns;    /* ns from the first get_ranges after construction / reset to the first chunk sent   */
+    uint64_t max_dio_align;     /* largest per-file O_DIRECT alignment seen                                         */
 } lsio_uring_cuda_stats;
+
+/* Per-chunk latency histogram (submit of the request -> chunk in the channel), log2 buckets of microseconds:
+ * bucket i counts latencies in [2^i, 2^(i+1)) us, i = 0..31.  Reset together with the stats' first_chunk_ns. */
+int lsio_uring_cuda_get_latency_histogram(const lsio_uring_cuda* self, uint64_t buckets[32]);
+void lsio_uring_cuda_reset_latency(lsio_uring_cuda* self);
 
 void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg);
 /* IoUring::new(n_worker_threads): device 0, default config. Returns 0 or an error code. */
@@ -129,6 +172,14 @@ const char* lsio_uring_cuda_last_error(void);
  * once. *gib_per_s receives aggregate GiB/s. */
 int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads,
                             uint32_t queue_depth, uint32_t o_direct, double* gib_per_s);
+
+/* Same, reading the way the backend itself would with `inline_reads` (lsio_uring_cuda_config): 0 = always READ_FIXED
+ * through the ring, 1 = files the kernel cannot read asynchronously are read with preadv2 on the probing thread (cycling
+ * through the same queue_depth * block_bytes window), 2 = always preadv2.  The I/O ceiling bench.py reports is the best
+ * of several shapes of this probe, so that it bounds what the pipeline -- which does strictly more work per byte --
+ * can reach on the same files. */
+int lsio_probe_read_ceiling_ex(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads,
+                               uint32_t queue_depth, uint32_t o_direct, uint32_t inline_reads, double* gib_per_s);
 
 /* Test aid: host-logic self tests of the shipped components (tracker, user_data, channel, staging
  * log, arena, GF(2) combine), no GPU needed; see csrc/selftest.cpp. 0 = pass. */

@@ -37,6 +37,7 @@ class CudaSegment(ctypes.Structure):
 
 PACK_STORE = 1
 PACK_CRC32C = 2
+PACK_LIGHT = 4
 
 lib.lsio_cuda_pack_plan_create.restype = ctypes.c_int
 lib.lsio_cuda_pack_plan_create.argtypes = [ctypes.c_int, ctypes.POINTER(CudaSegment), ctypes.c_size_t, ctypes.c_uint32,
@@ -140,13 +141,18 @@ class CConfig(ctypes.Structure):
                 ("merge_ranges", ctypes.c_uint32), ("merge_gap_bytes", ctypes.c_uint64),
                 ("statx_via_ring", ctypes.c_uint32), ("poll_sleep_us", ctypes.c_uint32), ("zero_copy", ctypes.c_uint32),
                 ("staging_mode", ctypes.c_uint32), ("host_slots_per_worker", ctypes.c_uint32), ("host_slot_kib", ctypes.c_uint32),
-                ("pack_threads", ctypes.c_uint32)]
+                ("pack_threads", ctypes.c_uint32),
+                ("inline_reads", ctypes.c_uint32), ("force_align", ctypes.c_uint32), ("debug_short_read_every", ctypes.c_uint32),
+                ("null_source", ctypes.c_uint32), ("direct_landing", ctypes.c_uint32), ("cpu_first", ctypes.c_uint32),
+                ("cpu_count", ctypes.c_uint32), ("steal_batch", ctypes.c_uint32), ("pack_light_below_mib", ctypes.c_uint32)]
 
 
 class CStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("requests", "ranges", "reads", "short_reads", "read_bytes", "h2d_copies", "h2d_bytes",
                                                "pack_launches", "kernel_launches", "payload_bytes", "chunks_ok", "errors",
-                                               "staging_stalls", "arena_stalls")]
+                                               "staging_stalls", "arena_stalls", "inline_reads", "direct_extents", "direct_copies",
+                                               "read_ns", "copy_enqueue_ns", "worker_stall_ns", "worker_busy_ns", "pack_kernel_ns",
+                                               "pack_kernel_bytes", "first_chunk_ns", "max_dio_align")]
 
 
 for _name, _res, _args in [
@@ -159,6 +165,8 @@ for _name, _res, _args in [
     ("lsio_uring_cuda_next_group", ctypes.c_uint64, [_vp]),
     ("lsio_uring_cuda_current_group", ctypes.c_uint64, [_vp]),
     ("lsio_uring_cuda_get_stats", ctypes.c_int, [_vp, ctypes.POINTER(CStats)]),
+    ("lsio_uring_cuda_get_latency_histogram", ctypes.c_int, [_vp, c_u64p]),
+    ("lsio_uring_cuda_reset_latency", None, [_vp]),
     ("lsio_uring_cuda_last_error", ctypes.c_char_p, []),
     ("lsio_uring_cuda_free", None, [_vp]),
 ]:
@@ -188,6 +196,11 @@ lib.lsio_aligned_bytes_describe_many.argtypes = [ctypes.c_void_p, ctypes.c_size_
 lib.lsio_probe_read_ceiling.restype = ctypes.c_int
 lib.lsio_probe_read_ceiling.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
                                         ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
+
+
+lib.lsio_probe_read_ceiling_ex.restype = ctypes.c_int
+lib.lsio_probe_read_ceiling_ex.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
+                                           ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
 
 
 # ---- include/lsio_bench.h -------------------------------------------------------------------------

@@ -36,7 +36,15 @@ inline uint64_t now_ns() {
     return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-constexpr uint64_t kAlign = 512;  // crates/lsio_uring/src/sqe.rs:12
+constexpr uint64_t kAlign = 512;  // crates/lsio_uring/src/sqe.rs:12 -- the MINIMUM; the per-file value is Request::align
+
+// Limits that keep every unit of work inside one pack batch (device_stage.cpp flushes whole extents):
+// a read carries at most kMaxSegsPerRead descriptors / kMaxTilesPerRead kernel tiles (the planner cuts there),
+// an extent at most kMaxSegsPerExtent / kMaxTilesPerExtent (the worker closes it there), a batch holds
+// kBatchMaxSegs / kBatchMaxTiles.
+constexpr uint32_t kMaxSegsPerRead = 1024, kMaxTilesPerRead = 16384;
+constexpr uint32_t kMaxSegsPerExtent = 4096, kMaxTilesPerExtent = 32768;
+constexpr size_t kBatchMaxSegs = 8192, kBatchMaxTiles = 1 << 16;
 
 struct Group;
 struct Backend;
@@ -52,6 +60,7 @@ struct ReadPlan {
     uint32_t read_len = 0;   // multiple of 512
     uint32_t needed = 0;     // bytes that must land: the furthest payload byte of any of its segments
     uint32_t first_seg = 0, nsegs = 0;  // its segments are consecutive in Request::segs
+    uint32_t ntiles = 0;     // kernel tiles its segments need (pack_tile_count over their destinations)
 };
 struct SegPlan {
     uint32_t range = 0;
@@ -84,6 +93,9 @@ struct Request {
     uint8_t n_cqes_received = 0;
     uint64_t total_bytes = 0;
     uint64_t arena_epoch_seen = 0;  // arena epoch when this request last found the arena full
+    uint32_t align = kAlign;        // O_DIRECT alignment of this file: max(512, stx_dio_offset_align, stx_dio_mem_align) (open_file.rs:23-25)
+    bool inline_io = false;         // the kernel cannot read this file asynchronously: the worker reads it with preadv2 itself
+    uint64_t submit_ns = 0;         // when get_ranges was called (chunk latency)
     std::shared_ptr<InnerBuffer> buffer;  // the request's HBM buffer
     std::unique_ptr<RangePlan[]> ranges;
     std::vector<ReadPlan> reads;
@@ -111,11 +123,15 @@ struct Batch {
     uint32_t* crc_host = nullptr;  // pinned + mapped: the kernel writes results straight to the host
     uint32_t* crc_dev = nullptr;   // device alias of crc_host
     cudaEvent_t copied = nullptr, done = nullptr;
+    cudaEvent_t k0 = nullptr, k1 = nullptr;  // timing pair around this batch's kernel launches (stats.pack_kernel_ns)
+    bool timed = false;
+    uint64_t algo_bytes = 0;
     uint64_t seq_begin = 0, seq_end = 0;
     struct DescRef {
         uint64_t seq;  // staging extent (holds the request alive until the batch retires)
         uint32_t ref;  // read inside the extent
         uint32_t seg;
+        uint32_t kidx;  // index of its descriptor in the kernel batch (its CRC slot), or UINT32_MAX: landed directly, no checksum wanted
     };
     std::vector<DescRef> desc;  // segment of each descriptor
     std::vector<cudaEvent_t> copy_events;
@@ -146,7 +162,10 @@ struct WorkerSlots {
 
 struct Stats {
     std::atomic<uint64_t> requests{0}, ranges{0}, reads{0}, short_reads{0}, read_bytes{0}, h2d_copies{0}, h2d_bytes{0}, pack_launches{0},
-        kernel_launches{0}, payload_bytes{0}, chunks_ok{0}, errors{0}, staging_stalls{0}, arena_stalls{0};
+        kernel_launches{0}, payload_bytes{0}, chunks_ok{0}, errors{0}, staging_stalls{0}, arena_stalls{0}, inline_reads{0}, direct_extents{0},
+        direct_copies{0}, read_ns{0}, copy_enqueue_ns{0}, worker_stall_ns{0}, worker_busy_ns{0}, pack_kernel_ns{0}, pack_kernel_bytes{0},
+        first_submit_ns{0}, first_chunk_ns{0}, max_dio_align{0}, read_seq{0};
+    std::atomic<uint64_t> latency[32] = {};  // log2(us) buckets: request submitted -> chunk in the channel
 };
 
 struct Backend;

@@ -40,6 +40,16 @@ static void send_chunk(Group& g, const std::shared_ptr<Request>& rp, uint32_t ra
     o.chunk.user_data = p.user_data;
     o.group = r.op_group;
     be->stats.payload_bytes += p.len;
+    {   // chunk latency: request submitted -> chunk handed to the channel (log2 buckets of microseconds)
+        const uint64_t now = now_ns();
+        const uint64_t us = (now - r.submit_ns) / 1000;
+        be->stats.latency[us ? std::min(31, 63 - __builtin_clzll(us)) : 0].fetch_add(1, std::memory_order_relaxed);
+        if (!be->stats.first_chunk_ns.load(std::memory_order_relaxed)) {
+            uint64_t zero = 0;
+            const uint64_t first = be->stats.first_submit_ns.load(std::memory_order_relaxed);
+            be->stats.first_chunk_ns.compare_exchange_strong(zero, now > first ? now - first : 1);
+        }
+    }
     g.out_pending.push_back(o);  // flushed by flush_outputs(): one lock + one wake-up per retired batch, not per chunk
 }
 
@@ -72,9 +82,20 @@ static int flush_xxh(Group& g) {
             xb->ptrs[XxhBatch::kMax + i] = p.len;
         }
         int rc = xxh64_launch_async(xb->dev, xb->dev + XxhBatch::kMax, n, xb->dev + 2 * XxhBatch::kMax, g.s_pack);
-        if (rc) return rc;
-        g.be->stats.kernel_launches++;
-        LSIO_CUDA_TRY(cudaEventRecord(xb->done, g.s_pack));
+        if (rc == 0) {
+            g.be->stats.kernel_launches++;
+            const cudaError_t ce = cudaEventRecord(xb->done, g.s_pack);
+            if (ce != cudaSuccess) rc = cuda_fail(ce, "cudaEventRecord (xxh64 stage)", __FILE__, __LINE__);
+        }
+        if (rc) {
+            // errors instead of a hang: every range of this batch gets its Err item, the batch goes back to the pool
+            cudaStreamSynchronize(g.s_pack);
+            cudaGetLastError();
+            for (auto& it : xb->items) send_error(g.be, rc, 0, *it.req, (int)it.range, "CUDA error while enqueueing the xxh64 stage");
+            xb->items.clear();
+            g.xxh_free.push_back(xb);
+            return rc;
+        }
         g.xxh_inflight.push_back(xb);
     }
     return 0;
@@ -90,10 +111,20 @@ static void retire_batch(Group& g, Batch& b) {
             for (uint32_t k = 0; k < rd.nsegs; k++) ref.req->ranges[ref.req->segs[rd.first_seg + k].range].segs_left.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
-    for (uint32_t i = 0; i < b.counts.nsegs; i++) {
+    if (b.timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, b.k0, b.k1) == cudaSuccess) {
+            g.be->stats.pack_kernel_ns += (uint64_t)(ms * 1e6);
+            g.be->stats.pack_kernel_bytes += b.algo_bytes;
+        } else {
+            cudaGetLastError();
+        }
+        b.timed = false;
+    }
+    for (size_t i = 0; i < b.desc.size(); i++) {
         const std::shared_ptr<Request>& rp = g.log.at(b.desc[i].seq).reads[b.desc[i].ref].req;
         SegPlan& sp = rp->segs[b.desc[i].seg];
-        sp.crc = b.crc_host[i];
+        sp.crc = b.desc[i].kidx != UINT32_MAX ? b.crc_host[b.desc[i].kidx] : 0;
         RangePlan& p = rp->ranges[sp.range];
         if (p.segs_left.fetch_sub(1, std::memory_order_acq_rel) == 1) emit_range(g, rp, sp.range);
     }
@@ -115,8 +146,10 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
     const StageEntry& last = g.log.at(seq_end - 1);
     const uint64_t phys = first.log_off % cap, bytes = last.log_off + last.len - first.log_off;
     const bool store = true;
-    const uint32_t flags = LSIO_CUDA_PACK_STORE | ((be->cfg.checksum & LSIO_CHECKSUM_CRC32C) ? LSIO_CUDA_PACK_CRC32C : 0);
+    const bool want_crc = be->cfg.checksum & LSIO_CHECKSUM_CRC32C;
+    const uint32_t flags = LSIO_CUDA_PACK_STORE | (want_crc ? LSIO_CUDA_PACK_CRC32C : 0);
     uint64_t landed_bytes = 0;
+    b->algo_bytes = 0;
     std::vector<cudaEvent_t>& copy_events = b->copy_events;  // staging_mode 1: the H2D copy of every extent in this run
     copy_events.clear();
     for (uint64_t s = seq_begin; s < seq_end; s++) {
@@ -128,9 +161,16 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
             for (uint32_t k = 0; k < rd.nsegs; k++) {
                 const SegPlan& sp = ref.req->segs[rd.first_seg + k];
                 lsio_cuda_segment seg;
-                seg.src = (uint64_t)(uintptr_t)((be->cfg.zero_copy ? g.host_ring_dev : g.dev_ring) + e.log_off % cap + ref.off + sp.head);
                 seg.dst = (uint64_t)(uintptr_t)(ref.req->buffer->buf + sp.dst_off);
+                // an extent that landed directly is already in place: src == dst tells the kernel to checksum only
+                seg.src = e.direct ? seg.dst : (uint64_t)(uintptr_t)((be->cfg.zero_copy ? g.host_ring_dev : g.dev_ring) + e.log_off % cap + ref.off + sp.head);
                 seg.len = sp.payload_len;
+                if (e.direct && !want_crc) {  // nothing left to do on the device for this segment
+                    b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k, UINT32_MAX});
+                    continue;
+                }
+                b->algo_bytes += e.direct ? sp.payload_len : 2 * sp.payload_len;
+                const uint32_t kidx = b->counts.nsegs;
                 if (!pack_batch_append(b->lay, b->host_desc, &b->counts, seg, store)) {
                     // cannot happen: device_main sizes every run with the same tile arithmetic
                     RangePlan& p = ref.req->ranges[sp.range];
@@ -138,7 +178,7 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
                     p.segs_left.fetch_sub(1, std::memory_order_acq_rel);
                     continue;
                 }
-                b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k});
+                b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k, kidx});
             }
             landed_bytes += rd.read_len;
         }
@@ -159,10 +199,19 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
             be->stats.h2d_bytes += bytes;
             LSIO_CUDA_TRY(cudaStreamWaitEvent(g.s_pack, b->copied, 0));
         }
-        LSIO_CUDA_TRY(cudaMemcpyAsync(b->dev_desc, b->host_desc, b->lay.upload_bytes, cudaMemcpyHostToDevice, g.s_pack));
-        unsigned launches = 0;
-        int rc = pack_batch_launch(g.device, b->lay, b->dev_desc, b->counts, flags, b->crc_dev, g.s_pack, &launches, be->cfg.pack_threads);
+    }
+    if (b->counts.ntiles) {
+        // only the part of the descriptor block this batch filled travels (Seg | tiles | multi are separate arrays)
+        int rc = pack_batch_upload(b->lay, b->host_desc, b->dev_desc, b->counts, g.s_pack);
         if (rc) return rc;
+        unsigned launches = 0;
+        const bool light = be->cfg.pack_light_below_mib && b->counts.payload < ((uint64_t)be->cfg.pack_light_below_mib << 20);
+        LSIO_CUDA_TRY(cudaEventRecord(b->k0, g.s_pack));
+        rc = pack_batch_launch(g.device, b->lay, b->dev_desc, b->counts, flags | (light ? LSIO_CUDA_PACK_LIGHT : 0), b->crc_dev, g.s_pack, &launches,
+                               be->cfg.pack_threads);
+        if (rc) return rc;
+        LSIO_CUDA_TRY(cudaEventRecord(b->k1, g.s_pack));
+        b->timed = true;
         be->stats.pack_launches++;
         be->stats.kernel_launches += launches;
     }
@@ -182,7 +231,7 @@ void device_main(Group& g) {
     }
     cudaSetDevice(g.device);
     const uint64_t cap = g.log.capacity();
-    const size_t max_segs = g.batches[0].lay.max_segs, max_tiles = g.batches[0].lay.max_tiles;
+    const size_t max_segs = g.batches[0].lay.max_segs, max_tiles = g.batches[0].lay.max_tiles;  // >= 2 extents' worth: see backend.hpp
     const uint64_t max_batch_bytes = std::max<uint64_t>(cfg.min_copy_bytes * 4, 64ull << 20);
     unsigned idle_spins = 0;
     while (true) {
@@ -195,7 +244,7 @@ void device_main(Group& g) {
             if (q != cudaSuccess) {
                 cuda_fail(q, "pack batch", __FILE__, __LINE__);
                 fprintf(stderr, "lsio_b200: %s\n", last_error_text().c_str());
-                for (uint32_t i = 0; i < b->counts.nsegs; i++) {
+                for (size_t i = 0; i < b->desc.size(); i++) {
                     Request& rq = *g.log.at(b->desc[i].seq).reads[b->desc[i].ref].req;
                     const uint32_t range = rq.segs[b->desc[i].seg].range;
                     if (!rq.ranges[range].failed.exchange(true)) send_error(be, (int)q, 0, rq, (int)range, "CUDA error in the H2D/pack stage");
@@ -240,18 +289,9 @@ void device_main(Group& g) {
                     hit_limit = true;
                     break;
                 }
-                size_t t = 0;
-                size_t ns = 0;
-                for (auto& ref : e.reads) {
-                    if (ref.state != kStageLanded) continue;
-                    const ReadPlan& rd = ref.req->reads[ref.read];
-                    for (uint32_t k = 0; k < rd.nsegs; k++) {
-                        const SegPlan& sp = ref.req->segs[rd.first_seg + k];
-                        t += pack_tile_count((uint64_t)(uintptr_t)(ref.req->buffer->buf + sp.dst_off), sp.payload_len);
-                    }
-                    ns += rd.nsegs;
-                    if (!oldest) oldest = e.landed_ns;
-                }
+                // descriptors and kernel tiles of its landed reads, counted by the worker that published it
+                const size_t t = e.ntiles, ns = e.nsegs;
+                if (ns && !oldest) oldest = e.landed_ns;
                 newest = std::max(newest, e.landed_ns);
                 if (nsegs + ns > max_segs || ntiles + t > max_tiles || (bytes && bytes + e.len > max_batch_bytes)) {
                     hit_limit = true;

@@ -72,6 +72,8 @@ static std::vector<int> numa_cpus_of_device(int device) {
 static void free_group_cuda(Group& g) {
     DeviceGuard dg(g.device);
     for (Batch& b : g.batches) {
+        if (b.k0) cudaEventDestroy(b.k0);
+        if (b.k1) cudaEventDestroy(b.k1);
         if (b.host_desc) cudaFreeHost(b.host_desc);
         if (b.dev_desc) cudaFree(b.dev_desc);
         if (b.crc_host) cudaFreeHost(b.crc_host);
@@ -106,17 +108,23 @@ static int init_group(Group& g) {
     if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
     int rc = pack_prepare_device(g.device);
     if (rc) return rc;
-    if (cfg.pin_threads) g.cpus = numa_cpus_of_device(g.device);
+    if (cfg.cpu_count) {  // an explicit CPU slice (one process per GPU on a shared box: disjoint slices per rank)
+        for (uint32_t c = 0; c < cfg.cpu_count; c++) g.cpus.push_back((int)(cfg.cpu_first + c));
+    } else if (cfg.pin_threads) {
+        g.cpus = numa_cpus_of_device(g.device);
+    }
     const uint64_t ring_bytes = cfg.staging_bytes / 4096 * 4096;
     if (cfg.staging_mode == 1) {
         // per-worker cache-sized windows of pinned slots; the ordered log lives on the device only
         g.slot_bytes = std::max<uint64_t>((uint64_t)cfg.host_slot_kib << 10, (cfg.max_read_bytes + 4095) / 4096 * 4096);
         const uint64_t per_worker = g.slot_bytes * cfg.host_slots_per_worker;
-        LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.slot_block, per_worker * cfg.n_worker_threads, cudaHostAllocPortable));
+        // + 64 KiB: slots start at a 64 KiB boundary whatever the allocator returns (O_DIRECT memory alignment up to 64 KiB)
+        LSIO_CUDA_TRY(cudaHostAlloc((void**)&g.slot_block, per_worker * cfg.n_worker_threads + 65536, cudaHostAllocPortable));
+        uint8_t* slots0 = (uint8_t*)(((uintptr_t)g.slot_block + 65535) & ~(uintptr_t)65535);
         g.wslots.resize(cfg.n_worker_threads);
         for (uint32_t w = 0; w < cfg.n_worker_threads; w++) {
             WorkerSlots& ws = g.wslots[w];
-            ws.base = g.slot_block + per_worker * w;
+            ws.base = slots0 + per_worker * w;
             LSIO_CUDA_TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
             ws.ev.resize(cfg.host_slots_per_worker);
             ws.busy.assign(cfg.host_slots_per_worker, 0);
@@ -144,7 +152,7 @@ static int init_group(Group& g) {
     LSIO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     LSIO_CUDA_TRY(cudaStreamCreateWithPriority(&g.s_copy, cudaStreamNonBlocking, prio_hi));
     LSIO_CUDA_TRY(cudaStreamCreateWithPriority(&g.s_pack, cudaStreamNonBlocking, prio_hi));
-    const size_t max_segs = 8192, max_tiles = 1 << 16;
+    const size_t max_segs = kBatchMaxSegs, max_tiles = kBatchMaxTiles;
     g.batches.resize(8);
     for (Batch& b : g.batches) {
         b.lay = pack_batch_layout(max_segs, max_tiles);
@@ -155,6 +163,8 @@ static int init_group(Group& g) {
         LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&b.crc_dev, b.crc_host, 0));
         LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
         LSIO_CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        LSIO_CUDA_TRY(cudaEventCreate(&b.k0));
+        LSIO_CUDA_TRY(cudaEventCreate(&b.k1));
         b.desc.reserve(max_segs);
         g.free_batches.push_back(&b);
     }
@@ -217,6 +227,14 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->host_slot_kib = 2048;
     cfg->pack_threads = 0;
     cfg->poll_sleep_us = 50;  // measured: same throughput as spinning (33-34 GiB/s C2, 27.7 vs 28.1 C3) without burning a core per GPU
+    cfg->inline_reads = 1;
+    cfg->force_align = 0;
+    cfg->debug_short_read_every = 0;
+    cfg->null_source = 0;
+    cfg->direct_landing = 1;
+    cfg->cpu_first = cfg->cpu_count = 0;
+    cfg->steal_batch = 4;
+    cfg->pack_light_below_mib = 512;
 }
 
 int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {
@@ -228,6 +246,23 @@ int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uri
         cfg.min_copy_bytes = std::min<uint64_t>(cfg.min_copy_bytes, cfg.staging_bytes / 4);
     }
     if (cfg.zero_copy) cfg.staging_mode = 0;  // the kernel needs the whole pinned ring mapped
+    if (cfg.staging_mode == 1) {
+        // every worker must be able to hold two extents in the device log at once, and a slot holds at least one read
+        const uint64_t slot_bytes = std::max<uint64_t>((uint64_t)cfg.host_slot_kib << 10, (cfg.max_read_bytes + 4095) / 4096 * 4096);
+        if (cfg.host_slot_kib == 0 || slot_bytes > cfg.staging_bytes / 2) {
+            set_error("staging_mode 1: host_slot_kib must be > 0 and a slot (max(host_slot_kib KiB, max_read_bytes) = %llu B) at most staging_bytes / 2",
+                      (unsigned long long)slot_bytes);
+            return -EINVAL;
+        }
+    }
+    if (cfg.force_align && ((cfg.force_align & (cfg.force_align - 1)) || cfg.force_align < kAlign || cfg.force_align > 65536 || cfg.force_align > cfg.max_read_bytes)) {
+        set_error("force_align must be a power of two in [512, 65536] and at most max_read_bytes");
+        return -EINVAL;
+    }
+    if (cfg.inline_reads > 2) {
+        set_error("inline_reads must be 0, 1 or 2");
+        return -EINVAL;
+    }
     if (cfg.staging_mode == 1 && (cfg.host_slots_per_worker == 0 || cfg.host_slots_per_worker > 256 || cfg.n_worker_threads > 64)) {
         set_error("staging_mode 1 needs 1..256 host_slots_per_worker and at most 64 worker threads per device");
         return -EINVAL;
@@ -280,7 +315,7 @@ int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uri
             worker_main(*g, wt);
             g->workers_alive.fetch_sub(1, std::memory_order_acq_rel);
             g->be->out->remove_sender();
-        }, g->cpus);
+        }, g->cpus, cfg.steal_batch);
     }
     auto* h = new lsio_uring_cuda();
     h->be = std::move(be);
@@ -307,6 +342,11 @@ static int submit(lsio_uring_cuda* self, int group, const char* location, const 
     r->starts.assign(rs, rs + n);
     r->ends.assign(re, re + n);
     r->user_data.assign(ud, ud + n);
+    r->submit_ns = now_ns();
+    {
+        uint64_t zero = 0;
+        be->stats.first_submit_ns.compare_exchange_strong(zero, r->submit_ns);
+    }
     const size_t gi = group >= 0 ? (size_t)group : (size_t)(be->rr.fetch_add(1) % be->groups.size());
     if (gi >= be->groups.size()) return -EINVAL;
     r->grp = be->groups[gi].get();
@@ -347,7 +387,24 @@ int lsio_uring_cuda_get_stats(const lsio_uring_cuda* self, lsio_uring_cuda_stats
     o->h2d_copies = s.h2d_copies; o->h2d_bytes = s.h2d_bytes; o->pack_launches = s.pack_launches; o->kernel_launches = s.kernel_launches;
     o->payload_bytes = s.payload_bytes; o->chunks_ok = s.chunks_ok; o->errors = s.errors; o->staging_stalls = s.staging_stalls;
     o->arena_stalls = s.arena_stalls;
+    o->inline_reads = s.inline_reads; o->direct_extents = s.direct_extents; o->direct_copies = s.direct_copies; o->read_ns = s.read_ns;
+    o->copy_enqueue_ns = s.copy_enqueue_ns; o->worker_stall_ns = s.worker_stall_ns; o->worker_busy_ns = s.worker_busy_ns;
+    o->pack_kernel_ns = s.pack_kernel_ns; o->pack_kernel_bytes = s.pack_kernel_bytes; o->first_chunk_ns = s.first_chunk_ns;
+    o->max_dio_align = s.max_dio_align;
     return 0;
+}
+
+int lsio_uring_cuda_get_latency_histogram(const lsio_uring_cuda* self, uint64_t buckets[32]) {
+    if (!self || !buckets) return -EINVAL;
+    for (int i = 0; i < 32; i++) buckets[i] = self->be->stats.latency[i].load(std::memory_order_relaxed);
+    return 0;
+}
+void lsio_uring_cuda_reset_latency(lsio_uring_cuda* self) {
+    if (!self) return;
+    Stats& s = self->be->stats;
+    for (auto& b : s.latency) b.store(0, std::memory_order_relaxed);
+    s.first_submit_ns.store(0);
+    s.first_chunk_ns.store(0);
 }
 
 const char* lsio_uring_cuda_last_error(void) { return g_last_error.c_str(); }

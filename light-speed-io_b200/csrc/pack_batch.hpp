@@ -12,11 +12,12 @@
 namespace lsio {
 
 // Memory layout of one batch's descriptor block (same offsets on host and device):
-//   Seg[max_segs] | uint2 tiles[max_tiles] | u32 multi[max_segs] || u32 partials[max_tiles] | u32 sched[2]
+//   Seg[max_segs] | uint2 tiles[max_tiles] | u32 multi[max_segs] || u32 partials[max_tiles] | u32 sched[2] | u32 seg_done[max_segs]
 // Only the part before `||` (upload_bytes) is written by the host and copied to the device.
 struct PackBatchLayout {
     size_t max_segs = 0, max_tiles = 0;
     size_t off_tiles = 0, off_multi = 0, off_partials = 0, off_sched = 0;  // sched: 2 words, must be zero before the first launch
+    size_t off_segdone = 0;  // light variant: one counter per segment, zero before the first launch (the kernel re-arms them)
     size_t upload_bytes = 0, total_bytes = 0;
 };
 PackBatchLayout pack_batch_layout(size_t max_segs, size_t max_tiles);
@@ -31,10 +32,14 @@ struct PackBatchCounts {
 // Appends one segment to a host block; returns false if it does not fit the layout.
 bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCounts* c, const lsio_cuda_segment& seg, bool store);
 
+// Copies the filled part of a host block (Seg, tile and multi arrays up to the counts) to its device twin.
+int pack_batch_upload(const PackBatchLayout& lay, const void* host_block, void* dev_block, const PackBatchCounts& c, cudaStream_t stream);
+
 // One-time per-device set-up (GF(2) tables to the device, kernel attributes). 0 or error code.
 int pack_prepare_device(int device);
 // Enqueues the pack kernel (+ fold kernel if any segment spans several tiles). The device must
-// be current. `threads` per CTA: 0 = 1024 (the roofline configuration), or a smaller multiple of 32. Returns 0 or a cudaError_t.
+// be current. `threads` per CTA: 0 = 1024 (the roofline configuration), or a smaller multiple of 32; ignored with
+// LSIO_CUDA_PACK_LIGHT in `flags` (256-thread CTAs, fold fused: exactly one launch). Returns 0 or a cudaError_t.
 int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, const PackBatchCounts& c, uint32_t flags,
                       uint32_t* crc_out, cudaStream_t stream, unsigned* launches, unsigned threads);
 

@@ -138,6 +138,7 @@ struct Params {
     uint32_t* crc_out;   // one per segment
     const uint32_t* tables;
     uint32_t* sched;     // [0] next tile, [1] warps finished: the dynamic tile scheduler (zero between launches)
+    uint32_t* seg_done;  // light variant: tiles finished per segment (zero between launches); the last one folds
 };
 
 // ---- device helpers ----------------------------------------------------------------------
@@ -166,13 +167,23 @@ __device__ __forceinline__ void st_vec(uint4* p, const uint4& v) {
 }
 
 // acc * x^4096 with the lane-private tables; ltb = (char*)gtab + lane*4
-__device__ __forceinline__ uint32_t mul_g(uint32_t a, const char* ltb) {
+__device__ __forceinline__ uint32_t mul_g_private(uint32_t a, const char* ltb) {
     const uint32_t o0 = (a << 7) & 0x7F80u;
     const uint32_t o1 = (a >> 1) & 0x7F80u;
     const uint32_t o2 = (a >> 9) & 0x7F80u;
     const uint32_t o3 = (a >> 17) & 0x7F80u;
     return *(const uint32_t*)(ltb + o0) ^ *(const uint32_t*)(ltb + 32768 + o1) ^ *(const uint32_t*)(ltb + 65536 + o2) ^
            *(const uint32_t*)(ltb + 98304 + o3);
+}
+// Light variant: one shared [4][256] copy of G (4 KiB per CTA instead of 128 KiB; bank conflicts accepted:
+// its launches are small pipeline batches bound by latency and by PCIe, not by shared-memory throughput).
+__device__ __forceinline__ uint32_t mul_g_shared(uint32_t a, const char* tb) {
+    const uint32_t* t = (const uint32_t*)tb;
+    return t[a & 0xFF] ^ t[256 + ((a >> 8) & 0xFF)] ^ t[512 + ((a >> 16) & 0xFF)] ^ t[768 + (a >> 24)];
+}
+template <bool kLight>
+__device__ __forceinline__ uint32_t mul_g(uint32_t a, const char* tb) {
+    return kLight ? mul_g_shared(a, tb) : mul_g_private(a, tb);
 }
 // a * K with an ordinary [4][256] byte-sliced table (rare path: bank conflicts tolerated)
 __device__ __forceinline__ uint32_t mul_t(uint32_t a, const uint32_t* t) {
@@ -255,9 +266,11 @@ __device__ __forceinline__ void store_bytes(uint64_t addr, const uint4& d, int l
 // One tile (kTileRows rows ending at vector `vend`, exclusive) of one segment, by one warp.
 // Returns the tile partial (valid in every lane): the tile's bytes as a polynomial mod P,
 // positioned at the tile's last word.
-template <int WS, bool kStore, bool kCrc>
-__device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, const char* ltb, const uint32_t* sh) {
-    constexpr int kUnroll = WS < 0 ? LSIO_UNROLL : LSIO_UNROLL_SHIFTED;
+// `h`: the six [4][256] merge tables (shared memory in the roofline variant, global/L1 in the light one).
+template <int WS, bool kStore, bool kCrc, bool kLight>
+__device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, const char* ltb, const uint32_t* h) {
+    // the light variant runs few warps per SM with registers to spare: twice the rows in flight per warp
+    constexpr int kUnroll = (WS < 0 ? LSIO_UNROLL : LSIO_UNROLL_SHIFTED) * (kLight ? 2 : 1);
     const int bs = (g.delta & 3) * 8;
     uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     uint4* const dvec = (uint4*)g.a0;
@@ -293,10 +306,10 @@ __device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, c
             for (int u = 0; u < kUnroll; u++) {
                 if (kStore) st_vec(dvec + vr + 32 * u + lane, d[u]);
                 if (kCrc) {
-                    a0 = mul_g(a0, ltb) ^ d[u].x;
-                    a1 = mul_g(a1, ltb) ^ d[u].y;
-                    a2 = mul_g(a2, ltb) ^ d[u].z;
-                    a3 = mul_g(a3, ltb) ^ d[u].w;
+                    a0 = mul_g<kLight>(a0, ltb) ^ d[u].x;
+                    a1 = mul_g<kLight>(a1, ltb) ^ d[u].y;
+                    a2 = mul_g<kLight>(a2, ltb) ^ d[u].z;
+                    a3 = mul_g<kLight>(a3, ltb) ^ d[u].w;
                 }
             }
             vr += 32 * kUnroll;
@@ -306,10 +319,10 @@ __device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, c
             const uint4 d = fetch<WS, false>(g, vr + lane, bs);
             if (kStore) st_vec(dvec + vr + lane, d);
             if (kCrc) {
-                a0 = mul_g(a0, ltb) ^ d.x;
-                a1 = mul_g(a1, ltb) ^ d.y;
-                a2 = mul_g(a2, ltb) ^ d.z;
-                a3 = mul_g(a3, ltb) ^ d.w;
+                a0 = mul_g<kLight>(a0, ltb) ^ d.x;
+                a1 = mul_g<kLight>(a1, ltb) ^ d.y;
+                a2 = mul_g<kLight>(a2, ltb) ^ d.z;
+                a3 = mul_g<kLight>(a3, ltb) ^ d.w;
             }
             vr += 32;
             continue;
@@ -337,16 +350,15 @@ __device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, c
             }
         }
         if (kCrc) {
-            a0 = mul_g(a0, ltb) ^ d.x;
-            a1 = mul_g(a1, ltb) ^ d.y;
-            a2 = mul_g(a2, ltb) ^ d.z;
-            a3 = mul_g(a3, ltb) ^ d.w;
+            a0 = mul_g<kLight>(a0, ltb) ^ d.x;
+            a1 = mul_g<kLight>(a1, ltb) ^ d.y;
+            a2 = mul_g<kLight>(a2, ltb) ^ d.z;
+            a3 = mul_g<kLight>(a3, ltb) ^ d.w;
         }
         vr += 32;
     }
     if (!kCrc) return 0;
     // merge the four word accumulators (x^32 apart), then the 32 lanes (x^128 apart)
-    const uint32_t* h = sh + kSmH;
     uint32_t V = mul_t(mul_t(mul_t(a0, h) ^ a1, h) ^ a2, h) ^ a3;
 #pragma unroll
     for (int j = 0; j < 5; j++) {
@@ -358,20 +370,48 @@ __device__ __forceinline__ uint32_t run_tile(const Geo& g, int vend, int lane, c
     return __shfl_sync(0xFFFFFFFFu, V, 31);
 }
 
-template <bool kStore, bool kCrc>
-__global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
+// One warp folds a multi-tile segment: V = sum_k partial[k] * Z^k (k counted from the segment's end).
+// Lane t folds k = t, t+32, ... with Z^32 (byte tables), then the lanes are joined with Z; the trailing zero
+// padding is undone (x^(32-8z)) and the final NOT applied.  `parts` is read with L1 bypassed (other SMs wrote it).
+__device__ __forceinline__ uint32_t fold_segment(const uint32_t* parts, int n, uint64_t dst, uint64_t len, const uint32_t* z32, const uint32_t* zrow,
+                                                 const uint32_t* frow, int lane) {
+    uint32_t L = 0;
+    if (lane < n) {
+        int k = lane + ((n - 1 - lane) & ~31);  // highest k congruent to lane
+        L = __ldcg(parts + k);
+        for (k -= 32; k >= 0; k -= 32) L = mul_t(L, z32) ^ __ldcg(parts + k);
+    }
+    uint32_t V = 0;
+    for (int t = min(31, n - 1); t >= 0; t--) V = warp_mul(V, zrow, lane) ^ __shfl_sync(0xFFFFFFFFu, L, t);
+    const int z = (int)(((dst + len + 15ull) & ~15ull) - (dst + len));
+    return ~warp_mul(V, frow + z * 32, lane);
+}
+
+// Roofline variant (kLight = false): one 1024-thread CTA per SM, 128 KiB of lane-private tables, multi-tile
+// segments finished by fold_kernel.  Light variant: 256-thread CTAs that need 4 KiB of shared memory and fit
+// next to a consumer's kernels; merge tables come from global memory through L1; the warp that finishes a
+// segment's last tile folds the partials itself (one launch per batch); a segment with src == dst (landed
+// directly by DMA) is checksummed in place.
+template <bool kStore, bool kCrc, bool kLight>
+__global__ void __launch_bounds__(kLight ? 256 : kThreads, kLight ? 3 : 1) pack_kernel(const Params p) {
     extern __shared__ __align__(16) uint32_t sh[];
     const int tid = threadIdx.x, lane = tid & 31;
     if (kCrc) {
-        // replicate the 4 KiB G table into the lane-private layout; copy the small tables
-        for (int i = tid; i < 1024 * 32; i += blockDim.x) sh[kSmG + i] = __ldg(p.tables + kG + (i >> 5));
-        for (int i = tid; i < kSmWords - kSmH; i += blockDim.x) sh[kSmH + i] = __ldg(p.tables + kH + i);
+        if (kLight) {
+            for (int i = tid; i < 1024; i += blockDim.x) sh[i] = __ldg(p.tables + kG + i);
+        } else {
+            // replicate the 4 KiB G table into the lane-private layout; copy the small tables
+            for (int i = tid; i < 1024 * 32; i += blockDim.x) sh[kSmG + i] = __ldg(p.tables + kG + (i >> 5));
+            for (int i = tid; i < kSmWords - kSmH; i += blockDim.x) sh[kSmH + i] = __ldg(p.tables + kH + i);
+        }
         __syncthreads();
     }
-    const char* ltb = (const char*)(sh + kSmG) + lane * 4;
+    const char* ltb = kLight ? (const char*)sh : (const char*)(sh + kSmG) + lane * 4;
+    const uint32_t* htab = kLight ? p.tables + kH : sh + kSmH;
+    const uint32_t* ftab = kLight ? p.tables + kF : sh + kSmF;
 
     // Dynamic tile scheduler: every warp takes the NEXT tile from a global counter, like the hardware
-    // block scheduler would.  Measured on a plain copy (tools/copy_pattern_bench4.cu): static striding lets
+    // block scheduler would.  Measured on a plain copy (tools/copy_pattern_bench.cu): static striding lets
     // warps drift apart until the concurrently touched window spans hundreds of MB (94 % of the HBM copy
     // peak); taking tiles in order keeps a dense sliding window (101 %).
     for (;;) {
@@ -382,11 +422,13 @@ __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
         const uint2 te = __ldg(p.tiles + t);
         const Seg s = *(p.segs + te.x);  // 32 B, warp-uniform broadcast
         const uint64_t dst = kStore ? s.dst : s.src;  // crc-only: checksum in place
+        const bool in_place = kStore && s.src == s.dst;  // landed by DMA: nothing to move
+        if (!kCrc && in_place) continue;
         if (s.len < 4) {  // scalar path (covers empty segments): ntiles == 1 by construction
             if (lane == 0) {
                 uint8_t b[4];
                 for (int i = 0; i < (int)s.len; i++) b[i] = *(const uint8_t*)(s.src + i);
-                if (kStore) for (int i = 0; i < (int)s.len; i++) *(uint8_t*)(s.dst + i) = b[i];
+                if (kStore && !in_place) for (int i = 0; i < (int)s.len; i++) *(uint8_t*)(s.dst + i) = b[i];
                 if (kCrc) p.crc_out[te.x] = crc_bitwise_dev(b, (int)s.len);
             }
             continue;
@@ -401,22 +443,42 @@ __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
         g.src_lo = s.src; g.src_hi = s.src + s.len;
         const int vend = g.nvec - (int)te.y * kTileVecs;
         uint32_t part;
-        if (g.delta == 0) part = run_tile<-1, kStore, kCrc>(g, vend, lane, ltb, sh);
+        if (in_place) part = run_tile<-1, false, kCrc, kLight>(g, vend, lane, ltb, htab);
+        else if (g.delta == 0) part = run_tile<-1, kStore, kCrc, kLight>(g, vend, lane, ltb, htab);
         else switch (g.delta >> 2) {
-            case 0: part = run_tile<0, kStore, kCrc>(g, vend, lane, ltb, sh); break;
-            case 1: part = run_tile<1, kStore, kCrc>(g, vend, lane, ltb, sh); break;
-            case 2: part = run_tile<2, kStore, kCrc>(g, vend, lane, ltb, sh); break;
-            default: part = run_tile<3, kStore, kCrc>(g, vend, lane, ltb, sh); break;
+            case 0: part = run_tile<0, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
+            case 1: part = run_tile<1, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
+            case 2: part = run_tile<2, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
+            default: part = run_tile<3, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
         }
         if (!kCrc) continue;
 
-        if (s.ntiles > 1) {  // fold_kernel finishes multi-tile segments
-            if (lane == 0) p.partials[s.tile_base + te.y] = part;
+        if (s.ntiles > 1) {
+            if (!kLight) {  // fold_kernel finishes multi-tile segments
+                if (lane == 0) p.partials[s.tile_base + te.y] = part;
+                continue;
+            }
+            // light: publish the partial; whoever completes the segment folds it.  The fence orders the partial
+            // (and, harmlessly, this warp's data stores) before the count; it costs nothing at pipeline rates.
+            uint32_t before = 0;
+            if (lane == 0) {
+                p.partials[s.tile_base + te.y] = part;
+                __threadfence();
+                before = atomicAdd(p.seg_done + te.x, 1u);
+            }
+            before = __shfl_sync(0xFFFFFFFFu, before, 0);
+            if (before != s.ntiles - 1) continue;
+            __threadfence();
+            const uint32_t crc = fold_segment(p.partials + s.tile_base, (int)s.ntiles, dst, s.len, p.tables + kZ32, p.tables + kZ, p.tables + kF, lane);
+            if (lane == 0) {
+                p.crc_out[te.x] = crc;
+                p.seg_done[te.x] = 0;  // re-armed for the next launch of this batch / plan
+            }
             continue;
         }
         // undo the z trailing zero bytes of the aligned superset and apply the final x^32
         const int z = (int)(a1 - (dst + s.len));
-        const uint32_t crc = ~warp_mul(part, sh + kSmF + z * 32, lane);
+        const uint32_t crc = ~warp_mul(part, ftab + z * 32, lane);
         if (lane == 0) p.crc_out[te.x] = crc;
     }
     // the last warp to run dry re-arms the scheduler for the next launch of this batch / plan
@@ -429,8 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) pack_kernel(const Params p) {
     }
 }
 
-// One warp per multi-tile segment: V = sum_k partial[k] * Z^k (k counted from the segment's end).
-// Lane t folds k = t, t+32, ... with Z^32 (byte tables), then the lanes are joined with Z.
+// One warp per multi-tile segment (roofline variant only; a kernel boundary instead of fences in the hot loop).
 template <bool kStore>
 __global__ void __launch_bounds__(256) fold_kernel(const Params p) {
     __shared__ uint32_t z32[1024];
@@ -445,19 +506,7 @@ __global__ void __launch_bounds__(256) fold_kernel(const Params p) {
     if (w >= p.nmulti) return;
     const uint32_t si = __ldg(p.multi + w);
     const Seg s = p.segs[si];
-    const uint32_t* parts = p.partials + s.tile_base;
-    uint32_t L = 0;
-    const int n = (int)s.ntiles;
-    if (lane < n) {
-        int k = lane + ((n - 1 - lane) & ~31);  // highest k congruent to lane
-        L = parts[k];
-        for (k -= 32; k >= 0; k -= 32) L = mul_t(L, z32) ^ parts[k];
-    }
-    uint32_t V = 0;
-    for (int t = min(31, n - 1); t >= 0; t--) V = warp_mul(V, zrow, lane) ^ __shfl_sync(0xFFFFFFFFu, L, t);
-    const uint64_t dst = kStore ? s.dst : s.src;
-    const int z = (int)(((dst + s.len + 15ull) & ~15ull) - (dst + s.len));
-    const uint32_t crc = ~warp_mul(V, frow + z * 32, lane);
+    const uint32_t crc = fold_segment(p.partials + s.tile_base, (int)s.ntiles, kStore ? s.dst : s.src, s.len, z32, zrow, frow, lane);
     if (lane == 0) p.crc_out[si] = crc;
 }
 
@@ -481,8 +530,8 @@ static int get_device_tables(int device, const uint32_t** out, int* sms) {
         LSIO_CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
         int n = 0;
         LSIO_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
-        LSIO_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmBytes));
-        LSIO_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmBytes));
+        LSIO_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmBytes));
+        LSIO_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmBytes));
         dt.dev[device] = d;
         dt.sms[device] = n;
     }
@@ -514,7 +563,8 @@ PackBatchLayout pack_batch_layout(size_t max_segs, size_t max_tiles) {
     l.upload_bytes = l.off_multi + up(max_segs * 4);
     l.off_partials = l.upload_bytes;
     l.off_sched = l.off_partials + up(max_tiles * 4);
-    l.total_bytes = l.off_sched + 256;
+    l.off_segdone = l.off_sched + 256;
+    l.total_bytes = l.off_segdone + up(max_segs * 4);
     return l;
 }
 
@@ -535,9 +585,19 @@ bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCo
     return true;
 }
 
+int pack_batch_upload(const PackBatchLayout& lay, const void* host_block, void* dev_block, const PackBatchCounts& c, cudaStream_t st) {
+    const char* h = (const char*)host_block;
+    char* d = (char*)dev_block;
+    LSIO_CUDA_TRY(cudaMemcpyAsync(d, h, (size_t)c.nsegs * sizeof(Seg), cudaMemcpyHostToDevice, st));
+    LSIO_CUDA_TRY(cudaMemcpyAsync(d + lay.off_tiles, h + lay.off_tiles, (size_t)c.ntiles * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    if (c.nmulti) LSIO_CUDA_TRY(cudaMemcpyAsync(d + lay.off_multi, h + lay.off_multi, (size_t)c.nmulti * 4, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
 int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, const PackBatchCounts& c, uint32_t flags,
                       uint32_t* crc_out, cudaStream_t st, unsigned* launches, unsigned threads) {
-    if (threads == 0) threads = kThreads;
+    const bool light = flags & LSIO_CUDA_PACK_LIGHT;
+    if (threads == 0 || light) threads = light ? 256 : kThreads;
     if (threads % 32 || threads > (unsigned)kThreads) return -EINVAL;
     const bool store = flags & LSIO_CUDA_PACK_STORE, crc = flags & LSIO_CUDA_PACK_CRC32C;
     if (launches) *launches = 0;
@@ -548,13 +608,24 @@ int pack_batch_launch(int device, const PackBatchLayout& lay, void* dev_block, c
     if (rc) return rc;
     char* base = (char*)dev_block;
     Params p{(const Seg*)base, (const uint2*)(base + lay.off_tiles), c.ntiles, (uint32_t*)(base + lay.off_partials),
-             (const uint32_t*)(base + lay.off_multi), c.nmulti, crc_out, tables, (uint32_t*)(base + lay.off_sched)};
+             (const uint32_t*)(base + lay.off_multi), c.nmulti, crc_out, tables, (uint32_t*)(base + lay.off_sched), (uint32_t*)(base + lay.off_segdone)};
+    if (light) {
+        // small CTAs, several per SM; every warp takes tiles from the counter, so any grid size is correct
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms * 6, (c.ntiles + 7) / 8);
+        if (store && crc) pack_kernel<true, true, true><<<grid, 256, 4096, st>>>(p);
+        else if (crc) pack_kernel<false, true, true><<<grid, 256, 4096, st>>>(p);
+        else pack_kernel<true, false, true><<<grid, 256, 0, st>>>(p);
+        launch_counter().fetch_add(1, std::memory_order_relaxed);
+        if (launches) ++*launches;
+        LSIO_CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     // one CTA per SM; `threads` < 1024 is the small-footprint launch for a GPU shared with the consumer's kernels
     // (a 1024-thread CTA with 64 registers per thread needs a whole SM to itself)
     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms, (c.ntiles + threads / 32 - 1) / (threads / 32));
-    if (store && crc) pack_kernel<true, true><<<grid, threads, kSmBytes, st>>>(p);
-    else if (crc) pack_kernel<false, true><<<grid, threads, kSmBytes, st>>>(p);
-    else pack_kernel<true, false><<<grid, threads, 0, st>>>(p);
+    if (store && crc) pack_kernel<true, true, false><<<grid, threads, kSmBytes, st>>>(p);
+    else if (crc) pack_kernel<false, true, false><<<grid, threads, kSmBytes, st>>>(p);
+    else pack_kernel<true, false, false><<<grid, threads, 0, st>>>(p);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     if (launches) ++*launches;
     LSIO_CUDA_TRY(cudaGetLastError());
@@ -583,7 +654,8 @@ extern "C" {
 
 int lsio_cuda_pack_plan_create(int device, const lsio_cuda_segment* segs, size_t n, uint32_t flags, lsio_cuda_pack_plan** out) {
     using namespace lsio;
-    if (!out || (!segs && n) || !(flags & (LSIO_CUDA_PACK_STORE | LSIO_CUDA_PACK_CRC32C))) return -EINVAL;
+    if (!out || (!segs && n) || !(flags & (LSIO_CUDA_PACK_STORE | LSIO_CUDA_PACK_CRC32C)) || (flags & ~(LSIO_CUDA_PACK_STORE | LSIO_CUDA_PACK_CRC32C | LSIO_CUDA_PACK_LIGHT)))
+        return -EINVAL;
     const bool store = flags & LSIO_CUDA_PACK_STORE;
     size_t ntiles = 0;
     for (size_t i = 0; i < n; i++) {

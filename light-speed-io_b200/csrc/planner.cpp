@@ -88,7 +88,7 @@ Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op
     auto buf = std::make_shared<InnerBuffer>();
     buf->buf = block;
     buf->size = r.total_bytes;
-    buf->align = kAlign;
+    buf->align = r.align;
     buf->kind = MemKind::Device;
     buf->device = g.device;
     buf->release = [arena = g.arena, block](InnerBuffer&) { arena->release(block); };
@@ -96,29 +96,41 @@ Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op
 
     // Read plan: sort the ranges' padded spans, merge spans that touch / overlap / sit within
     // merge_gap_bytes of each other into runs, cut every run into reads of at most max_read_bytes
-    // (reference: one read per range, panics above 2 GiB, get_range.rs:23-30).
-    const uint64_t max_read = std::max<uint64_t>(kAlign, cfg.max_read_bytes / kAlign * kAlign);
+    // (reference: one read per range, panics above 2 GiB, get_range.rs:23-30).  Offsets and lengths are
+    // multiples of the FILE's O_DIRECT alignment (reference: 512 hard-coded, sqe.rs:12, with the statx value
+    // fetched and unused, open_file.rs:23-25).
+    const uint64_t al = r.align;
+    const uint64_t max_read = std::max<uint64_t>(al, cfg.max_read_bytes / al * al);
     std::vector<uint32_t> order;
     for (size_t i = 0; i < n; i++)
         if (r.ranges[i].valid) order.push_back((uint32_t)i);
-    auto span_lo = [&](uint32_t i) { return (uint64_t)r.ranges[i].start_off / kAlign * kAlign; };                   // sqe.rs:83
-    auto span_hi = [&](uint32_t i) { return ((uint64_t)r.ranges[i].end_off + kAlign - 1) / kAlign * kAlign; };     // padded length
+    auto span_lo = [&](uint32_t i) { return (uint64_t)r.ranges[i].start_off / al * al; };              // sqe.rs:83
+    auto span_hi = [&](uint32_t i) { return ((uint64_t)r.ranges[i].end_off + al - 1) / al * al; };    // padded length
     if (cfg.merge_ranges) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return span_lo(a) < span_lo(b); });
     for (size_t k = 0; k < order.size();) {
         uint64_t run_lo = span_lo(order[k]), run_hi = span_hi(order[k]);
         size_t k_end = k + 1;
         if (cfg.merge_ranges)
-            while (k_end < order.size() && k_end - k < 1024 && span_lo(order[k_end]) <= run_hi + cfg.merge_gap_bytes) {  // <= 1024 segments per read: a read must fit one batch
+            while (k_end < order.size() && span_lo(order[k_end]) <= run_hi + cfg.merge_gap_bytes) {
                 run_hi = std::max(run_hi, span_hi(order[k_end]));
                 k_end++;
             }
+        size_t j_lo = k;  // ranges before j_lo end at or before the current read: skipped
         for (uint64_t fo = run_lo; fo < run_hi; fo += max_read) {
             ReadPlan rd;
             rd.file_off = fo;
             rd.read_len = (uint32_t)std::min<uint64_t>(max_read, run_hi - fo);
             rd.first_seg = (uint32_t)r.segs.size();
-            for (size_t j = k; j < k_end; j++) {
+            auto close_read = [&] {
+                rd.nsegs = (uint32_t)r.segs.size() - rd.first_seg;
+                if (rd.nsegs) r.reads.push_back(rd);  // a read that carries no payload (pure gap) is skipped
+                rd.first_seg = (uint32_t)r.segs.size();
+                rd.nsegs = rd.ntiles = rd.needed = 0;
+            };
+            while (j_lo < k_end && (uint64_t)r.ranges[order[j_lo]].end_off <= fo && span_hi(order[j_lo]) <= fo) j_lo++;
+            for (size_t j = j_lo; j < k_end; j++) {
                 RangePlan& p = r.ranges[order[j]];
+                if ((uint64_t)p.start_off >= fo + rd.read_len) break;  // sorted by span_lo: nothing further starts inside this read
                 const uint64_t lo = std::max<uint64_t>(fo, (uint64_t)p.start_off), hi = std::min<uint64_t>(fo + rd.read_len, (uint64_t)p.end_off);
                 if (lo >= hi) continue;
                 SegPlan sp;
@@ -126,12 +138,16 @@ Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op
                 sp.head = (uint32_t)(lo - fo);  // sqe.rs:116: the view starts at start_off - aligned_start
                 sp.payload_len = hi - lo;
                 sp.dst_off = p.dst_off + (lo - (uint64_t)p.start_off);
+                const uint32_t t = (uint32_t)pack_tile_count((uint64_t)(uintptr_t)(block + sp.dst_off), sp.payload_len);
+                // A read must fit one pack batch with room to spare: many (duplicate / overlapping) ranges over the same
+                // bytes are served by several reads of the same span.
+                if (rd.first_seg != r.segs.size() && ((uint32_t)r.segs.size() - rd.first_seg >= kMaxSegsPerRead || rd.ntiles + t > kMaxTilesPerRead)) close_read();
                 p.seg_ids.push_back((uint32_t)r.segs.size());
                 rd.needed = std::max<uint32_t>(rd.needed, (uint32_t)(hi - fo));
+                rd.ntiles += t;
                 r.segs.push_back(sp);
             }
-            rd.nsegs = (uint32_t)r.segs.size() - rd.first_seg;
-            if (rd.nsegs) r.reads.push_back(rd);  // a read that carries no payload (pure gap) is skipped
+            close_read();
         }
         k = k_end;
     }

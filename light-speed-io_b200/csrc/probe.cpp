@@ -1,5 +1,7 @@
 // probe.cpp -- lsio_probe_read_ceiling: raw READ_FIXED read rate of a file set with no GPU work
 // (measurement aid; stands in for crates/lsio_uring/benches/fio.ini).
+#include <sys/uio.h>
+
 #include "backend.hpp"
 
 using namespace lsio;
@@ -8,6 +10,11 @@ extern "C" {
 
 int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads, uint32_t queue_depth,
                             uint32_t o_direct, double* gib_per_s) {
+    return lsio_probe_read_ceiling_ex(paths, n_paths, block_bytes, n_threads, queue_depth, o_direct, 0, gib_per_s);
+}
+
+int lsio_probe_read_ceiling_ex(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads, uint32_t queue_depth,
+                               uint32_t o_direct, uint32_t inline_reads, double* gib_per_s) {
     if (!paths || !n_paths || !gib_per_s || !n_threads || !queue_depth || block_bytes < kAlign || block_bytes % kAlign) return -EINVAL;
     const uint64_t slot_bytes = block_bytes * queue_depth;
     uint8_t* pinned = nullptr;
@@ -33,6 +40,25 @@ int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t b
                 struct stat st;
                 fstat(fd, &st);
                 const uint64_t nblk = ((uint64_t)st.st_size + block_bytes - 1) / block_bytes;
+                // the product's own rule (worker.cpp configure_request): a file the kernel cannot read asynchronously is
+                // read with preadv2 on this thread instead of being handed to an io-wq thread by io_uring
+                bool inl = inline_reads == 2;
+                if (inline_reads == 1) {
+                    uint8_t byte;
+                    iovec iv{&byte, 1};
+                    inl = preadv2(fd, &iv, 1, 0, RWF_NOWAIT) < 0 && errno == EOPNOTSUPP;
+                }
+                if (inl) {
+                    uint8_t* base = pinned + (uint64_t)t * slot_bytes;
+                    for (uint64_t k = 0; k < nblk; k++) {
+                        iovec iv{base + (k % queue_depth) * block_bytes, (size_t)block_bytes};
+                        const ssize_t n = preadv2(fd, &iv, 1, (off_t)(k * block_bytes), 0);
+                        if (n < 0) { err.store(-errno); break; }
+                        bytes += (uint64_t)n;
+                    }
+                    close(fd);
+                    continue;
+                }
                 uint64_t issued = 0, done = 0;
                 std::vector<unsigned> free_slots;
                 for (unsigned i = 0; i < queue_depth; i++) free_slots.push_back(i);

@@ -44,6 +44,8 @@ struct StageEntryT {
     void* copy_event = nullptr;  // staging_mode 1: the cudaEvent_t recorded after this extent's H2D copy
     uint32_t owner = 0;          // staging_mode 1: the io worker (copy stream) that issued it
     uint32_t used = 0;           // staging_mode 1: bytes of the extent actually filled (= copied)
+    uint32_t nsegs = 0, ntiles = 0;  // pack descriptors / kernel tiles its landed reads need (set before `state` is published)
+    bool direct = false;         // its payload was copied straight into the request buffers (the kernel checksums in place)
 };
 
 template <class R>
@@ -58,11 +60,12 @@ class StagingLogT {
     }
     uint64_t capacity() const { return cap_; }
 
-    // Reserve `len` bytes (multiple of 512).  Thread-safe.  nullptr = ring or entry table full.
-    StageEntry* alloc(uint32_t len) {
+    // Reserve `len` bytes (multiple of 512) at a multiple of `align` (a power of two dividing the capacity).
+    // Thread-safe.  nullptr = ring or entry table full.
+    StageEntry* alloc(uint32_t len, uint32_t align = 512) {
         std::lock_guard<std::mutex> lk(mu_);
         if (alloc_seq_ - retire_seq_.load(std::memory_order_acquire) >= entries_.size()) return nullptr;
-        uint64_t off = alloc_off_;
+        uint64_t off = (alloc_off_ + align - 1) / align * align;
         const uint64_t phys = off % cap_;
         const uint64_t boundary = std::min<uint64_t>(cap_, (phys / kRegBoundary + 1) * kRegBoundary);
         if (phys + len > boundary) off += boundary - phys;  // never straddle the ring end or a registration boundary
@@ -73,6 +76,8 @@ class StagingLogT {
         e.state.store(kStageReading, std::memory_order_relaxed);
         e.reads.clear();
         e.used = 0;
+        e.nsegs = e.ntiles = 0;
+        e.direct = false;
         e.copy_event = nullptr;
         alloc_off_ = off + len;
         alloc_seq_pub_.store(++alloc_seq_, std::memory_order_release);

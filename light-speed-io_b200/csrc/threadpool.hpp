@@ -56,8 +56,28 @@ class WorkerThread {
             }
         }
         const size_t n = s_->locals.size();
-        for (size_t k = 1; k < n; k++)
-            if (auto t = pop(*s_->locals[(id_ + k) % n])) return t;
+        for (size_t k = 1; k < n; k++) {
+            Local& victim = *s_->locals[(id_ + k) % n];
+            if (s_->steal_batch <= 1) {  // the reference's Stealer::steal(): one task (worker.rs:58-62)
+                if (auto t = pop(victim)) return t;
+                continue;
+            }
+            // take up to steal_batch CONSECUTIVE tasks (reads that fill one extent stay together)
+            std::vector<T> got;
+            {
+                std::lock_guard<std::mutex> lk(victim.mu);
+                while (!victim.q.empty() && got.size() < s_->steal_batch) {
+                    got.push_back(std::move(victim.q.front()));
+                    victim.q.pop_front();
+                }
+            }
+            if (got.empty()) continue;
+            if (got.size() > 1) {
+                std::lock_guard<std::mutex> lk(local().mu);
+                for (size_t i = 1; i < got.size(); i++) local().q.push_back(std::move(got[i]));
+            }
+            return std::move(got[0]);
+        }
         return std::nullopt;
     }
     bool keep_running() const { return s_->keep_running.load(std::memory_order_relaxed); }  // worker.rs:67-69
@@ -122,6 +142,7 @@ class WorkerThread {
         std::vector<std::unique_ptr<Parker>> parkers;
         std::unique_ptr<std::atomic<uint64_t>[]> n_parks;
         int park_timeout_ms = 50;
+        size_t steal_batch = 1;
         void unpark(size_t id) {
             auto& p = *parkers[id];
             std::lock_guard<std::mutex> lk(p.mu);
@@ -159,7 +180,9 @@ class ThreadPool {
     using Op = std::function<void(WorkerThread<T>&)>;
     // threadpool.rs:78-127.  `cpus`: if non-empty every worker is pinned to this CPU set
     // (the NUMA node of the group's GPU).
-    ThreadPool(size_t n_worker_threads, Op op, const std::vector<int>& cpus = {}) : s_(std::make_shared<typename WorkerThread<T>::Shared>()) {
+    ThreadPool(size_t n_worker_threads, Op op, const std::vector<int>& cpus = {}, size_t steal_batch = 1)
+        : s_(std::make_shared<typename WorkerThread<T>::Shared>()) {
+        s_->steal_batch = steal_batch ? steal_batch : 1;
         s_->n_parks.reset(new std::atomic<uint64_t>[n_worker_threads]);
         for (size_t i = 0; i < n_worker_threads; i++) {
             s_->locals.emplace_back(new typename WorkerThread<T>::Local());

@@ -110,12 +110,13 @@ class Ring {
         for (;;) {
             int rc = (int)syscall(__NR_io_uring_enter, fd_, to_submit, wait_nr, flags, argp, argsz);
             if (rc < 0 && errno == EINTR) continue;
-            if (rc < 0 && errno == ETIME) {
+            if (rc < 0 && errno == ETIME) {  // the wait timed out; with EXT_ARG the submission part has already happened
                 unsubmitted_ = 0;
                 return 0;
             }
             if (rc < 0) return -errno;
-            unsubmitted_ = 0;
+            // the kernel may consume fewer SQEs than offered: the rest stay counted and go with the next enter
+            unsubmitted_ -= (unsigned)rc < to_submit ? (unsigned)rc : to_submit;
             return rc;
         }
     }

@@ -1,6 +1,10 @@
 // worker.cpp -- one io worker: private io_uring, tracker of in-flight ops, the GetRanges / Read / Close state
 // machines and the staging of landed reads (crates/lsio_uring/src/worker.rs:24-135, get_ranges.rs, get_range.rs,
-// close.rs, sqe.rs builders).
+// close.rs, sqe.rs builders, open_file.rs).
+#include <sys/uio.h>
+
+#include <unordered_map>
+
 #include "backend.hpp"
 
 namespace lsio {
@@ -16,6 +20,12 @@ struct Worker {
     // completion and consumption of earlier reads that frees the arena).
     std::deque<Op> stalled_reads, stalled_plans;
     WorkerSlots* slots = nullptr;  // staging_mode 1
+    // Can the kernel read files of this filesystem asynchronously (FMODE_NOWAIT)?  One probe per st_dev.
+    std::unordered_map<uint64_t, bool> async_capable;
+    // thread-local counters, folded into Backend::stats when the worker parks / exits
+    uint64_t c_read_ns = 0, c_copy_ns = 0, c_stall_ns = 0, c_busy_ns = 0, c_inline = 0;
+    static constexpr size_t kNoIdx = ~size_t(0);
+
     Worker(Group& grp, WorkerThread<Op>& w) : g(grp), wt(w), tracker(grp.be->cfg.sq_entries) {
         if (grp.be->cfg.staging_mode == 1) {
             slots = &grp.wslots[w.id()];
@@ -23,27 +33,79 @@ struct Worker {
         }
     }
 
+    void fold_counters() {
+        Stats& s = g.be->stats;
+        s.read_ns += c_read_ns;
+        s.copy_enqueue_ns += c_copy_ns;
+        s.worker_stall_ns += c_stall_ns;
+        s.worker_busy_ns += c_busy_ns;
+        s.inline_reads += c_inline;
+        c_read_ns = c_copy_ns = c_stall_ns = c_busy_ns = c_inline = 0;
+    }
+
     // staging_mode 1: per-slot extent bookkeeping (this worker only)
     struct Extent {
         StageEntry* entry = nullptr;
         uint32_t pending = 0;  // reads submitted but not yet landed/failed
         bool closed = false;   // no more reads will be added
+        uint32_t nsegs = 0, ntiles = 0;  // descriptors / kernel tiles of the reads placed so far (bounded: one extent fits one pack batch)
     };
     std::vector<Extent> extents;  // one per slot
     int cur = -1;                 // slot of the extent being filled, or -1
 
-    // The extent's reads have all landed (or failed) and nothing more will be added: copy it to the device log
-    // with ONE cudaMemcpyAsync while it is still in this core's cache, then publish it to the device thread.
+    // The extent's reads have all landed (or failed) and nothing more will be added: copy it to the device
+    // while it is still in this core's cache, then publish it to the device thread.  Two ways:
+    //   direct  -- its payload forms a few runs contiguous both in the slot and in the request buffers: one
+    //              cudaMemcpyAsync per run straight into the arena; the kernel later only checksums in place
+    //   ring    -- ONE cudaMemcpyAsync of the whole extent into its reservation in the device log; the pack
+    //              kernel strips the padding and scatters the ranges (small / unaligned / interleaved ranges)
     void finish_extent(int slot) {
         Extent& x = extents[slot];
         StageEntry* ent = x.entry;
         Backend* be = g.be;
-        bool any = false;
-        for (auto& r : ent->reads) any |= r.state == kStageLanded;
-        if (any) {
-            const uint64_t phys = ent->log_off % g.log.capacity();
-            cudaError_t ce = cudaMemcpyAsync(g.dev_ring + phys, slots->base + (uint64_t)slot * g.slot_bytes, ent->used, cudaMemcpyHostToDevice, slots->stream);
+        const lsio_uring_cuda_config& cfg = be->cfg;
+        struct Run {
+            uint32_t src;
+            uint8_t* dst;
+            uint64_t len;
+        };
+        constexpr int kMaxRuns = 4;
+        Run runs[kMaxRuns];
+        int nruns = 0;
+        bool direct = cfg.direct_landing != 0;
+        uint64_t payload = 0;
+        uint32_t nsegs = 0, ntiles = 0;
+        for (auto& r : ent->reads) {
+            if (r.state != kStageLanded) continue;
+            const ReadPlan& rd = r.req->reads[r.read];
+            nsegs += rd.nsegs;
+            ntiles += rd.ntiles;
+            for (uint32_t k = 0; direct && k < rd.nsegs; k++) {
+                const SegPlan& sp = r.req->segs[rd.first_seg + k];
+                const uint32_t src = r.off + sp.head;
+                uint8_t* dst = r.req->buffer->buf + sp.dst_off;
+                payload += sp.payload_len;
+                if (nruns && runs[nruns - 1].src + runs[nruns - 1].len == src && runs[nruns - 1].dst + runs[nruns - 1].len == dst) runs[nruns - 1].len += sp.payload_len;
+                else if (nruns == kMaxRuns) direct = false;
+                else runs[nruns++] = Run{src, dst, sp.payload_len};
+            }
+        }
+        // several small copies cost more than one large copy plus the kernel's scatter
+        direct = direct && nruns > 0 && (nruns == 1 || payload >= (uint64_t)nruns * (128u << 10));
+        ent->nsegs = nsegs;
+        ent->ntiles = ntiles;
+        if (nsegs) {
+            const uint64_t t0 = now_ns();
+            uint8_t* sbase = slots->base + (uint64_t)slot * g.slot_bytes;
+            cudaError_t ce = cudaSuccess;
+            if (direct) {
+                for (int i = 0; i < nruns && ce == cudaSuccess; i++) ce = cudaMemcpyAsync(runs[i].dst, sbase + runs[i].src, runs[i].len, cudaMemcpyHostToDevice, slots->stream);
+            } else {
+                const uint64_t phys = ent->log_off % g.log.capacity();
+                ce = cudaMemcpyAsync(g.dev_ring + phys, sbase, ent->used, cudaMemcpyHostToDevice, slots->stream);
+            }
             if (ce == cudaSuccess) ce = cudaEventRecord(slots->ev[slot], slots->stream);
+            c_copy_ns += now_ns() - t0;
             if (ce != cudaSuccess) {
                 cudaGetLastError();
                 for (auto& r : ent->reads) {
@@ -55,13 +117,22 @@ struct Worker {
                         if (!r.req->ranges[range].failed.exchange(true)) send_error(be, (int)ce, 0, *r.req, (int)range, "cudaMemcpyAsync (H2D) failed");
                     }
                 }
+                ent->nsegs = ent->ntiles = 0;
                 slots->busy[slot] = 0;
             } else {
                 slots->busy[slot] = 2;
                 ent->copy_event = slots->ev[slot];
                 ent->owner = (uint32_t)wt.id();
-                be->stats.h2d_copies++;
-                be->stats.h2d_bytes += ent->used;
+                ent->direct = direct;
+                if (direct) {
+                    be->stats.direct_extents++;
+                    be->stats.direct_copies += (uint64_t)nruns;
+                    be->stats.h2d_copies += (uint64_t)nruns;
+                    be->stats.h2d_bytes += payload;
+                } else {
+                    be->stats.h2d_copies++;
+                    be->stats.h2d_bytes += ent->used;
+                }
             }
         } else {
             slots->busy[slot] = 0;
@@ -97,22 +168,124 @@ struct Worker {
         return e;
     }
 
+    // Host address this read lands at (+ the bytes already landed).
+    uint8_t* read_dst(const Op& op) const {
+        if (slots) return slots->base + (uint64_t)op.slot * g.slot_bytes + op.entry->reads[op.ref].off + op.done;
+        return g.host_ring + op.entry->log_off % g.log.capacity() + op.done;
+    }
+
+    // Test knob (debug_short_read_every): every k-th read is issued shorter than it should be, so that the
+    // continuation path below runs (the reference leaves short reads as a TODO: get_range.rs:66-68).
+    uint32_t maybe_truncate(const Request& r, uint32_t len) {
+        const uint32_t k = g.be->cfg.debug_short_read_every;
+        if (!k || len <= r.align) return len;
+        if (g.be->stats.read_seq.fetch_add(1, std::memory_order_relaxed) % k != k - 1) return len;
+        return std::max<uint32_t>(r.align, len / 2 / r.align * r.align);
+    }
+
     void push_read_sqe(size_t idx, Op& op) {
         const ReadPlan& sp = op.req->reads[op.read];
         io_uring_sqe* e = must_get_sqe();
         e->opcode = IORING_OP_READ_FIXED;  // north star: READ_FIXED into registered pinned memory (reference: Read, sqe.rs:95)
         e->fd = op.req->fd;
-        if (slots) {
-            e->addr = (uint64_t)(uintptr_t)(slots->base + (uint64_t)op.slot * g.slot_bytes + op.entry->reads[op.ref].off + op.done);
-            e->buf_index = 0;
-        } else {
-            const uint64_t phys = op.entry->log_off % g.log.capacity() + op.done;
-            e->addr = (uint64_t)(uintptr_t)(g.host_ring + phys);
-            e->buf_index = (uint16_t)(phys / StagingLog::kRegBoundary);
-        }
-        e->len = sp.read_len - op.done;
+        e->addr = (uint64_t)(uintptr_t)read_dst(op);
+        e->buf_index = slots ? 0 : (uint16_t)((op.entry->log_off % g.log.capacity() + op.done) / StagingLog::kRegBoundary);
+        e->len = maybe_truncate(*op.req, sp.read_len - op.done);
         e->off = sp.file_off + op.done;
         e->user_data = UringUserData::pack((uint32_t)idx, IORING_OP_READ_FIXED);
+    }
+
+    // Per-file set-up once fd and statx are known (OpenFileBuilder::build, open_file.rs:69-78): the O_DIRECT
+    // alignment the reference fetches and never uses, and how this file is read.
+    bool configure_request(Request& r) {
+        const lsio_uring_cuda_config& cfg = g.be->cfg;
+        uint32_t al = (uint32_t)kAlign;
+        if (cfg.force_align) al = cfg.force_align;
+        else if (cfg.o_direct && (r.stx.stx_mask & STATX_DIOALIGN)) al = std::max<uint32_t>(al, std::max(r.stx.stx_dio_offset_align, r.stx.stx_dio_mem_align));
+        const uint64_t room = slots ? g.slot_bytes : std::min<uint64_t>(g.log.capacity() / 4, 1u << 16);
+        if ((al & (al - 1)) || al > room || al > 65536) {
+            send_error(g.be, -EINVAL, IORING_OP_STATX, r, -1, "unsupported O_DIRECT alignment reported for this file");
+            return false;
+        }
+        r.align = al;
+        uint64_t seen = g.be->stats.max_dio_align.load(std::memory_order_relaxed);
+        while (al > seen && !g.be->stats.max_dio_align.compare_exchange_weak(seen, al)) {}
+        if (cfg.inline_reads == 2) r.inline_io = true;
+        else if (cfg.inline_reads == 1) {
+            const uint64_t dev = ((uint64_t)r.stx.stx_dev_major << 32) | r.stx.stx_dev_minor;
+            auto it = async_capable.find(dev);
+            if (it == async_capable.end()) {
+                // RWF_NOWAIT is refused with EOPNOTSUPP exactly when the file lacks FMODE_NOWAIT -- the same test io_uring
+                // applies before it hands a read to an io-wq thread instead of issuing it from the submitter.
+                uint8_t byte;
+                iovec iv{&byte, 1};
+                const ssize_t rc = preadv2(r.fd, &iv, 1, 0, RWF_NOWAIT);
+                it = async_capable.emplace(dev, !(rc < 0 && errno == EOPNOTSUPP)).first;
+            }
+            r.inline_io = !it->second;
+        }
+        return true;
+    }
+
+    // One Err per range that this read was carrying (reference: one Err per failed CQE = per range), then the
+    // read counts as done.
+    void fail_read(size_t idx, Op& op, int status, const char* what) {
+        Request& r = *op.req;
+        const ReadPlan& rd = r.reads[op.read];
+        uint32_t last = UINT32_MAX;
+        for (uint32_t k = 0; k < rd.nsegs; k++) {
+            const uint32_t range = r.segs[rd.first_seg + k].range;
+            if (range == last) continue;
+            last = range;
+            if (!r.ranges[range].failed.exchange(true, std::memory_order_relaxed)) send_error(g.be, status, IORING_OP_READ_FIXED, r, (int)range, what);
+        }
+        read_done(op, kStageFailed);
+        finish_read_accounting(idx, op);
+    }
+
+    // The kernel cannot issue this file's reads asynchronously (or null_source): the worker performs the read
+    // itself, straight into the slot, handling short reads and errors exactly like the CQE path.
+    void read_inline(Op& op) {
+        Backend* be = g.be;
+        Request& r = *op.req;
+        const ReadPlan& rd = r.reads[op.read];
+        const uint64_t t0 = now_ns();
+        int err = 0;
+        const char* what = nullptr;
+        while (op.done < rd.needed) {
+            const uint32_t want = maybe_truncate(r, rd.read_len - op.done);
+            ssize_t n;
+            if (be->cfg.null_source) {
+                n = want;
+            } else {
+                iovec iv{read_dst(op), want};
+                n = preadv2(r.fd, &iv, 1, (off_t)(rd.file_off + op.done), 0);
+                if (n < 0 && errno == EINTR) continue;
+            }
+            if (n < 0) {
+                err = -errno;
+                what = "read failed";
+                break;
+            }
+            op.done += (uint32_t)n;
+            be->stats.read_bytes += (uint64_t)n;
+            if (op.done < rd.needed) {
+                if (n == 0 || (op.done % r.align) != 0) {
+                    err = -EIO;
+                    what = "short read (unexpected end of file)";
+                    break;
+                }
+                be->stats.short_reads++;
+            }
+        }
+        c_read_ns += now_ns() - t0;
+        c_inline++;
+        if (err) {
+            fail_read(kNoIdx, op, err, what);
+            return;
+        }
+        read_done(op, kStageLanded);
+        finish_read_accounting(kNoIdx, op);
     }
 
     Start start(Op& op) {
@@ -144,13 +317,19 @@ struct Worker {
         case Op::Plan:
             return plan_request(g, op.req, wt);
         case Op::Read: {  // get_range.rs:43-51 + sqe.rs:59-122
-            const ReadPlan& sp = op.req->reads[op.read];
+            Request& r = *op.req;
+            const ReadPlan& sp = r.reads[op.read];
             StageEntry* ent;
             uint32_t off = 0;
             int slot = -1;
             if (slots) {
-                // pack this read behind the previous ones of the current extent, or open a new extent
-                if (cur >= 0 && extents[cur].entry->used + sp.read_len > g.slot_bytes) close_current_extent();
+                // pack this read behind the previous ones of the current extent (at the file's alignment), or open a new extent;
+                // an extent never outgrows a pack batch (segments / kernel tiles)
+                if (cur >= 0) {
+                    const Extent& x = extents[cur];
+                    off = (x.entry->used + r.align - 1) / r.align * r.align;
+                    if (off + sp.read_len > g.slot_bytes || x.nsegs + sp.nsegs > kMaxSegsPerExtent || x.ntiles + sp.ntiles > kMaxTilesPerExtent) close_current_extent();
+                }
                 if (cur < 0) {
                     const int free_slot = acquire_slot();
                     if (free_slot < 0) {  // all of this worker's slots are still being read or copied
@@ -163,30 +342,39 @@ struct Worker {
                         return Start::Retry;
                     }
                     slots->busy[free_slot] = 1;
-                    extents[free_slot] = Extent{fresh, 0, false};
+                    extents[free_slot] = Extent{fresh, 0, false, 0, 0};
                     cur = free_slot;
+                    off = 0;
                 }
                 slot = cur;
-                ent = extents[cur].entry;
-                off = ent->used;
-                ent->used += sp.read_len;
-                extents[cur].pending++;
+                Extent& x = extents[cur];
+                ent = x.entry;
+                ent->used = off + sp.read_len;
+                x.pending++;
+                x.nsegs += sp.nsegs;
+                x.ntiles += sp.ntiles;
             } else {
-                ent = g.log.alloc(sp.read_len);
+                ent = g.log.alloc(sp.read_len, r.align);
                 if (!ent) {
                     be->stats.staging_stalls++;
                     return Start::Retry;
                 }
+                ent->nsegs = sp.nsegs;
+                ent->ntiles = sp.ntiles;
             }
             op.ref = (uint32_t)ent->reads.size();
             ent->reads.push_back(ReadRefT<Request>{op.req, op.read, off, kStageReading});
             op.entry = ent;
             op.done = 0;
             op.slot = slot;
+            be->stats.reads++;
+            if (r.inline_io || be->cfg.null_source) {
+                read_inline(op);
+                return Start::Finished;
+            }
             auto idx = tracker.get_next_index();
             push_read_sqe(*idx, op);
             tracker.put(*idx, std::move(op));
-            be->stats.reads++;
             return Start::Started;
         }
         case Op::Close:
@@ -204,6 +392,7 @@ struct Worker {
             x.pending--;
             if (x.closed && x.pending == 0) finish_extent(op.slot);
         } else {
+            if (state != kStageLanded) ent->nsegs = ent->ntiles = 0;
             ent->landed_ns = now_ns();
             ent->state.store(kStageLanded, std::memory_order_release);  // staging_mode 0: one read per extent
         }
@@ -213,6 +402,11 @@ struct Worker {
         // get_range.rs:78-90: the last reader of the file closes it, re-using this tracker slot
         Request& r = *op.req;
         if (r.reads_left.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+            if (idx == kNoIdx) {  // inline read: no tracker slot to re-use, no reason to go through the ring
+                close(r.fd);
+                r.fd = -1;
+                return;
+            }
             io_uring_sqe* e = must_get_sqe();  // sqe.rs:126-133
             e->opcode = IORING_OP_CLOSE;
             e->fd = r.fd;
@@ -224,7 +418,7 @@ struct Worker {
             tracker.replace(idx, std::move(c));  // NextStep::ReplaceWith
             return;
         }
-        tracker.remove(idx);  // NextStep::Done
+        if (idx != kNoIdx) tracker.remove(idx);  // NextStep::Done
     }
 
     void handle(const io_uring_cqe& cqe) {
@@ -245,21 +439,18 @@ struct Worker {
                     r.have_statx = true;
                 }
             }
-            if (!be->cfg.statx_via_ring) {  // fast metadata path: size from fstat on the fd we just opened
+            if (!be->cfg.statx_via_ring) {
+                // fast metadata path: statx on the fd we just opened (size + STATX_DIOALIGN, as open_file.rs:23-25
+                // wants them); as cheap as an fstat and never blocks
                 if (r.have_fd) {
-                    struct stat st;
-                    if (fstat(r.fd, &st) == 0) {
-                        r.stx.stx_size = (uint64_t)st.st_size;
-                        r.have_statx = true;
-                    } else {
-                        send_error(be, -errno, IORING_OP_STATX, r, -1, "fstat failed");
-                    }
+                    if (statx(r.fd, "", AT_EMPTY_PATH, STATX_SIZE | STATX_DIOALIGN, &r.stx) == 0) r.have_statx = true;
+                    else send_error(be, -errno, IORING_OP_STATX, r, -1, "statx failed");
                 }
             } else if (r.n_cqes_received < 2) {
                 return;  // NextStep::Pending
             }
             Op done = tracker.remove(ud.index_of_op);
-            if (r.have_fd && r.have_statx) {
+            if (r.have_fd && r.have_statx && configure_request(r)) {
                 done.kind = Op::Plan;
                 if (plan_request(g, done.req, wt) == Start::Retry) stalled_plans.push_back(std::move(done));
             } else if (r.have_fd) {
@@ -270,27 +461,15 @@ struct Worker {
         }
         case Op::Read: {  // get_range.rs:53-91
             const ReadPlan& rd = r.reads[op->read];
-            auto fail = [&](int status, const char* what) {
-                // one Err per range that this CQE was carrying (reference: one Err per failed CQE = per range)
-                uint32_t last = UINT32_MAX;
-                for (uint32_t k = 0; k < rd.nsegs; k++) {
-                    const uint32_t range = r.segs[rd.first_seg + k].range;
-                    if (range == last) continue;
-                    last = range;
-                    if (!r.ranges[range].failed.exchange(true, std::memory_order_relaxed)) send_error(be, status, IORING_OP_READ_FIXED, r, (int)range, what);
-                }
-                read_done(*op, kStageFailed);
-                finish_read_accounting(ud.index_of_op, *op);
-            };
             if (cqe.res < 0) {
-                fail(cqe.res, "read failed");
+                fail_read(ud.index_of_op, *op, cqe.res, "read failed");
                 return;
             }
             op->done += (uint32_t)cqe.res;
             be->stats.read_bytes += (uint64_t)cqe.res;
             if (op->done < rd.needed) {  // the reference does not check (get_range.rs:66-68, issue #100)
-                if (cqe.res == 0 || (op->done % kAlign) != 0) {
-                    fail(-EIO, "short read (unexpected end of file)");
+                if (cqe.res == 0 || (op->done % r.align) != 0) {
+                    fail_read(ud.index_of_op, *op, -EIO, "short read (unexpected end of file)");
                     return;
                 }
                 be->stats.short_reads++;
@@ -330,18 +509,24 @@ struct Worker {
         }
         const bool ring_ok = rc == 0;
         const unsigned sq = ring_ok ? ring.sq_entries() : 0;
+        uint64_t t_awake = now_ns();
         while (true) {
             const bool running = wt.keep_running();
             if (!running && tracker.is_empty()) break;
-            unsigned started = 0;
+            unsigned started = 0, inline_done = 0;
             if (running) {
                 auto room = [&] { return !ring_ok || !(tracker.is_full() || ring.sq_len() + 2 > sq || ring.sq_len() + ring.cq_len() + 2 > sq); };
+                // Reads done inline block this thread: after an extent's worth the loop goes on to submit and reap what
+                // is queued in the ring (the openat of the next file, closes) before taking more.
+                auto inline_budget = [&] { return inline_done < 8; };
                 // 1. reads that waited for staging space, in order
-                while (!stalled_reads.empty() && room()) {
+                while (!stalled_reads.empty() && room() && inline_budget()) {
+                    const uint64_t before = c_inline;
                     const Start s = start(stalled_reads.front());
                     if (s == Start::Retry) break;
                     stalled_reads.pop_front();
                     if (s == Start::Started) started++;
+                    inline_done += (unsigned)(c_inline - before);
                 }
                 // 2. plans that waited for HBM, each once
                 for (size_t n = stalled_plans.size(); n-- > 0;) {
@@ -357,7 +542,7 @@ struct Worker {
                 }
                 // 3. top up the SQ with new tasks (worker.rs:65-88), two SQEs of headroom (MAX_SQ_ENTRIES_PER_ITERATION)
                 bool ran_dry = false;
-                while (stalled_reads.empty() && room()) {
+                while (stalled_reads.empty() && room() && inline_budget()) {
                     auto t = wt.find_task();
                     if (!t) {
                         ran_dry = true;
@@ -368,9 +553,11 @@ struct Worker {
                         send_error(be, rc, 0, *op.req, -1, "io_uring unavailable");
                         continue;
                     }
+                    const uint64_t before = c_inline;
                     const Start s = start(op);
                     if (s == Start::Retry) (op.kind == Op::Read ? stalled_reads : stalled_plans).push_back(std::move(op));
                     else if (s == Start::Started) started++;
+                    inline_done += (unsigned)(c_inline - before);
                 }
                 // nothing more to add right now: let the partly filled extent go (bounds latency, ends a workload)
                 if (slots && ran_dry && stalled_reads.empty()) close_current_extent();
@@ -385,14 +572,26 @@ struct Worker {
                 handle(cqe);
             }
             if (ring_ok && ring.unsubmitted()) ring.submit();
-            if (got || started) continue;
+            if (got || started || inline_done) continue;
             if (tracker.is_empty() && stalled_reads.empty() && stalled_plans.empty()) {
-                if (running) wt.park();  // worker.rs:93-99
+                if (running) {
+                    c_busy_ns += now_ns() - t_awake;
+                    fold_counters();
+                    wt.park();  // worker.rs:93-99
+                    t_awake = now_ns();
+                }
                 continue;
             }
-            if (!tracker.is_empty()) ring.submit(1, 200);  // submit_and_wait(1), bounded so new tasks are noticed
-            else std::this_thread::sleep_for(std::chrono::microseconds(50));  // only waiting for staging / HBM space
+            if (!tracker.is_empty()) {
+                ring.submit(1, 200);  // submit_and_wait(1), bounded so new tasks are noticed
+            } else {  // only waiting for staging / HBM space
+                const uint64_t t0 = now_ns();
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+                c_stall_ns += now_ns() - t0;
+            }
         }
+        c_busy_ns += now_ns() - t_awake;
+        fold_counters();
     }
 };
 

@@ -31,8 +31,8 @@ def _segments(src_addrs, dst_addrs, lens):
 class PackPlan:
     """Device-resident descriptor table for one pack_strip[_crc32c] launch."""
 
-    def __init__(self, device, src_addrs, dst_addrs, lens, store=True, crc32c=True):
-        flags = (N.PACK_STORE if store else 0) | (N.PACK_CRC32C if crc32c else 0)
+    def __init__(self, device, src_addrs, dst_addrs, lens, store=True, crc32c=True, light=False):
+        flags = (N.PACK_STORE if store else 0) | (N.PACK_CRC32C if crc32c else 0) | (N.PACK_LIGHT if light else 0)
         segs, n = _segments(src_addrs, dst_addrs, lens)
         self._h = ctypes.c_void_p()
         N.check(N.lib.lsio_cuda_pack_plan_create(int(device), segs, n, flags, ctypes.byref(self._h)), "pack_plan_create")
@@ -65,16 +65,17 @@ class PackPlan:
             pass
 
 
-def pack_strip_crc32c(src, dst, src_off, dst_off, lens, store=True, crc32c=True, stream=None):
+def pack_strip_crc32c(src, dst, src_off, dst_off, lens, store=True, crc32c=True, stream=None, light=False):
     """Gather src[src_off[i]:+len[i]] into dst[dst_off[i]:] (uint8 CUDA tensors) and return the
-    per-segment CRC-32C as a uint32 CUDA tensor (or None)."""
+    per-segment CRC-32C as a uint32 CUDA tensor (or None).  light=True: the small-footprint kernel variant
+    the pipeline uses for its batches (LSIO_CUDA_PACK_LIGHT)."""
     import torch
 
     dev = src.device.index
     base_s, base_d = src.data_ptr(), (dst.data_ptr() if dst is not None else 0)
     s = np.asarray(src_off, dtype=np.uint64) + np.uint64(base_s)
     d = np.asarray(dst_off, dtype=np.uint64) + np.uint64(base_d)
-    plan = PackPlan(dev, s, d, lens, store=store, crc32c=crc32c)
+    plan = PackPlan(dev, s, d, lens, store=store, crc32c=crc32c, light=light)
     out = torch.empty(max(len(lens), 1), dtype=torch.int32, device=src.device) if crc32c else None
     try:
         plan.launch(out, stream)
@@ -117,13 +118,15 @@ def fill_pattern(buf, file_id, file_off=0, stream=None):
                                          _stream_ptr(stream)), "fill_pattern")
 
 
-def probe_read_ceiling(paths, block_bytes=1 << 20, n_threads=8, queue_depth=32, o_direct=True):
-    """GiB/s of raw READ_FIXED reads over `paths` with no GPU work (stand-in for benches/fio.ini)."""
+def probe_read_ceiling(paths, block_bytes=1 << 20, n_threads=8, queue_depth=32, o_direct=True, inline_reads=0):
+    """GiB/s of raw reads over `paths` with no GPU work (stand-in for benches/fio.ini): READ_FIXED through io_uring, or
+    -- inline_reads=1, the backend's own default rule -- preadv2 on the probing thread for files the kernel cannot read
+    asynchronously (tmpfs)."""
     import os
 
     arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
     out = ctypes.c_double(0)
-    N.check(N.lib.lsio_probe_read_ceiling(arr, len(paths), block_bytes, n_threads, queue_depth, int(o_direct), ctypes.byref(out)),
+    N.check(N.lib.lsio_probe_read_ceiling_ex(arr, len(paths), block_bytes, n_threads, queue_depth, int(o_direct), int(inline_reads), ctypes.byref(out)),
             "probe_read_ceiling")
     return out.value
 

@@ -115,15 +115,35 @@ class Receiver:
             raise Disconnected()
         if rc != N.RECV_OK:
             raise RuntimeError(f"lsio_completion_recv_batch: {rc}")
-        rec = np.frombuffer(arr, dtype=OUTPUT_DTYPE, count=n.value)
-        rec.flags.writeable = False
-        return rec
+        return np.frombuffer(arr, dtype=OUTPUT_DTYPE, count=n.value)  # writable: take_buffer() clears the handles it hands out
+
+    # A chunk handle has ONE owner.  A record array owns the handles in its chunk.buffer field until they are either
+    # dropped with drop_buffers(records) or moved out with take_buffer(s), which clears the field so that a later
+    # drop_buffers() on the same records skips them (a handle wrapped in AlignedBytes AND dropped in bulk was a
+    # double free).
+    @staticmethod
+    def take_buffer(records, i):
+        """Move the chunk buffer of records[i] out as an AlignedBytes (the record's field becomes NULL)."""
+        h = int(records["chunk"]["buffer"][i])
+        if not h:
+            raise ValueError("records[%d] holds no chunk buffer (an error item, or already taken)" % i)
+        records["chunk"]["buffer"][i] = 0
+        return AlignedBytes(h)
+
+    @staticmethod
+    def take_buffers(records):
+        """Move every chunk buffer out: a list of AlignedBytes (None for error items); the records keep none."""
+        hs = [int(h) for h in records["chunk"]["buffer"]]
+        records["chunk"]["buffer"][:] = 0
+        return [AlignedBytes(h) if h else None for h in hs]
 
     @staticmethod
     def drop_buffers(records):
-        """Drop the chunk buffers of a record array from recv_batch (lsio_aligned_bytes_drop each)."""
+        """Drop the chunk buffers a record array from recv_batch still owns (lsio_aligned_bytes_drop each; NULLs are skipped)."""
         ptrs = np.ascontiguousarray(records["chunk"]["buffer"], dtype=np.uint64)
         N.lib.lsio_aligned_bytes_drop_many(ptrs.ctypes.data, len(ptrs))
+        if records.flags.writeable:
+            records["chunk"]["buffer"][:] = 0
 
     def __len__(self):
         return N.lib.lsio_completion_len(self._h)
@@ -242,6 +262,26 @@ class IoUringCuda:
         s = N.CStats()
         N.lib.lsio_uring_cuda_get_stats(self._h, ctypes.byref(s))
         return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def latency_histogram(self):
+        """Per-chunk latency (request submitted -> chunk in the channel) as 32 log2 buckets of microseconds."""
+        b = (ctypes.c_uint64 * 32)()
+        N.lib.lsio_uring_cuda_get_latency_histogram(self._h, b)
+        return np.array(list(b), dtype=np.uint64)
+
+    def latency_summary(self):
+        """{first_chunk_ms, p50_ms, p99_ms (upper bucket edges), chunks} since the last reset_latency()."""
+        h = self.latency_histogram()
+        n = int(h.sum())
+        out = {"chunks": n, "first_chunk_ms": self.stats()["first_chunk_ns"] / 1e6}
+        if n:
+            c = np.cumsum(h)
+            for name, q in (("p50_ms", 0.5), ("p99_ms", 0.99)):
+                out[name] = float(2 ** (int(np.searchsorted(c, q * n)) + 1)) / 1e3
+        return out
+
+    def reset_latency(self):
+        N.lib.lsio_uring_cuda_reset_latency(self._h)
 
     def drop(self):
         """Drop: joins the workers; receivers see Disconnected once drained."""

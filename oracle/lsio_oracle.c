@@ -242,6 +242,32 @@ uint32_t lsio_oracle_crc32c(uint32_t crc, const uint8_t* p, size_t n) {
 #endif
     return ~c;
 }
+/* CRC-32C of consecutive blocks of a file: out[k] = crc32c(file[k*blocksize, min((k+1)*blocksize, size))), k < n_blocks.
+ * Buffered pread, one block at a time (bench.py builds its expected-CRC tables with this: the landed chunks'
+ * device CRCs are compared with values the product never computed).  Returns blocks done or -errno. */
+int64_t lsio_oracle_crc32c_file_blocks(const char* path, uint64_t blocksize, uint64_t n_blocks, uint32_t* out) {
+    if (!path || !blocksize || !out) return -EINVAL;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return -errno;
+    uint8_t* buf = (uint8_t*)malloc(blocksize);
+    if (!buf) { close(fd); return -ENOMEM; }
+    uint64_t k = 0;
+    for (; k < n_blocks; k++) {
+        uint64_t done = 0;
+        while (done < blocksize) {
+            ssize_t n = pread(fd, buf + done, blocksize - done, (off_t)(k * blocksize + done));
+            if (n < 0) { if (errno == EINTR) continue; int e = errno; free(buf); close(fd); return -e; }
+            if (n == 0) break;
+            done += (uint64_t)n;
+        }
+        if (!done) break;
+        out[k] = lsio_oracle_crc32c(0, buf, done);
+        if (done < blocksize) { k++; break; }
+    }
+    free(buf);
+    close(fd);
+    return (int64_t)k;
+}
 /* table-only variant kept callable so the SSE path can be cross-checked in tests */
 uint32_t lsio_oracle_crc32c_table(uint32_t crc, const uint8_t* p, size_t n) {
     if (!__atomic_load_n(&crc_tab_ready, __ATOMIC_ACQUIRE)) crc_tab_init();

@@ -93,6 +93,7 @@ int64_t lsio_oracle_pread_range(const char* path, int64_t start, int64_t end, ui
 uint32_t lsio_oracle_crc32c_bitwise(uint32_t crc, const uint8_t* p, size_t n); /* definition */
 uint32_t lsio_oracle_crc32c(uint32_t crc, const uint8_t* p, size_t n);         /* slice-by-8 / SSE4.2 */
 uint32_t lsio_oracle_crc32c_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+int64_t lsio_oracle_crc32c_file_blocks(const char* path, uint64_t blocksize, uint64_t n_blocks, uint32_t* out);
 uint64_t lsio_oracle_xxh64(const uint8_t* p, size_t n, uint64_t seed);
 
 /* ---- pack/strip restatement: what the pack kernel must produce -------------------------- */

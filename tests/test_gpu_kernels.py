@@ -32,16 +32,30 @@ def _run_pack(lsio, oracle, dev, rng, lens, src_align=1, dst_align=1):
     src = rng.integers(0, 256, ssz, dtype=np.uint8)
     want_dst, want_crc, _ = oracle.pack(src, so, do, lens, dsz)
     tsrc = torch.from_numpy(src).to(dev)
-    tdst = torch.zeros(dsz, dtype=torch.uint8, device=dev)
-    crc = lsio.cuda_ops.pack_strip_crc32c(tsrc, tdst, so, do, lens)
-    assert np.array_equal(tdst.cpu().numpy(), want_dst), "packed bytes differ (or bytes outside the ranges were touched)"
-    assert np.array_equal(crc.cpu().numpy().view(np.uint32), want_crc), "crc32c differs"
-    # crc-only (in place) and store-only variants
-    crc2 = lsio.cuda_ops.pack_strip_crc32c(tsrc, None, so, do, lens, store=False)
-    assert np.array_equal(crc2.cpu().numpy().view(np.uint32), want_crc)
-    tdst2 = torch.zeros(dsz, dtype=torch.uint8, device=dev)
-    lsio.cuda_ops.pack_strip_crc32c(tsrc, tdst2, so, do, lens, crc32c=False)
-    assert np.array_equal(tdst2.cpu().numpy(), want_dst)
+    for light in (False, True):  # the roofline variant and the pipeline's small-footprint variant: same results
+        tdst = torch.zeros(dsz, dtype=torch.uint8, device=dev)
+        crc = lsio.cuda_ops.pack_strip_crc32c(tsrc, tdst, so, do, lens, light=light)
+        assert np.array_equal(tdst.cpu().numpy(), want_dst), "packed bytes differ (or bytes outside the ranges were touched)"
+        assert np.array_equal(crc.cpu().numpy().view(np.uint32), want_crc), "crc32c differs"
+        # crc-only (in place) and store-only variants
+        crc2 = lsio.cuda_ops.pack_strip_crc32c(tsrc, None, so, do, lens, store=False, light=light)
+        assert np.array_equal(crc2.cpu().numpy().view(np.uint32), want_crc)
+        tdst2 = torch.zeros(dsz, dtype=torch.uint8, device=dev)
+        lsio.cuda_ops.pack_strip_crc32c(tsrc, tdst2, so, do, lens, crc32c=False, light=light)
+        assert np.array_equal(tdst2.cpu().numpy(), want_dst)
+        # segments that landed in place (src == dst, what a direct H2D landing hands the kernel) mixed with segments
+        # that move: the in-place ones are only checksummed, the bytes around them stay untouched
+        tmix = tdst.clone()
+        s_mix = np.where(np.arange(len(lens)) % 2 == 0, do + np.uint64(tmix.data_ptr()), so + np.uint64(tsrc.data_ptr()))
+        d_mix = do + np.uint64(tmix.data_ptr())
+        plan = lsio.cuda_ops.PackPlan(dev.index, s_mix, d_mix, lens, light=light)
+        out = torch.empty(max(len(lens), 1), dtype=torch.int32, device=dev)
+        plan.launch(out)
+        plan.launch(out)  # a plan can be launched again: scheduler words and per-segment counters re-arm themselves
+        torch.cuda.synchronize(dev)
+        plan.close()
+        assert np.array_equal(tmix.cpu().numpy(), want_dst)
+        assert np.array_equal(out[: len(lens)].cpu().numpy().view(np.uint32), want_crc)
 
 
 def test_golden_vectors_through_the_kernel(lsio, oracle, cuda_dev):
@@ -97,10 +111,11 @@ def test_pack_all_sixteen_relative_shifts(lsio, oracle, cuda_dev):
             spos += ln; dpos += ln
     want_dst, want_crc, _ = oracle.pack(src, so, do, lens, dpos + 4096)
     tsrc = torch.from_numpy(src).to(cuda_dev)
-    tdst = torch.zeros(dpos + 4096, dtype=torch.uint8, device=cuda_dev)
-    crc = lsio.cuda_ops.pack_strip_crc32c(tsrc, tdst, so, do, lens)
-    assert np.array_equal(tdst.cpu().numpy(), want_dst)
-    assert np.array_equal(crc.cpu().numpy().view(np.uint32), want_crc)
+    for light in (False, True):
+        tdst = torch.zeros(dpos + 4096, dtype=torch.uint8, device=cuda_dev)
+        crc = lsio.cuda_ops.pack_strip_crc32c(tsrc, tdst, so, do, lens, light=light)
+        assert np.array_equal(tdst.cpu().numpy(), want_dst)
+        assert np.array_equal(crc.cpu().numpy().view(np.uint32), want_crc)
 
 
 def test_pack_multi_tile_and_large(lsio, oracle, cuda_dev):

@@ -19,7 +19,7 @@ for rnd in range(12):
             ud = int(r["chunk"]["user_data"]); f, k = ud >> 32, ud & 0xFFFFFFFF
             if r["status"] != 0: errs.append((f, k, int(r["status"]), r["context"][:120]))
             elif r["crc32c"] != crc[f, k]:
-                v = L.AlignedBytes(int(r["chunk"]["buffer"])); data = v.as_slice(); v._h = None  # drop_buffers() below owns it
+                v = L.AlignedBytes(int(r["chunk"]["buffer"])); data = v.as_slice(); v._h = None  # borrowed: the record keeps the handle, drop_buffers() below frees it
                 want = np.fromfile(paths[f], dtype=np.uint8, count=bench.BLOCK, offset=k * bench.BLOCK)
                 diff = np.nonzero(data != want)[0]
                 got_crc = int(r["crc32c"])
