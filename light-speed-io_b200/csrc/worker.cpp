@@ -512,7 +512,12 @@ struct Worker {
         uint64_t t_awake = now_ns();
         while (true) {
             const bool running = wt.keep_running();
-            if (!running && tracker.is_empty()) break;
+            if (!running) {
+                // shutting down: the partly filled extent must still be published (the device thread waits for every
+                // extent that was reserved in the log) -- with inline reads it can be open while the tracker is empty
+                if (slots) close_current_extent();
+                if (tracker.is_empty()) break;
+            }
             unsigned started = 0, inline_done = 0;
             if (running) {
                 auto room = [&] { return !ring_ok || !(tracker.is_full() || ring.sq_len() + 2 > sq || ring.sq_len() + ring.cq_len() + 2 > sq); };
@@ -561,8 +566,6 @@ struct Worker {
                 }
                 // nothing more to add right now: let the partly filled extent go (bounds latency, ends a workload)
                 if (slots && ran_dry && stalled_reads.empty()) close_current_extent();
-            } else if (slots) {
-                close_current_extent();
             }
             if (ring_ok && ring.unsubmitted()) ring.submit();  // one enter per batch (reference: per op, worker.rs:79)
             bool got = false;
