@@ -6,16 +6,20 @@
 
 Workload (BASELINE.json configs[1], "C2"): the lsio_bench README workload -- 500 files x
 41,214,400 B read as 157 blocks of 262,144 B per file (crates/lsio_bench/src/main.rs:137) --
-delivered into the HBM of one B200, bit-exact.  A "step" is one pass over all 78,500 ranges.
+delivered into the HBM of one B200, bit-exact.  A "step" is one pass over all 78,500 ranges of
+every rank's shard (files dealt file_idx mod N, no collective on the data path).
 
-  value   : payload GiB/s of the device-resident pass: the 500 padded-read images are already
-            in HBM when the timed region starts; one step = one pack_strip_crc32c launch (+ its
-            fold kernel) over all 78,500 ranges.  CUDA events on the launching stream.
-  e2e     : the same metric through the reference-facing C ABI (lsio_uring_cuda_get_ranges +
-            completion channel) from files: O_DIRECT reads -> pinned ring -> H2D -> pack+crc ->
-            one chunk per range received and its CRC checked, all inside the timed region.
-  N > 1   : one process per GPU (torchrun); ranks share no data path: each rank lands the 500
-            files of its own shard in its own GPU ("weak"); value = all ranks' bytes / max time.
+  value    : payload GiB/s landed in HBM through the C ABI (lsio_uring_cuda_get_ranges + completion
+             channel, driven by the native lsio_bench driver, csrc/lsio_bench.cpp): files -> reads
+             into pinned slots -> H2D -> checksum (+pack) kernel -> one chunk per range, the fused
+             CRC-32C of EVERY chunk compared with a table the ORACLE made from the files.
+             Sum of the bytes of all ranks / max over ranks of the time of the K steps.
+  e2e      : the same workload through the Python mirror of the reference API (the call a user
+             makes: IoUringCuda.get_ranges + Receiver.recv_batch), CRCs checked in numpy.
+  roofline : the checksum/pack kernel alone, device-resident (one launch over all ranges per step,
+             CUDA events on the launching stream) + `pipeline_kernel`: the same kernel's launches
+             inside the timed region of `value` (event pairs recorded by the backend).
+  N > 1    : extra legs C4 (1 MiB ranges) and, at N = 8, C5 (4 MiB ranges looped to ~1 TB).
 """
 import argparse
 import json
@@ -39,6 +43,7 @@ N_FILES = 500
 N_CHUNKS = FILE_SIZE // BLOCK  # 157: lsio_bench drops the 57,792-byte tail
 METRIC = "GiB/s of byte ranges landed in HBM"
 GIB = float(1 << 30)
+MIB = 1 << 20
 
 
 def log(*a):
@@ -70,7 +75,7 @@ def barrier():
         dist.barrier()
 
 
-def reduce_bytes_and_time(nbytes, secs, device):
+def reduce_sum_max(nbytes, secs, device):
     """Whole-job aggregation: SUM of the units every rank processed, MAX of the time."""
     import torch
     import torch.distributed as dist
@@ -82,6 +87,19 @@ def reduce_bytes_and_time(nbytes, secs, device):
     dist.all_reduce(b, op=dist.ReduceOp.SUM)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return int(b.item()), float(t.item())
+
+
+def gather_floats(x, device):
+    """[x of rank 0, x of rank 1, ...] on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return [float(x)]
+    t = torch.zeros(dist.get_world_size(), dtype=torch.float64, device=device)
+    t[dist.get_rank()] = float(x)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.cpu()]
 
 
 # ---- clocks during the timed region (B200_PROFILING.md) -------------------------------------------
@@ -130,13 +148,14 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---- workload -------------------------------------------------------------------------------------
+# ---- synthetic files and their expected checksums: made by the ORACLE, never by the product ---------
 def pick_data_dir(args, need_bytes):
     if args.dir:
         return args.dir, ("tmpfs" if args.dir.startswith("/dev/shm") else "disk")
     try:
         st = os.statvfs("/dev/shm")
-        if st.f_bavail * st.f_frsize > need_bytes + (8 << 30):
+        have = sum(os.path.getsize(os.path.join("/dev/shm/lsio_bench", f)) for f in os.listdir("/dev/shm/lsio_bench")) if os.path.isdir("/dev/shm/lsio_bench") else 0
+        if st.f_bavail * st.f_frsize + have > need_bytes + (8 << 30):
             return "/dev/shm/lsio_bench", "tmpfs"
     except OSError:
         pass
@@ -148,350 +167,495 @@ def chunk_ranges():
     return starts, starts + BLOCK
 
 
-def make_files(directory, n_files, device_index, want_crc=True):
-    """Create the synthetic files with the product's own fill_pattern kernel (position-keyed
-    content) and return (paths, expected crc32c[n_files, N_CHUNKS]) -- the expected
-    CRCs come from the crc-only kernel over the generated image, not from the oracle."""
-    import torch
+def _threads(fn, items, nt=None):
+    nt = nt or min(32, os.cpu_count() or 8, max(1, len(items)))
+    errs = []
 
-    from lsio_b200 import cuda_ops
+    def work(sub):
+        try:
+            for it in sub:
+                fn(it)
+        except Exception as ex:  # surfaced below
+            errs.append(ex)
+
+    ths = [threading.Thread(target=work, args=(items[k::nt],)) for k in range(nt)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    if errs:
+        raise errs[0]
+
+
+def write_files_cpu(directory, prefix, n_files, size, id_base=0):
+    """Position-keyed synthetic files (byte = f(file id, offset)) written by the oracle's generator
+    (oracle/lsio_oracle.c), so that neither the content nor the expected checksums come from the product."""
+    from oracle import oracle
 
     os.makedirs(directory, exist_ok=True)
-    paths = [os.path.join(directory, f"lsio_bench_{i}") for i in range(n_files)]
-    crc_path = os.path.join(directory, f"expected_crc32c_{n_files}.npy")
-    if os.path.exists(crc_path) and all(os.path.exists(p) and os.path.getsize(p) == FILE_SIZE for p in paths):
-        return paths, np.load(crc_path)
-    dev = torch.device(f"cuda:{device_index}")
-    group = 16  # files per generation batch
-    dbuf = torch.empty(group * FILE_SIZE, dtype=torch.uint8, device=dev)
-    hbuf = torch.empty(group * FILE_SIZE, dtype=torch.uint8, pin_memory=True)
-    crc_all = np.zeros((n_files, N_CHUNKS), dtype=np.uint32)
-    starts, _ = chunk_ranges()
-    for g0 in range(0, n_files, group):
-        g1 = min(n_files, g0 + group)
-        for i in range(g0, g1):
-            cuda_ops.fill_pattern(dbuf[(i - g0) * FILE_SIZE:(i - g0 + 1) * FILE_SIZE], i, 0)
-        offs = np.concatenate([starts + (i - g0) * FILE_SIZE for i in range(g0, g1)]).astype(np.uint64)
-        crc = cuda_ops.pack_strip_crc32c(dbuf, None, offs, offs, np.full(len(offs), BLOCK, dtype=np.uint64), store=False)
-        crc_all[g0:g1] = crc.cpu().numpy().view(np.uint32).reshape(g1 - g0, N_CHUNKS)
-        hbuf[: (g1 - g0) * FILE_SIZE].copy_(dbuf[: (g1 - g0) * FILE_SIZE])
-        torch.cuda.synchronize(dev)
-        harr = hbuf.numpy()
-
-        def write(i):
-            with open(paths[i], "wb") as f:
-                f.write(memoryview(harr[(i - g0) * FILE_SIZE:(i - g0 + 1) * FILE_SIZE]))
-                f.flush()
-                os.fsync(f.fileno())
-
-        ths = [threading.Thread(target=write, args=(i,)) for i in range(g0, g1)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
-    np.save(crc_path, crc_all)
-    del dbuf, hbuf
-    torch.cuda.empty_cache()
-    return paths, crc_all
+    paths = [os.path.join(directory, f"{prefix}_{i}") for i in range(n_files)]
+    todo = [i for i, p in enumerate(paths) if not (os.path.exists(p) and os.path.getsize(p) == size)]
+    _threads(lambda i: oracle.write_file(paths[i], id_base + i, size), todo)
+    return paths
 
 
-# ---- the device-resident pass (`value`, roofline) ---------------------------------------------------
-def run_value(args, dev, n_files, expect_crc):
+def oracle_crc_table(directory, tag, paths, blocksize, n_blocks):
+    """uint32[n_files, n_blocks]: CRC-32C of every block of every file, computed by the ORACLE from the files
+    (SSE4.2, one thread per file; the ctypes call releases the GIL).  Cached next to the files."""
+    from oracle import oracle
+
+    fn = os.path.join(directory, f"oracle_crc32c_{tag}_{len(paths)}x{n_blocks}x{blocksize}.npy")
+    if os.path.exists(fn):
+        t = np.load(fn)
+        if t.shape == (len(paths), n_blocks):
+            return t
+    t = np.zeros((len(paths), n_blocks), dtype=np.uint32)
+
+    def one(i):
+        c = oracle.crc32c_file_blocks(paths[i], blocksize, n_blocks)
+        assert len(c) == n_blocks, (paths[i], len(c))
+        t[i] = c
+
+    _threads(one, list(range(len(paths))))
+    np.save(fn + ".tmp.npy", t)
+    os.replace(fn + ".tmp.npy", fn)
+    return t
+
+
+def evict_page_cache(paths):
+    """crates/lsio_bench/src/main.rs:192-199 (`vmtouch -e`) restated: fsync + posix_fadvise(DONTNEED).
+    A no-op on tmpfs (the files ARE the page cache)."""
+    for p in paths:
+        try:
+            fd = os.open(p, os.O_RDONLY)
+            try:
+                os.fsync(fd)
+                os.posix_fadvise(fd, 0, 0, os.POSIX_FADV_DONTNEED)
+            finally:
+                os.close(fd)
+        except OSError:
+            pass
+
+
+# ---- backend construction ----------------------------------------------------------------------------
+def cpu_slice(rank, world):
+    """Disjoint CPU slice of this rank (one process per GPU on a shared box), or (0, 0) when alone / not contiguous."""
+    cpus = sorted(os.sched_getaffinity(0))
+    if world <= 1:
+        return 0, 0, len(cpus)
+    per = len(cpus) // world
+    mine = cpus[rank * per:(rank + 1) * per]
+    if not mine or mine != list(range(mine[0], mine[0] + len(mine))):
+        return 0, 0, per
+    return mine[0], len(mine), per
+
+
+def backend(args, dev, workers=None, **over):
+    import lsio_b200 as L
+
+    kw = dict(devices=(dev.index,), arena_bytes=args.arena_gib << 30, staging_bytes=args.staging_mib << 20, min_copy_bytes=args.min_copy_mib << 20,
+              flush_us=args.flush_us, pack_threads=args.pack_threads, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10,
+              merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us, staging_mode=args.staging_mode,
+              host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib, statx_via_ring=args.statx_via_ring,
+              inline_reads=args.inline_reads, direct_landing=args.direct_landing, steal_batch=args.steal_batch,
+              pack_light_below_mib=args.pack_light_below_mib, completion_bound=args.completion_bound, copy_coalesce_slots=args.copy_coalesce_slots)
+    if args.pin and args.cpu_count:
+        kw.update(cpu_first=args.cpu_first, cpu_count=args.cpu_count)
+    kw.update(over)
+    return L.IoUringCuda(workers or args.workers, **kw)
+
+
+PIPE_KEYS = ("requests", "reads", "read_bytes", "short_reads", "inline_reads", "h2d_copies", "h2d_bytes", "direct_extents", "pack_launches", "kernel_launches",
+             "staging_stalls", "arena_stalls", "read_ns", "copy_enqueue_ns", "worker_stall_ns", "worker_busy_ns", "pack_kernel_ns", "pack_kernel_bytes",
+             "max_dio_align", "payload_bytes")
+
+
+def stats_delta(a, b):
+    return {k: b[k] - a[k] for k in PIPE_KEYS if k != "max_dio_align"} | {"max_dio_align": b["max_dio_align"]}
+
+
+def per_worker(st, workers, secs):
+    """What one worker thread does with its time (verdict r1 #2c: a number, not an inference)."""
+    out = {"workers": workers}
+    if st["read_ns"]:
+        out["inline_read_gib_s_per_thread"] = st["read_bytes"] / st["read_ns"] * 1e9 / GIB if st["inline_reads"] else None
+    busy = max(1, st["worker_busy_ns"])
+    out["frac_of_awake_time_reading"] = st["read_ns"] / busy
+    out["frac_of_awake_time_enqueueing_h2d"] = st["copy_enqueue_ns"] / busy
+    out["frac_of_awake_time_waiting_for_slots_or_hbm"] = st["worker_stall_ns"] / busy
+    out["awake_frac_of_wall"] = st["worker_busy_ns"] / max(1.0, workers * secs * 1e9)
+    return out
+
+
+# ---- passes over the C2 workload --------------------------------------------------------------------
+def native_pass(u, paths, ids, expect):
+    """lsio_bench::read_files over the C ABI (csrc/lsio_bench.cpp): submit every file, receive one chunk per
+    range, compare its fused CRC with the oracle's table, drop it; ends with a device synchronise."""
+    secs, nbytes, ok, bad = u.bench_read_files(paths, ids, BLOCK, N_CHUNKS, expect)
+    return secs, nbytes, bad + (len(paths) * N_CHUNKS - ok - bad)
+
+
+def python_pass(u, paths, ids, expect, dev):
+    """The same pass written against the Python mirror of the reference API, as a user would."""
+    import torch
+
+    from lsio_b200.io_uring_cuda import Receiver
+
+    starts, ends = chunk_ranges()
+    lo = np.arange(N_CHUNKS, dtype=np.uint64)
+    total = len(paths) * N_CHUNKS
+    rx = u.completion()
+    t0 = time.perf_counter()
+    for p, fid in zip(paths, ids):
+        u.get_ranges_arrays(p, starts, ends, (np.uint64(fid) << np.uint64(32)) | lo)
+    got = nbytes = bad = 0
+    while got < total:
+        rec = rx.recv_batch(8192, 60.0)
+        ok = rec["status"] == 0
+        ud = rec["chunk"]["user_data"]
+        good = ok & (rec["crc32c"] == expect[(ud >> np.uint64(32)).astype(np.int64) % len(expect), (ud & np.uint64(0xFFFFFFFF)).astype(np.int64) % N_CHUNKS])
+        bad += int(len(rec) - good.sum())
+        nbytes += int(good.sum()) * BLOCK
+        Receiver.drop_buffers(rec)
+        got += len(rec)
+    torch.cuda.synchronize(dev)
+    return time.perf_counter() - t0, nbytes, bad
+
+
+def timed_leg(u, one_pass, steps, warmup, dev):
+    """W untimed passes, then exactly K passes bracketed by barrier + synchronize on both sides."""
+    import torch
+
+    for _ in range(warmup):
+        one_pass()
+    torch.cuda.synchronize(dev)
+    barrier()
+    u.reset_latency()
+    st0 = u.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    secs, nbytes, bad = [], 0, 0
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        s, b, x = one_pass()
+        secs.append(s)
+        nbytes += b
+        bad += x
+    torch.cuda.synchronize(dev)
+    t_all = time.perf_counter() - t_all
+    e1.record()
+    torch.cuda.synchronize(dev)
+    barrier()
+    return {"secs": secs, "total_secs": t_all, "cuda_event_secs": e0.elapsed_time(e1) * 1e-3, "bytes": nbytes, "bad": bad,
+            "stats": stats_delta(st0, u.stats()), "latency": u.latency_summary()}
+
+
+# ---- the device-resident kernel pass (`roofline`) -----------------------------------------------------
+def run_kernel(args, dev, n_files, expect_crc, in_place=False):
+    """The padded-read images are already in HBM; one step = one launch of the pack+crc kernel over all ranges
+    (+ its fold kernel).  `in_place`: the crc-only form the pipeline runs on directly landed extents (traffic L)."""
     import torch
 
     from lsio_b200 import cuda_ops
 
     payload = n_files * N_CHUNKS * BLOCK
-    src = torch.empty(n_files * FILE_SIZE, dtype=torch.uint8, device=dev)  # the padded-read images, as the H2D stage leaves them
+    src = torch.empty(n_files * FILE_SIZE, dtype=torch.uint8, device=dev)
     for i in range(n_files):
         cuda_ops.fill_pattern(src[i * FILE_SIZE:(i + 1) * FILE_SIZE], i, 0)
-    dst = torch.empty(payload, dtype=torch.uint8, device=dev)                # per-request packed buffers, back to back
+    dst = None if in_place else torch.empty(payload, dtype=torch.uint8, device=dev)
     starts, _ = chunk_ranges()
     so = np.concatenate([starts.astype(np.uint64) + np.uint64(i * FILE_SIZE) for i in range(n_files)])
-    do = np.arange(n_files * N_CHUNKS, dtype=np.uint64) * np.uint64(BLOCK)
+    do = so if in_place else np.arange(n_files * N_CHUNKS, dtype=np.uint64) * np.uint64(BLOCK)
     lens = np.full(len(so), BLOCK, dtype=np.uint64)
-    plan = cuda_ops.PackPlan(dev.index, so + np.uint64(src.data_ptr()), do + np.uint64(dst.data_ptr()), lens)
+    plan = cuda_ops.PackPlan(dev.index, so + np.uint64(src.data_ptr()), do + np.uint64((src if in_place else dst).data_ptr()), lens, store=not in_place)
     crc = torch.empty(len(so), dtype=torch.int32, device=dev)
     st = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(st):
-        for _ in range(args.warmup):
+        for _ in range(max(3, args.warmup)):
             plan.launch(crc, st)
     torch.cuda.synchronize(dev)
-    barrier()
     launches0 = cuda_ops.launch_count()
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    steps = max(5, min(args.steps, 20))
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     with torch.cuda.stream(st):
         e[0].record(st)
-        for k in range(args.steps):  # 41 GB touched per step >> 126 MB L2: no flush needed
+        for k in range(steps):  # 41 GB touched per step >> 126 MB L2: no flush needed
             plan.launch(crc, st)
             e[k + 1].record(st)
     torch.cuda.synchronize(dev)
-    barrier()
     launches = cuda_ops.launch_count() - launches0
-    step_ms = [e[k].elapsed_time(e[k + 1]) for k in range(args.steps)]
-    total_ms = e[0].elapsed_time(e[-1])
-    # parity at full size: CRCs equal the table made at generation time; bytes equal the pattern
+    step_ms = [e[k].elapsed_time(e[k + 1]) for k in range(steps)]
     got = crc.cpu().numpy().view(np.uint32).reshape(n_files, N_CHUNKS)
-    crc_ok = bool(np.array_equal(got, expect_crc[:n_files]))
-    ids = np.repeat(np.arange(n_files, dtype=np.uint64), N_CHUNKS)
-    foffs = np.tile(starts.astype(np.uint64), n_files)
-    mism = cuda_ops.verify_pattern(dst, do, lens, ids, foffs)
+    crc_ok = bool(np.array_equal(got, expect_crc[:n_files]))  # the generator kernel's image == the oracle's files, CRC by CRC
     algo = plan.algorithmic_bytes
     plan.close()
     del src, dst
     torch.cuda.empty_cache()
-    return {"payload": payload, "total_ms": total_ms, "step_ms": step_ms, "algo_bytes": algo, "launches": launches,
-            "crc_ok": crc_ok, "mismatched_bytes": mism}
+    return {"payload": payload, "step_ms": step_ms, "algo_bytes": algo, "launches": launches, "steps": steps, "crc_ok": crc_ok}
 
 
-# ---- the end-to-end pass through the C ABI (`e2e`) ----------------------------------------------------
-def e2e_pass(u, paths, file_ids, expect_crc, starts, ends, ud_lo):
-    """One pass of lsio_bench::read_files over the backend's C ABI (native driver, csrc/lsio_bench.cpp):
-    submit every file, receive one chunk per range, check its device CRC against the table made at
-    generation time, drop it; ends with a device synchronise."""
-    secs, nbytes, ok, bad = u.bench_read_files(paths, file_ids, BLOCK, N_CHUNKS, expect_crc)
-    return secs, nbytes, bad + (len(paths) * N_CHUNKS - ok - bad)
-
-
-def run_e2e(args, dev, paths, file_ids, expect_crc, steps, warmup, workers, o_direct=True):
-    import lsio_b200 as L
-
-    starts, ends = chunk_ranges()
-    ud_lo = np.arange(N_CHUNKS, dtype=np.uint64)
-    u = L.IoUringCuda(workers, devices=(dev.index,), arena_bytes=args.arena_gib << 30, staging_bytes=args.staging_mib << 20, o_direct=int(o_direct),
-                      min_copy_bytes=args.min_copy_mib << 20, flush_us=args.flush_us, pack_threads=args.pack_threads, sq_entries=args.sq_entries, max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
-                      staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib)
-    try:
-        for _ in range(warmup):
-            e2e_pass(u, paths, file_ids, expect_crc, starts, ends, ud_lo)
-        barrier()
-        secs, nbytes, bad = [], 0, 0
-        t_all = time.perf_counter()
-        for _ in range(steps):
-            s, b, x = e2e_pass(u, paths, file_ids, expect_crc, starts, ends, ud_lo)
-            secs.append(s)
-            nbytes += b
-            bad += x
-        t_all = time.perf_counter() - t_all
-        barrier()
-        stats = u.stats()
-    finally:
-        u.drop()
-    return {"secs": secs, "total_secs": t_all, "bytes": nbytes, "bad": bad, "stats": stats}
-
-
-def verify_full_landing(dev, paths, file_ids, workers, staging_mib):
-    """Untimed proof at full size: land every range, keep all chunks resident, and check every
-    landed byte against the pattern with the verify_pattern kernel (no D2H)."""
+# ---- parity beyond checksums: landed bytes vs file bytes -------------------------------------------------
+def verify_landed_bytes(args, dev, paths, ids, every):
+    """Untimed: land every `every`-th file of this rank's shard, copy each chunk back and compare it byte for byte
+    with the file's own bytes (read with numpy, no product code on the expectation side)."""
     import torch
 
     import lsio_b200 as L
-    from lsio_b200 import cuda_ops
-    from lsio_b200.io_uring_cuda import Receiver
 
     starts, ends = chunk_ranges()
-    ud_lo = np.arange(N_CHUNKS, dtype=np.uint64)
-    need = len(paths) * N_CHUNKS * BLOCK
-    u = L.IoUringCuda(workers, devices=(dev.index,), arena_bytes=need + (2 << 30), staging_bytes=staging_mib << 20)
-    recs = []
-    try:
-        for p, fid in zip(paths, file_ids):
-            u.get_ranges_arrays(p, starts, ends, (np.uint64(fid) << np.uint64(32)) | ud_lo)
-        got = 0
+    lo = np.arange(N_CHUNKS, dtype=np.uint64)
+    sel = list(range(0, len(paths), every))
+    mism = compared = 0
+    with backend(args, dev, arena_bytes=4 << 30) as u:
         rx = u.completion()
-        while got < len(paths) * N_CHUNKS:
-            r = rx.recv_batch(8192, 60.0).copy()
-            recs.append(r)
-            got += len(r)
-        rec = np.concatenate(recs)
-        assert (rec["status"] == 0).all(), "errors during full landing"
-        ud = rec["chunk"]["user_data"]
-        views = [L.AlignedBytes(int(h)) for h in rec["chunk"]["buffer"]]
-        ptrs = np.array([v.as_ptr() for v in views], dtype=np.uint64)
-        lens = np.array([v.len() for v in views], dtype=np.uint64)
-        anchor = torch.empty(1, dtype=torch.uint8, device=dev)
-        mism = cuda_ops.verify_pattern(anchor, ptrs - np.uint64(anchor.data_ptr()), lens, ud >> np.uint64(32),
-                                       (ud & np.uint64(0xFFFFFFFF)) * np.uint64(BLOCK))
-        for v in views:
-            v.drop()
-    finally:
-        u.drop()
-    return int(mism), int(lens.sum())
+        for base in range(0, len(sel), 16):
+            part = sel[base:base + 16]
+            for j in part:
+                u.get_ranges_arrays(paths[j], starts, ends, (np.uint64(j) << np.uint64(32)) | lo)
+            files = {j: np.fromfile(paths[j], dtype=np.uint8) for j in part}
+            got = 0
+            while got < len(part) * N_CHUNKS:
+                rec = rx.recv_batch(4096, 60.0).copy()
+                assert (rec["status"] == 0).all(), "errors while landing the verification sample"
+                bufs = L.Receiver.take_buffers(rec)
+                for r, b in zip(rec, bufs):
+                    ud = int(r["chunk"]["user_data"])
+                    j, k = ud >> 32, ud & 0xFFFFFFFF
+                    data = b.to_torch().cpu().numpy()
+                    want = files[j][k * BLOCK:(k + 1) * BLOCK]
+                    mism += int(np.count_nonzero(data != want)) if len(data) == len(want) else max(len(data), len(want))
+                    compared += len(want)
+                    b.drop()
+                got += len(rec)
+    torch.cuda.synchronize(dev)
+    return {"files": len(sel), "bytes_compared": compared, "mismatched_bytes": mism, "expectation": "numpy.fromfile of the same file"}
 
 
-# ---- the other BASELINE.json configs (parity-test cases with numbers; not the headline line) ---------------
-def make_pattern_files(directory, prefix, n_files, size, device_index, id_base):
-    """n_files files of `size` bytes, content byte(id_base + i, off); generated on the GPU."""
-    import torch
-
-    from lsio_b200 import cuda_ops
-
-    os.makedirs(directory, exist_ok=True)
-    paths = [os.path.join(directory, f"{prefix}_{i}") for i in range(n_files)]
-    if all(os.path.exists(p) and os.path.getsize(p) == size for p in paths):
-        return paths
-    dev = torch.device(f"cuda:{device_index}")
-    group = max(1, min(n_files, (1 << 30) // size))
-    dbuf = torch.empty(group * size, dtype=torch.uint8, device=dev)
-    hbuf = torch.empty(group * size, dtype=torch.uint8, pin_memory=True)
-    for g0 in range(0, n_files, group):
-        g1 = min(n_files, g0 + group)
-        for i in range(g0, g1):
-            cuda_ops.fill_pattern(dbuf[(i - g0) * size:(i - g0 + 1) * size], id_base + i, 0)
-        hbuf[: (g1 - g0) * size].copy_(dbuf[: (g1 - g0) * size])
-        torch.cuda.synchronize(dev)
-        harr = hbuf.numpy()
-
-        def write(ids):
-            for i in ids:
-                with open(paths[i], "wb") as f:
-                    f.write(memoryview(harr[(i - g0) * size:(i - g0 + 1) * size]))
-
-        ids = list(range(g0, g1))
-        ths = [threading.Thread(target=write, args=(ids[k::16],)) for k in range(16)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
-    return paths
-
-
-def config_workload(name, directory, device_index, args):
-    """Returns (paths, file_ids, ranges_per_file [(starts, ends)], sizes, description)."""
-    from numpy.random import MT19937, Generator
-
-    if name == "C3":  # Zarr-like random reads (SURVEY 8d)
-        n_files, size = args.c3_files, 1_049_576
-        paths = make_pattern_files(directory, "c3", n_files, size, device_index, 100_000)
-        per = []
-        for i in range(n_files):
-            rng = Generator(MT19937(0xC3 + i))
-            ln = rng.integers(4096, 65537, size=8)
-            st = (rng.random(8) * (size - ln + 1)).astype(np.int64)
-            s, e = st, st + ln
-            if i % 100 == 0:  # one range ending exactly at EOF and one written as negative -len..-1
-                s = np.concatenate([s, [size - 5000, -7000]])
-                e = np.concatenate([e, [size, -1]])
-            per.append((s.astype(np.int64), e.astype(np.int64)))
-        return paths, [100_000 + i for i in range(n_files)], per, size, f"C3: {n_files} files x {size} B, 8 ranges/file of 4-64 KiB at arbitrary offsets (+EOF/negative ranges)"
-    if name == "C4":  # 1 MiB ranges over the C1 file set
-        paths, _ = make_files(directory, args.files, device_index)
-        k = FILE_SIZE // (1 << 20)
-        st = np.arange(k, dtype=np.int64) << 20
-        return paths, list(range(args.files)), [(st, st + (1 << 20))] * args.files, FILE_SIZE, f"C4: {args.files} files x {FILE_SIZE} B, {k} ranges of 1 MiB per file"
-    if name == "C5":  # large streaming scan, 4 MiB ranges
-        n_files, size = args.c5_files, 1 << 30
-        paths = make_pattern_files(directory, "c5", n_files, size, device_index, 200_000)
-        st = np.arange(size >> 22, dtype=np.int64) << 22
-        return paths, [200_000 + i for i in range(n_files)], [(st, st + (1 << 22))] * n_files, size, f"C5: {n_files} files x 1 GiB, 256 ranges of 4 MiB per file, {args.c5_loops} loops"
-    raise ValueError(name)
-
-
+# ---- the other BASELINE.json configs ------------------------------------------------------------------------
 def resolve(size, s, e):
     so = np.where(s >= 0, s, size + s)
     eo = np.where(e >= 0, e, size + e + 1)
     return so, eo
 
 
-def run_config(args, dev, rank):
-    """One BASELINE config end to end through the C ABI: an untimed verification pass (every landed
-    byte checked on the device against the pattern, fused CRCs cross-checked by the crc-only kernel
-    over the landed chunks), then timed passes."""
+def c3_workload(args, directory):
+    from numpy.random import MT19937, Generator
+
+    n_files, size = args.c3_files, 1_049_576
+    paths = write_files_cpu(directory, "c3", n_files, size, 100_000)
+    per = []
+    for i in range(n_files):
+        rng = Generator(MT19937(0xC3 + i))
+        ln = rng.integers(4096, 65537, size=8)
+        st = (rng.random(8) * (size - ln + 1)).astype(np.int64)
+        s, e = st, st + ln
+        if i % 100 == 0:  # one range ending exactly at EOF and one written as negative -len..-1
+            s = np.concatenate([s, [size - 5000, -7000]])
+            e = np.concatenate([e, [size, -1]])
+        per.append((s.astype(np.int64), e.astype(np.int64)))
+    return paths, per, size, f"C3: {n_files} files x {size} B, 8 ranges/file of 4-64 KiB at arbitrary offsets (+EOF/negative ranges)"
+
+
+def oracle_crc_of_ranges(directory, tag, paths, per, size):
+    """Expected CRC-32C of every range, from the oracle's pread + crc32c (cached)."""
+    from oracle import oracle
+
+    n = sum(len(p[0]) for p in per)
+    fn = os.path.join(directory, f"oracle_crc32c_{tag}_{len(paths)}_{n}.npy")
+    if os.path.exists(fn):
+        t = np.load(fn)
+        if len(t) == n:
+            return t
+    base = np.cumsum([0] + [len(p[0]) for p in per])
+    t = np.zeros(n, dtype=np.uint32)
+
+    def one(i):
+        data = np.fromfile(paths[i], dtype=np.uint8)
+        so, eo = resolve(size, per[i][0], per[i][1])
+        for k in range(len(so)):
+            t[base[i] + k] = oracle.crc32c(data[so[k]:eo[k]])
+
+    _threads(one, list(range(len(paths))))
+    np.save(fn + ".tmp.npy", t)
+    os.replace(fn + ".tmp.npy", fn)
+    return t
+
+
+def ranges_leg(args, dev, paths, per, expect, payload, steps, warmup, loops=1, **over):
+    """K timed steps of `loops` passes each over (paths, per-file range arrays) through the native driver; every chunk's
+    fused CRC is compared with `expect` (indexed by the global range index)."""
+    n_ranges = sum(len(p[0]) for p in per)
+    with backend(args, dev, **over) as u:
+        def one():
+            t = nb = bad = 0
+            for _ in range(loops):
+                s, b, ok, x = u.bench_read_ranges(paths, per, expect)
+                t += s
+                nb += b
+                bad += x + (n_ranges - ok - x)
+            return t, nb, bad
+
+        leg = timed_leg(u, one, steps, warmup, dev)
+    leg["payload_per_step"] = payload * loops
+    return leg
+
+
+def leg_summary(leg, dev, workers, n_gpus):
+    """Reduce one leg over the ranks: SUM bytes / MAX time."""
+    b, t = reduce_sum_max(leg["bytes"], leg["total_secs"], dev)
+    bad, _ = reduce_sum_max(leg["bad"], 0.0, dev)
+    per_rank = gather_floats(leg["bytes"] / leg["total_secs"] / GIB, dev)
+    st = leg["stats"]
+    return {"gib_s": b / t / GIB, "bytes": b, "secs": t, "steps": len(leg["secs"]), "ms_per_step": 1e3 * t / len(leg["secs"]), "bad_chunks": bad,
+            "per_rank_gib_s": [round(x, 2) for x in per_rank], "latency_rank0": leg["latency"],
+            "pipeline_rank0": {k: st[k] for k in ("reads", "read_bytes", "short_reads", "inline_reads", "h2d_copies", "h2d_bytes", "direct_extents",
+                                                  "pack_launches", "kernel_launches", "staging_stalls", "arena_stalls", "max_dio_align")},
+            "read_amplification": st["read_bytes"] / max(1, st["payload_bytes"]),
+            "per_worker_rank0": per_worker(st, workers, leg["total_secs"])}
+
+
+def pipeline_kernel(st, hbm_peak):
+    if not st["pack_kernel_ns"]:
+        return None
+    ach = st["pack_kernel_bytes"] / st["pack_kernel_ns"]  # bytes per ns = GB/s
+    return {"launches": st["pack_launches"], "algorithmic_bytes_per_launch": st["pack_kernel_bytes"] / max(1, st["pack_launches"]),
+            "us_per_launch": st["pack_kernel_ns"] / 1e3 / max(1, st["pack_launches"]), "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "is": "event pairs around every pack/checksum launch of the timed region (launch gaps included); batches are small because the pipeline is PCIe-bound: "
+                  "the kernel is busy for well under 2 % of the step"}
+
+
+# ---- ceilings ----------------------------------------------------------------------------------------------
+def pcie_h2d_gib_s(dev, secs=0.4):
     import torch
 
-    import lsio_b200 as L
+    h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    reps = 40
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize(dev)
+    return reps * (64 << 20) / (a.elapsed_time(b) * 1e-3) / GIB
+
+
+def source_ceiling(paths, thread_counts, o_direct=True, reps=1):
+    """Best raw read rate of the file set over several shapes (no GPU work): the same read sizes and slot geometry
+    as the product, deeper and shallower queues, READ_FIXED through the ring and preadv2 on the thread itself."""
     from lsio_b200 import cuda_ops
-    from lsio_b200.io_uring_cuda import Receiver
 
-    directory, source = pick_data_dir(args, 0)
-    directory = directory + "_" + args.config.lower()
-    paths, ids, per, size, desc = config_workload(args.config, directory, dev.index, args)
-    n_ranges = sum(len(p[0]) for p in per)
-    lens_by_file = []
-    for (s, e) in per:
-        so, eo = resolve(size, s, e)
-        lens_by_file.append((so, eo - so))
-    payload = int(sum(int(l.sum()) for _, l in lens_by_file))
-    base = np.cumsum([0] + [len(p[0]) for p in per])  # user_data = global range index
-    starts_all = np.concatenate([so for so, _ in lens_by_file]).astype(np.uint64)
-    lens_all = np.concatenate([l for _, l in lens_by_file]).astype(np.uint64)
-    fid_all = np.concatenate([np.full(len(p[0]), fid, dtype=np.uint64) for p, fid in zip(per, ids)])
-    keep_resident = payload < (60 << 30)
-    arena = (payload + (4 << 30)) if keep_resident else (8 << 30)
+    best, shapes = 0.0, []
+    for nthr in sorted(set(thread_counts)):
+        for block, qd, inl in ((512 << 10, 4, 1), (512 << 10, 4, 0), (1 << 20, 32, 0), (256 << 10, 64, 0), (2 << 20, 2, 1)):
+            try:
+                v = max(cuda_ops.probe_read_ceiling(paths, block, nthr, qd, o_direct, inl) for _ in range(reps))
+            except Exception as ex:
+                shapes.append({"threads": nthr, "block": block, "qd": qd, "inline": inl, "error": repr(ex)})
+                continue
+            shapes.append({"threads": nthr, "block": block, "qd": qd, "inline": inl, "gib_s": round(v, 2)})
+            best = max(best, v)
+    return best, shapes
 
-    def one_pass(u, keep):
-        rx = u.completion()
-        t0 = time.perf_counter()
-        for i, p in enumerate(paths):
-            s, e = per[i]
-            u.get_ranges_arrays(p, s, e, np.arange(base[i], base[i + 1], dtype=np.uint64))
-        got, recs = 0, []
-        while got < n_ranges:
-            rec = rx.recv_batch(8192, 120.0)
-            got += len(rec)
-            if keep:
-                recs.append(rec.copy())
-            else:
-                assert (rec["status"] == 0).all()
-                Receiver.drop_buffers(rec)
-        torch.cuda.synchronize()
-        return time.perf_counter() - t0, (np.concatenate(recs) if keep else None)
 
-    result = {"config": desc, "source": source, "ranges": n_ranges, "payload_bytes": payload}
-    with L.IoUringCuda(args.workers, devices=(dev.index,), arena_bytes=arena, staging_bytes=args.staging_mib << 20,
-                       min_copy_bytes=args.min_copy_mib << 20, sq_entries=args.sq_entries, statx_via_ring=args.statx_via_ring,
-                       max_read_bytes=args.max_read_kib << 10, merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us,
-                       staging_mode=args.staging_mode, host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib) as u:
-        if keep_resident:  # verification pass
-            _, rec = one_pass(u, True)
-            assert (rec["status"] == 0).all(), rec[rec["status"] != 0][:3]
-            ud = rec["chunk"]["user_data"].astype(np.int64)
-            views = [L.AlignedBytes(int(h)) for h in rec["chunk"]["buffer"]]
-            ptrs = np.array([v.as_ptr() for v in views], dtype=np.uint64)
-            vlen = np.array([v.len() for v in views], dtype=np.uint64)
-            assert np.array_equal(vlen, lens_all[ud]), "chunk lengths differ from end_off - start_off"
-            anchor = torch.empty(1, dtype=torch.uint8, device=dev)
-            rel = ptrs - np.uint64(anchor.data_ptr())
-            mism = cuda_ops.verify_pattern(anchor, rel, vlen, fid_all[ud], starts_all[ud])
-            crc2 = cuda_ops.pack_strip_crc32c(anchor, None, rel, rel, vlen, store=False).cpu().numpy().view(np.uint32)
-            result["verify"] = {"mismatched_bytes": int(mism), "crc_fused_equals_crc_of_landed_bytes": bool(np.array_equal(crc2, rec["crc32c"])),
-                                "chunks": len(views)}
-            for v in views:
-                v.drop()
-        secs = []
-        loops = args.c5_loops if args.config == "C5" else 1
-        expect = None
-        if keep_resident:  # the fused CRCs of the verified pass, indexed by user_data, are the expectation of the timed passes
-            expect = np.zeros(n_ranges, dtype=np.uint32)
-            expect[ud] = rec["crc32c"]
+# ---- CPU baselines (the only place the oracle is the thing being TIMED) ---------------------------------------
+def cpu_ref_pass(paths, workers, sqpoll=True, mode=0):
+    from oracle import oracle
 
-        def native_pass():  # timed passes run the native driver (csrc/lsio_bench.cpp): no Python in the loop
-            t, nb, ok, bad = u.bench_read_ranges(paths, per, expect)
-            assert bad == 0 and ok == n_ranges and nb == payload, (ok, bad, nb)
-            return t
+    starts, ends = chunk_ranges()
+    secs, nbytes, errors = oracle.bench_read_files(paths, starts, ends, workers, sqpoll=sqpoll, mode=mode)
+    return secs, nbytes, errors
 
-        for _ in range(max(1, args.warmup - 2)):
-            native_pass()
-        for _ in range(args.steps):
-            secs.append(sum(native_pass() for _ in range(loops)))
-        st = u.stats()
-    result["gib_s"] = payload * loops * len(secs) / sum(secs) / GIB
-    result["secs_per_step"] = secs
-    result["bytes_per_step"] = payload * loops
-    result["pipeline"] = {k: st[k] for k in ("reads", "read_bytes", "short_reads", "h2d_copies", "h2d_bytes", "pack_launches", "staging_stalls", "arena_stalls")}
-    result["read_amplification"] = st["read_bytes"] / max(1, st["payload_bytes"])
-    if rank == 0:
-        result["source_read_ceiling_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 2000)], min(1 << 20, size // 512 * 512), max(8, args.workers), 32, True)
-        if not args.no_cpu_baseline:  # the CPU port on the same files (the oracle's only use here)
-            from oracle import oracle
 
-            dt, okb, errs = oracle.bench_read_ranges(paths, per, 8, sqpoll=True)
-            result["cpu_baseline"] = {"value": okb / dt / GIB, "unit": "GiB/s", "kind": "port", "cores": 16, "errors": errs,
-                                      "sample": "one pass over the whole config, 8 workers + SQPOLL, C driver (oracle/lsio_uring_ref.c)"}
-        print(json.dumps(result), flush=True)
+def cpu_configs(cores):
+    """The reference's configurations (verdict r1 #4): the README one first, then the ones that use the whole box."""
+    return [("readme_8_workers_sqpoll", 8, True), (f"{max(1, cores // 2)}_workers_sqpoll", max(1, cores // 2), True), (f"{cores}_workers_no_sqpoll", cores, False)]
+
+
+def cpu_baseline_block(paths, source, cores):
+    rates = {}
+    for name, w, sq in cpu_configs(cores):
+        if name in rates:
+            continue
+        cpu_ref_pass(paths[: max(8, len(paths) // 10)], w, sq)  # warm the rings / kernel threads
+        s, b, errs = cpu_ref_pass(paths, w, sq)
+        rates[name] = {"gib_s": b / s / GIB, "workers": w, "sqpoll": sq, "threads": w * (2 if sq else 1), "errors": errs, "secs": s}
+    readme = rates["readme_8_workers_sqpoll"]
+    best_name = max(rates, key=lambda k: rates[k]["gib_s"])
+    s2, b2, _ = cpu_ref_pass(paths, 8, mode=1)
+    return {"value": readme["gib_s"], "unit": "GiB/s", "cores": readme["threads"], "kind": "port",
+            "sample": f"one pass over all {len(paths)} files ({readme['secs']:.2f} s) from {source}, README configuration: 8 worker threads + 8 SQPOLL kernel threads, into fresh host buffers; {readme['errors']} errors",
+            "nproc": cores, "configs": rates, "best_config": best_name, "best_gib_s": rates[best_name]["gib_s"],
+            # lsio_bench itself counts the 57,792-byte tail it never reads (main.rs:137, :181-183): +0.14 %
+            "reference_style_gib_s": readme["gib_s"] * FILE_SIZE / (N_CHUNKS * BLOCK),
+            "object_store_like_gib_s": b2 / s2 / GIB,
+            "object_store_like_is": ("buffered pread per range, 8 threads" + ("; the source is tmpfs, so this is a page-cache-hot memcpy that no eviction can cool down "
+                                     "(a disk-sourced, cache-evicted twin is in e2e_disk)" if source == "tmpfs" else "; page cache evicted first"))}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0  # rank 0 alone runs the CPU arm
+    need = args.files * FILE_SIZE
+    directory, source = pick_data_dir(args, need)
+    paths = write_files_cpu(directory, "lsio_bench", args.files, FILE_SIZE)
+    cores = os.cpu_count() or 1
+    # bound each step: estimate on a small sample, then size the sample for <= ~20 s per step
+    est_s, est_b, _ = cpu_ref_pass(paths[: min(20, len(paths))], 8)
+    rate = est_b / max(est_s, 1e-9)
+    n_sample = len(paths) if need / rate <= 20 else max(20, int(20 * rate / FILE_SIZE))
+    sample = paths[:n_sample]
+    if source != "tmpfs":
+        evict_page_cache(sample)
+    # one pass per configuration; the timed steps then run the BEST one, the README one is always reported
+    quick = {}
+    for name, w, sq in cpu_configs(cores):
+        if args.ref_workers:
+            name, w, sq = f"{args.ref_workers}_workers_sqpoll", args.ref_workers, True
+        if name in quick:
+            continue
+        cpu_ref_pass(sample[: max(8, len(sample) // 10)], w, sq)
+        s, b, e = cpu_ref_pass(sample, w, sq)
+        quick[name] = {"gib_s": b / s / GIB, "workers": w, "sqpoll": sq, "threads": w * (2 if sq else 1), "errors": e}
+    best = max(quick, key=lambda k: quick[k]["gib_s"])
+    w, sq = quick[best]["workers"], quick[best]["sqpoll"]
+    for _ in range(args.warmup):
+        cpu_ref_pass(sample, w, sq)
+    secs, nbytes, errors = [], 0, 0
+    for _ in range(args.steps):
+        s, b, e = cpu_ref_pass(sample, w, sq)
+        secs.append(s)
+        nbytes += b
+        errors += e
+    value = nbytes / sum(secs) / GIB
+    s2, b2, _ = cpu_ref_pass(sample, 8, mode=1)
+    desc = f"{n_sample} of {args.files} files x {N_CHUNKS} blocks of {BLOCK} B per step, source {source}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": "C2: lsio_bench README workload, 500 files x 41,214,400 B, 157 blocks of 262,144 B per file, into host buffers (CPU lsio_uring port)",
+                   "source": source, "dir": directory, "files": args.files, "worker_threads": w, "sqpoll": sq, "errors": errors,
+                   "timed_configuration": best, "timed_configuration_is": "the fastest of the configurations below on this box (one pass each); value is its K timed steps",
+                   "configurations_one_pass_gib_s": quick,
+                   "readme_configuration_gib_s": quick.get("readme_8_workers_sqpoll", {}).get("gib_s"),
+                   "object_store_like_gib_s": b2 / s2 / GIB,
+                   "object_store_like_is": "buffered pread per range, 8 threads" + (" (tmpfs: page-cache-hot by construction)" if source == "tmpfs" else ""),
+                   "note": "the reference is Rust and cannot be built here; this is oracle/lsio_uring_ref.c, its C restatement"},
+        "cpu_baseline": {"value": value, "unit": "GiB/s", "cores": quick[best]["threads"], "nproc": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
     return 0
 
 
+# ---- informative extra legs ------------------------------------------------------------------------------------
 def codec_leg(hbm_peak):
-    """Informative extra: the codec layer behind the same path.  Kernel numbers with CUDA
-    events on the launching stream; the pipeline number is wall clock from the first get_ranges to the last decoded,
-    device-verified row.  Shards are written with liblz4 (pyarrow), not with the oracle."""
+    """SURVEY 8f-4, DESIGN 3.3: the codec layer behind the same path.  Kernel numbers with CUDA events on the launching
+    stream; the pipeline number is wall clock from the first get_ranges to the last decoded, device-verified row.
+    Shards are written with liblz4 (pyarrow), not with the oracle."""
     import ctypes
 
     import torch
@@ -517,7 +681,6 @@ def codec_leg(hbm_peak):
         torch.cuda.synchronize()
         return statistics.mean(a.elapsed_time(b) for a, b in evs)
 
-    # byte unshuffle, element size 4: 1 GiB in, 1 GiB out per launch (>> L2)
     x = torch.randint(0, 256, (n, nbytes), dtype=torch.uint8, device="cuda")
     y = torch.empty_like(x)
     step = np.arange(n, dtype=np.uint64) * np.uint64(nbytes)
@@ -529,7 +692,6 @@ def codec_leg(hbm_peak):
     shuf = {"kernel": "shuffle_kernel<unshuffle>, elem 4", "algorithmic_bytes_per_launch": 2 * n * nbytes, "ms": ms,
             "achieved": 2 * n * nbytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s", "frac": 2 * n * nbytes / ms / 1e6 / hbm_peak, "bound": "hbm"}
     del x
-    # LZ4 block decode of 16,384 distinct-address blocks (64 liblz4-compressed chunks, each copied 256 times)
     pool = Z.make_pool(nbytes)
     bodies = [np.frombuffer(p[1][4:-4], dtype=np.uint8) for p in pool]  # strip the numcodecs header and the crc32c trailer
     stride = (max(len(b) for b in bodies) + 15) // 16 * 16
@@ -557,86 +719,46 @@ def codec_leg(hbm_peak):
             "shuffle_roofline": shuf, "lz4": lz4}
 
 
-def pcie_h2d_ceiling(dev):
+def disk_leg(args, dev):
+    """The same workload from a disk-backed directory (this pool: one virtio disk): O_DIRECT product path, the read
+    ceiling of that disk, and the CPU paths on the same files with the page cache evicted first."""
+    from oracle import oracle  # noqa: F401  (the CPU paths below)
+
+    free = shutil.disk_usage(os.path.dirname(args.disk_dir.rstrip("/")) or "/").free
+    if free < args.disk_files * FILE_SIZE + (4 << 30):
+        return {"skipped": "not enough free space"}
+    dpaths = write_files_cpu(args.disk_dir, "lsio_bench", args.disk_files, FILE_SIZE)
+    dcrc = oracle_crc_table(args.disk_dir, "c2", dpaths, BLOCK, N_CHUNKS)
+    evict_page_cache(dpaths)
+    ids = list(range(len(dpaths)))
+    with backend(args, dev, workers=min(args.workers, 8)) as u:
+        leg = timed_leg(u, lambda: native_pass(u, dpaths, ids, dcrc), 3, 1, dev)
+    ceil, shapes = source_ceiling(dpaths, [8, 16], True, reps=2)
+    val = leg["bytes"] / leg["total_secs"] / GIB
+    out = {"value": val, "unit": "GiB/s", "files": len(dpaths), "bad": leg["bad"], "read_ceiling_gib_s": ceil, "frac_of_ceiling": val / ceil if ceil else None,
+           "ceiling_shapes": shapes, "dir": args.disk_dir, "max_dio_align": leg["stats"]["max_dio_align"]}
+    s, b, e = cpu_ref_pass(dpaths, 8, True)
+    out["cpu_lsio_uring_o_direct_gib_s"] = b / s / GIB
+    evict_page_cache(dpaths)
+    s, b, e = cpu_ref_pass(dpaths, 8, mode=1)
+    out["cpu_object_store_like_cache_evicted_gib_s"] = b / s / GIB
+    return out
+
+
+def two_device_check(args, n_files, paths, expect):
+    """Single-process multi-device mode (one backend, two worker groups, files dealt round robin) on GPUs 0 and 1."""
     import torch
 
-    h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
-    d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(3):
-        d.copy_(h, non_blocking=True)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(40):
-        d.copy_(h, non_blocking=True)
-    b.record()
-    torch.cuda.synchronize(dev)
-    return 40 * (64 << 20) / (a.elapsed_time(b) * 1e-3) / GIB
+    import lsio_b200 as L
 
-
-# ---- CPU baselines (the only place the oracle is executed by bench.py) ----------------------------------
-def cpu_ref_pass(paths, workers, sqpoll=True, mode=0):
-    from oracle import oracle
-
-    starts, ends = chunk_ranges()
-    secs, nbytes, errors = oracle.bench_read_files(paths, starts, ends, workers, sqpoll=sqpoll, mode=mode)
-    return secs, nbytes, errors
-
-
-def write_files_cpu(directory, n_files):
-    """Reference arm only (no GPU needed there): files written by the oracle's generator."""
-    from oracle import oracle
-
-    os.makedirs(directory, exist_ok=True)
-    paths = [os.path.join(directory, f"lsio_bench_{i}") for i in range(n_files)]
-    todo = [i for i, p in enumerate(paths) if not (os.path.exists(p) and os.path.getsize(p) == FILE_SIZE)]
-
-    def work(ids):
-        for i in ids:
-            oracle.write_file(paths[i], i, FILE_SIZE)
-
-    nt = min(16, max(1, len(todo)))
-    ths = [threading.Thread(target=work, args=(todo[k::nt],)) for k in range(nt)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    return paths
-
-
-def run_reference(args):
-    rank, world, _ = dist_env()
-    if rank != 0:
-        return 0  # rank 0 alone runs the CPU arm
-    need = args.files * FILE_SIZE
-    directory, source = pick_data_dir(args, need)
-    paths = write_files_cpu(directory, args.files)
-    cores = os.cpu_count() or 1
-    workers = args.ref_workers or max(1, cores // 2)  # + one SQPOLL kernel thread per ring = all host threads
-    # bound each step: estimate on a small sample, then size the sample for <= ~20 s per step
-    est_s, est_b, _ = cpu_ref_pass(paths[: min(20, len(paths))], workers)
-    rate = est_b / max(est_s, 1e-9)
-    n_sample = len(paths) if need / rate <= 20 else max(20, int(20 * rate / FILE_SIZE))
-    sample = paths[:n_sample]
-    for _ in range(args.warmup):
-        cpu_ref_pass(sample, workers)
-    secs, nbytes, errors = [], 0, 0
-    for _ in range(args.steps):
-        s, b, e = cpu_ref_pass(sample, workers)
-        secs.append(s)
-        nbytes += b
-        errors += e
-    value = nbytes / sum(secs) / GIB
-    desc = f"{n_sample} of {args.files} files x {N_CHUNKS} blocks of {BLOCK} B per step, source {source}"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic",
-        "config": {"workload": "C2: lsio_bench README workload, 500 files x 41,214,400 B, 157 blocks of 262,144 B per file, into host buffers (CPU lsio_uring port)",
-                   "source": source, "dir": directory, "files": args.files, "worker_threads": workers, "sqpoll": True, "errors": errors,
-                   "note": "the reference is Rust and cannot be built here; this is oracle/lsio_uring_ref.c, its C restatement"},
-        "cpu_baseline": {"value": value, "unit": "GiB/s", "cores": workers * 2, "kind": "port", "sample": desc},
-        "e2e": {"value": value, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
-    return 0
+    if torch.cuda.device_count() < 2:
+        return {"skipped": "fewer than 2 visible devices"}
+    sub = paths[:n_files]
+    ids = list(range(n_files))
+    with L.IoUringCuda(4, devices=(0, 1), arena_bytes=4 << 30, staging_bytes=256 << 20) as u:
+        s, b, ok, bad = u.bench_read_files(sub, ids, BLOCK, N_CHUNKS, expect)
+        st = u.stats()
+    return {"devices": [0, 1], "files": n_files, "chunks_ok": ok, "bad_chunks": bad + (n_files * N_CHUNKS - ok - bad), "gib_s": b / s / GIB, "requests": st["requests"]}
 
 
 # ---- main ---------------------------------------------------------------------------------------------
@@ -648,12 +770,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dir", default=None, help="directory for the synthetic files (default: /dev/shm if it has room)")
     ap.add_argument("--files", type=int, default=N_FILES)
-    ap.add_argument("--workers", type=int, default=0, help="io_uring worker threads per GPU (0 = 8, the README config, capped by the CPUs available per rank)")
+    ap.add_argument("--workers", type=int, default=0, help="io worker threads per GPU (0 = as many as this rank's CPU share allows, at most 14)")
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--staging-mib", type=int, default=1024)
     ap.add_argument("--arena-gib", type=int, default=8)
     ap.add_argument("--min-copy-mib", type=int, default=64)
-    ap.add_argument("--pack-threads", type=int, default=0, help="threads per CTA of the pipeline's pack launches (0 = 1024)")
+    ap.add_argument("--pack-threads", type=int, default=0, help="threads per CTA of the pipeline's roofline-variant pack launches (0 = 1024)")
+    ap.add_argument("--pack-light-below-mib", type=int, default=512)
     ap.add_argument("--flush-us", type=int, default=2000, help="a pack batch is launched once it holds --min-copy-mib or its oldest extent has waited this long")
     ap.add_argument("--sq-entries", type=int, default=64)
     ap.add_argument("--max-read-kib", type=int, default=512, help="reads (merged or split) are cut at this size")
@@ -661,8 +784,13 @@ def main():
     ap.add_argument("--poll-sleep-us", type=int, default=50, help="device-thread poll interval in microseconds (0 = spin)")
     ap.add_argument("--staging-mode", type=int, default=1, help="1 = per-worker cache-sized pinned slots (default), 0 = one big pinned ring")
     ap.add_argument("--host-slots", type=int, default=4, help="staging mode 1: pinned slots per worker")
-    ap.add_argument("--host-slot-kib", type=int, default=2048, help="staging mode 1: slot (extent, H2D copy) size")
-    ap.add_argument("--e2e-dir", default=None, help="--e2e-only: run the pass over files in this directory instead")
+    ap.add_argument("--host-slot-kib", type=int, default=1024, help="staging mode 1: slot (extent, H2D copy) size")
+    ap.add_argument("--inline-reads", type=int, default=1)
+    ap.add_argument("--direct-landing", type=int, default=2, help="0 = ring + pack kernel, 1 = copy engine straight into the arena, 2 = pull kernel")
+    ap.add_argument("--steal-batch", type=int, default=8)
+    ap.add_argument("--completion-bound", type=int, default=0)
+    ap.add_argument("--copy-coalesce-slots", type=int, default=2)
+    ap.add_argument("--pin", type=int, default=1, help="N > 1: pin every rank's backend threads to its own slice of the CPUs")
     ap.add_argument("--zero-copy", type=int, default=0, help="1 = the pack kernel reads the pinned ring over PCIe (no H2D memcpy)")
     ap.add_argument("--statx-via-ring", type=int, default=0, help="1 = the reference's openat+statx SQE pair per file")
     ap.add_argument("--disk-dir", default="/tmp/lsio_bench_disk", help="secondary e2e leg on a disk-backed directory ('' disables)")
@@ -670,12 +798,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-codec", action="store_true", help="skip the informative codec-layer leg (N=1 only)")
-    ap.add_argument("--value-only", action="store_true", help="only the device-resident kernel pass (for ncu captures)")
-    ap.add_argument("--e2e-only", action="store_true", help="only the end-to-end pass (pipeline tuning sweeps)")
-    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"], help="C2 is the contract line; the others print an informational line")
+    ap.add_argument("--no-extra", action="store_true", help="only the contract legs (value, e2e, roofline, ceilings)")
+    ap.add_argument("--kernel-only", "--value-only", dest="kernel_only", action="store_true", help="only the device-resident kernel pass (for ncu captures)")
+    ap.add_argument("--kernel-in-place", action="store_true", help="--kernel-only: the crc-only in-place form")
+    ap.add_argument("--e2e-only", action="store_true", help="only the native end-to-end passes (pipeline tuning sweeps, ncu captures of pipeline launches)")
+    ap.add_argument("--null-source", type=int, default=0, help="--e2e-only: workers skip the reads (device stage alone)")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"], help="C2 is the contract line; the others print only that leg")
     ap.add_argument("--c3-files", type=int, default=10_000)
-    ap.add_argument("--c5-files", type=int, default=40)
-    ap.add_argument("--c5-loops", type=int, default=5)
+    ap.add_argument("--c5-files", type=int, default=16)
+    ap.add_argument("--c5-total-gb", type=float, default=1000.0, help="C5: bytes landed per step over all ranks (looped over the file set)")
+    ap.add_argument("--c5", type=int, default=-1, help="run the C5 leg: -1 = only at 8 GPUs, 0 = never, 1 = always")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -688,29 +820,32 @@ def main():
     from lsio_b200 import cuda_ops, sharding
 
     rank, world, local = dist_env()
-    cpus_per_rank = (os.cpu_count() or 8) // max(world, 1)
-    if args.workers <= 0:  # leave cores for the consumer and the (mostly sleeping) device thread
-        args.workers = max(2, min(8, cpus_per_rank - 2))
+    n_gpus = max(world, 1)
+    args.cpu_first, args.cpu_count, cpus_per_rank = cpu_slice(rank, n_gpus)
+    if args.workers <= 0:
+        # reads of memory-backed files run ON the worker (inline preadv2): one worker per CPU of this rank's share;
+        # alone on the box a couple of CPUs stay free for the consumer and the device thread
+        args.workers = max(2, min(12, cpus_per_rank - 4)) if n_gpus == 1 else max(2, min(12, cpus_per_rank))
+    if args.completion_bound <= 0:
+        args.completion_bound = 1 << 16
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist_init("nccl")
-    n_gpus = max(world, 1)
-
-    if args.config != "C2":
-        return run_config(args, dev, rank)
 
     need = args.files * FILE_SIZE
     directory, source = pick_data_dir(args, need)
     t_gen = time.time()
     if rank == 0:
-        paths, expect_crc = make_files(directory, args.files, local)
+        paths = write_files_cpu(directory, "lsio_bench", args.files, FILE_SIZE)
+        expect = oracle_crc_table(directory, "c2", paths, BLOCK, N_CHUNKS)
     barrier()
     if rank != 0:
-        paths, expect_crc = make_files(directory, args.files, local)  # already there: only loads the table
+        paths = write_files_cpu(directory, "lsio_bench", args.files, FILE_SIZE)  # already there
+        expect = oracle_crc_table(directory, "c2", paths, BLOCK, N_CHUNKS)        # cached by rank 0
     t_gen = time.time() - t_gen
     # weak scaling: n_gpus * files logical files dealt file_idx mod n_gpus; logical file j is
-    # physical file j % files (the file set is shared read-only to bound storage; O_DIRECT, no cache reuse)
+    # physical file j % files (the file set is shared read-only to bound storage; nothing is cached between passes)
     mine = sharding.files_for_rank(args.files * n_gpus, rank, n_gpus)
     my_paths = [paths[j % args.files] for j in mine]
     my_ids = [j % args.files for j in mine]
@@ -722,123 +857,137 @@ def main():
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
-    if args.value_only:
-        val = run_value(args, dev, args.files, expect_crc)
-        kernel_ms = statistics.mean(val["step_ms"])
-        print(json.dumps({"value_only": True, "files": args.files, "kernel_ms": kernel_ms, "achieved_gbs": val["algo_bytes"] / kernel_ms / 1e6,
-                          "frac": val["algo_bytes"] / kernel_ms / 1e6 / hbm_peak, "crc_ok": val["crc_ok"], "mismatched_bytes": val["mismatched_bytes"]}), flush=True)
+    if args.kernel_only:
+        k = run_kernel(args, dev, args.files, expect, in_place=args.kernel_in_place)
+        ms = statistics.mean(k["step_ms"])
+        print(json.dumps({"kernel_only": True, "in_place": args.kernel_in_place, "files": args.files, "kernel_ms": ms, "achieved_gbs": k["algo_bytes"] / ms / 1e6,
+                          "frac": k["algo_bytes"] / ms / 1e6 / hbm_peak, "crc_equals_oracle_table": k["crc_ok"]}), flush=True)
         return 0
 
     if args.e2e_only:
-        if args.e2e_dir:
-            my_paths, expect_crc = make_files(args.e2e_dir, args.files, local)
-            my_ids = list(range(args.files))
-        e2e = run_e2e(args, dev, my_paths, my_ids, expect_crc, args.steps, args.warmup, args.workers)
-        print(json.dumps({"e2e_only": True, "gib_s": e2e["bytes"] / sum(e2e["secs"]) / GIB, "bad": e2e["bad"], "workers": args.workers,
-                          "staging_mib": args.staging_mib, "min_copy_mib": args.min_copy_mib, "sq_entries": args.sq_entries,
-                          "stalls": [e2e["stats"]["staging_stalls"], e2e["stats"]["arena_stalls"]], "copies": e2e["stats"]["h2d_copies"]}), flush=True)
+        with backend(args, dev, null_source=args.null_source) as u:
+            leg = timed_leg(u, lambda: native_pass(u, my_paths, my_ids, None if args.null_source else expect), args.steps, args.warmup, dev)
+        s = leg_summary(leg, dev, args.workers, n_gpus)
+        if rank == 0:
+            print(json.dumps({"e2e_only": True, "null_source": args.null_source, "n_gpus": n_gpus, "workers": args.workers, "pin": [args.cpu_first, args.cpu_count],
+                              "pipeline_kernel": pipeline_kernel(leg["stats"], hbm_peak), **s}), flush=True)
         return 0
 
+    if args.config != "C2":
+        return run_config_only(args, dev, rank, n_gpus, directory, source, paths, hbm_peak)
+
+    # ---- the contract legs -------------------------------------------------------------------------------
     with ClockSampler(local) as clocks:
-        val = run_value(args, dev, args.files, expect_crc)
-        e2e = run_e2e(args, dev, my_paths, my_ids, expect_crc, args.steps, args.warmup, args.workers)
+        with backend(args, dev) as u:
+            val = timed_leg(u, lambda: native_pass(u, my_paths, my_ids, expect), args.steps, args.warmup, dev)
+        with backend(args, dev) as u:
+            e2e = timed_leg(u, lambda: python_pass(u, my_paths, my_ids, expect, dev), max(2, min(args.steps, 10)), 1, dev)
+        kern = run_kernel(args, dev, args.files, expect)
+        kern_ip = run_kernel(args, dev, args.files, expect, in_place=True)
     clk = clocks.summary()
+    v = leg_summary(val, dev, args.workers, n_gpus)
+    e = leg_summary(e2e, dev, args.workers, n_gpus)
 
-    # ceilings of the I/O roofline, measured in the same run (rank 0's view) while every other rank is idle
-    ceil = {}
+    # the device stage alone: workers skip the read (verdict r1 #2b) -- separates "the box cannot feed N GPUs" from "the pipeline cannot"
+    with backend(args, dev, null_source=1) as u:
+        nul = timed_leg(u, lambda: native_pass(u, my_paths, my_ids, None), 2, 1, dev)
+    nl = leg_summary(nul, dev, args.workers, n_gpus)
+
+    # ceilings of the I/O roofline: PCIe with all ranks copying at once; the source with every other rank idle
     barrier()
+    pcie_each = gather_floats(pcie_h2d_gib_s(dev), dev)
+    barrier()
+    ceil = {"pcie_h2d_gib_s_all_ranks_at_once": sum(pcie_each), "pcie_h2d_gib_s_per_gpu": [round(x, 2) for x in pcie_each]}
     if rank == 0:
-        ceil["pcie_h2d_gib_s"] = pcie_h2d_ceiling(dev)
-        nthr = min(os.cpu_count() or 8, max(8, args.workers) * n_gpus)
-        # raw READ_FIXED reads, no GPU work: into a large buffer (DRAM-bound destination) and into small per-thread
-        # buffers (cache-resident destination, what staging_mode 1 does); the ceiling is the better of the two
-        ceil["source_read_big_buffers_gib_s"] = cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 1 << 20, nthr, 32, True)
-        ceil["source_read_gib_s"] = max(ceil["source_read_big_buffers_gib_s"], cuda_ops.probe_read_ceiling(paths[: min(len(paths), 200)], 512 << 10, nthr, 4, True))
+        ceil["pcie_h2d_gib_s_one_gpu_alone"] = pcie_h2d_gib_s(dev)
+        ncpu = len(os.sched_getaffinity(0))
+        ceil["source_read_gib_s"], ceil["source_read_shapes"] = source_ceiling(paths[: min(len(paths), 250)], [args.workers * n_gpus, ncpu], True)
     barrier()
-    full = None
-    if not args.no_verify:
-        mism, landed = verify_full_landing(dev, my_paths, my_ids, args.workers, args.staging_mib)
-        full = {"landed_bytes": landed, "mismatched_bytes": mism}
 
-    # secondary leg: the same workload from a disk-backed directory (this box: one virtio disk)
-    disk = None
-    if rank == 0 and n_gpus == 1 and args.disk_dir and args.disk_files > 0 and source != "disk":
-        try:
-            free = shutil.disk_usage(os.path.dirname(args.disk_dir.rstrip("/")) or "/").free
-            if free > args.disk_files * FILE_SIZE + (4 << 30):
-                dpaths, dcrc = make_files(args.disk_dir, args.disk_files, local)
-                dres = run_e2e(args, dev, dpaths, list(range(args.disk_files)), dcrc, 2, 1, args.workers)
-                dceil = max(cuda_ops.probe_read_ceiling(dpaths, 1 << 20, 8, 32, True), cuda_ops.probe_read_ceiling(dpaths, 256 << 10, 8, 32, True))
-                disk = {"value": dres["bytes"] / sum(dres["secs"]) / GIB, "unit": "GiB/s", "files": args.disk_files, "bad": dres["bad"],
-                        "read_ceiling_gib_s": dceil, "frac_of_ceiling": dres["bytes"] / sum(dres["secs"]) / GIB / dceil, "dir": args.disk_dir}
-        except Exception as ex:  # the disk leg is informative only
-            disk = {"error": repr(ex)}
+    parity = {"expected_crc_source": "oracle", "expected_crc_is": "oracle.crc32c_file_blocks over files written by oracle.write_file (oracle/lsio_oracle.c); every chunk of every timed pass is compared with it",
+              "chunks_checked_timed_legs": (args.steps * len(my_paths) * N_CHUNKS + e["steps"] * len(my_paths) * N_CHUNKS) * 1,
+              "bad_chunks_all_ranks": v["bad_chunks"] + e["bad_chunks"],
+              "kernel_pass_crc_equals_oracle_table": kern["crc_ok"] and kern_ip["crc_ok"]}
+    if not args.no_verify:
+        parity["landed_bytes_vs_file_bytes"] = verify_landed_bytes(args, dev, my_paths, my_ids, 10)
+        mm, _ = reduce_sum_max(parity["landed_bytes_vs_file_bytes"]["mismatched_bytes"], 0.0, dev)
+        parity["landed_bytes_vs_file_bytes"]["mismatched_bytes_all_ranks"] = mm
+
+    extra = {}
+    if not args.no_extra:
+        if n_gpus > 1:
+            extra["c4"] = c4_leg(args, dev, rank, n_gpus, directory, paths)
+        if args.c5 == 1 or (args.c5 < 0 and n_gpus == 8):
+            extra["c5"] = c5_leg(args, dev, rank, n_gpus, directory)
+        if n_gpus > 1:
+            barrier()
+            if rank == 0:
+                try:
+                    extra["two_devices_one_process"] = two_device_check(args, 40, paths, expect)
+                except Exception as ex:
+                    extra["two_devices_one_process"] = {"error": repr(ex)}
+            barrier()
+        if n_gpus == 1:
+            try:
+                extra["c3"] = c3_leg(args, dev, rank, n_gpus, directory)
+            except Exception as ex:
+                extra["c3"] = {"error": repr(ex)}
+            if args.disk_dir and args.disk_files > 0 and source != "disk":
+                try:
+                    extra["e2e_disk"] = disk_leg(args, dev)
+                except Exception as ex:  # informative only
+                    extra["e2e_disk"] = {"error": repr(ex)}
+            if not args.no_codec:
+                try:
+                    extra["codec"] = codec_leg(hbm_peak)
+                except Exception as ex:  # informative only: never costs the contract line
+                    extra["codec"] = {"error": repr(ex)}
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        workers = 8  # the README configuration (8 worker threads + 8 SQPOLL kernel threads)
-        s, b, errs = cpu_ref_pass(paths, workers)
-        cpu = {"value": b / s / GIB, "unit": "GiB/s", "cores": min(cores, workers * 2), "kind": "port",
-               "sample": f"one pass over all {len(paths)} files ({b} B) from {source}, 8 worker threads + SQPOLL, into fresh host buffers; {errs} errors",
-               "nproc": cores}
-        # the figure as lsio_bench itself prints it: filesize x n_files / elapsed, i.e. counting the 57,792-byte tail of
-        # every file that it never reads (crates/lsio_bench/src/main.rs:137, :181-183): +0.14 %
-        cpu["reference_style_gib_s"] = FILE_SIZE * len(paths) / s / GIB
-        try:  # also at one worker per core, without SQPOLL (workers + kernel pollers would oversubscribe the box)
-            s3, b3, _ = cpu_ref_pass(paths, cores, sqpoll=False)
-            cpu["nproc_workers_no_sqpoll_gib_s"] = b3 / s3 / GIB
-        except Exception as ex:
-            cpu["nproc_workers_no_sqpoll_gib_s"] = repr(ex)
-        s2, b2, _ = cpu_ref_pass(paths, workers, mode=1)
-        cpu["object_store_like_gib_s"] = b2 / s2 / GIB
-
-    codec = None
-    if rank == 0 and n_gpus == 1 and not args.no_codec:
-        try:
-            codec = codec_leg(hbm_peak)
-        except Exception as ex:  # informative only: never costs the contract line
-            codec = {"error": repr(ex)}
-
-    # aggregate over ranks: sum of bytes, max of time
-    v_bytes, v_secs = reduce_bytes_and_time(val["payload"] * args.steps, val["total_ms"] * 1e-3, dev)
-    e_bytes, e_secs = reduce_bytes_and_time(e2e["bytes"], e2e["total_secs"], dev)
-    bad_total, _ = reduce_bytes_and_time(e2e["bad"] + (0 if val["crc_ok"] else 1) + val["mismatched_bytes"], 0.0, dev)
+        cpu = cpu_baseline_block(paths, source, os.cpu_count() or 1)
 
     if rank == 0:
-        kernel_ms = statistics.mean(val["step_ms"])
-        achieved = val["algo_bytes"] / (kernel_ms * 1e-3) / 1e9
-        e2e_gib = e_bytes / e_secs / GIB
-        io_ceiling = min(ceil["source_read_gib_s"], ceil["pcie_h2d_gib_s"] * n_gpus)
-        padded_per_step = len(my_paths) * N_CHUNKS * BLOCK  # aligned workload: padded == payload
+        kernel_ms = statistics.mean(kern["step_ms"])
+        achieved = kern["algo_bytes"] / (kernel_ms * 1e-3) / 1e9
+        ip_ms = statistics.mean(kern_ip["step_ms"])
+        pcie = ceil["pcie_h2d_gib_s_all_ranks_at_once"]
+        io_ceiling = min(ceil["source_read_gib_s"], pcie)
+        per_step = len(my_paths) * N_CHUNKS * BLOCK
+        io_roofline = {"bound": "source" if ceil["source_read_gib_s"] < pcie else "pcie", "achieved": v["gib_s"], "peak": io_ceiling, "unit": "GiB/s",
+                       "frac": v["gib_s"] / io_ceiling, "null_source_gib_s": nl["gib_s"], "null_source_frac_of_pcie": nl["gib_s"] / pcie,
+                       "null_source_is": "same pipeline, workers skip the read itself (slots keep stale bytes): the device stage alone", **ceil}
         line = {
-            "metric": METRIC, "value": v_bytes / v_secs / GIB, "unit": "GiB/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * v_secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "metric": METRIC, "value": v["gib_s"], "unit": "GiB/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": v["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {
-                "workload": "C2: lsio_bench README workload, 500 files x 41,214,400 B, 157 blocks of 262,144 B per file (78,500 ranges, 20,578,304,000 B) delivered into HBM of 1 B200, bit-exact",
-                "files": args.files, "ranges_per_step_per_gpu": len(my_paths) * N_CHUNKS, "source": source, "dir": directory,
-                "value_is": "device-resident pass: padded-read images already in HBM; one pack_strip_crc32c launch (+fold) per step over all ranges",
-                "e2e_is": "files -> O_DIRECT READ_FIXED -> pinned ring -> H2D -> pack+crc32c -> one chunk per range through the C ABI, CRC of every chunk checked",
-                "l2": "inputs larger than L2 (41 GB touched per step vs 126 MB)", "worker_threads_per_gpu": args.workers,
+                "workload": "C2: lsio_bench README workload, 500 files x 41,214,400 B, 157 blocks of 262,144 B per file (78,500 ranges, 20,578,304,000 B) per GPU, delivered into B200 HBM, bit-exact",
+                "files": args.files, "ranges_per_step_per_gpu": len(my_paths) * N_CHUNKS, "bytes_per_step_per_gpu": per_step, "source": source, "dir": directory,
+                "value_is": "files -> reads into pinned slots -> H2D -> checksum/pack kernel -> one chunk per range through the C ABI (native lsio_bench driver), fused CRC-32C of every chunk == oracle table; sum of bytes over ranks / max time over ranks",
+                "e2e_is": "the same through the Python mirror of the reference API (get_ranges + recv_batch), CRCs compared in numpy",
+                "l2": "inputs larger than L2 (20.6 GB land per step vs 126 MB)", "worker_threads_per_gpu": args.workers,
+                "cpu_pinning": {"cpu_first": args.cpu_first, "cpu_count": args.cpu_count} if args.pin and args.cpu_count else None, "nproc": os.cpu_count(),
                 "multi_gpu": "files dealt file_idx mod n_gpus, no collective on the data path; each rank lands 500 files (shared read-only file set)",
-                "file_generation_s": round(t_gen, 1),
+                "file_generation_s": round(t_gen, 1), "files_written_by": "oracle.write_file",
             },
-            "e2e": {"value": e2e_gib, "unit": "GiB/s", "h2d_bytes_per_step": padded_per_step, "d2h_bytes_per_step": 4 * len(my_paths) * N_CHUNKS,
-                    "ms_per_step": 1e3 * e_secs / args.steps, "bad_chunks": e2e["bad"],
-                    "io_roofline": {"bound": "source" if ceil["source_read_gib_s"] < ceil["pcie_h2d_gib_s"] * n_gpus else "pcie", "achieved": e2e_gib,
-                                    "peak": io_ceiling, "unit": "GiB/s", "frac": e2e_gib / io_ceiling, **ceil},
-                    "pipeline": {k: e2e["stats"][k] for k in ("reads", "short_reads", "h2d_copies", "h2d_bytes", "pack_launches", "kernel_launches", "staging_stalls", "arena_stalls")}},
-            "gpu_launches": val["launches"],
+            "e2e": {"value": e["gib_s"], "unit": "GiB/s", "h2d_bytes_per_step": per_step, "d2h_bytes_per_step": 4 * len(my_paths) * N_CHUNKS,
+                    "ms_per_step": e["ms_per_step"], "steps": e["steps"], "bad_chunks": e["bad_chunks"], "per_rank_gib_s": e["per_rank_gib_s"], "io_roofline": io_roofline},
+            "gpu_launches": val["stats"]["kernel_launches"],
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "pack_kernel<store,crc32c> + fold_kernel, per step", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": val["algo_bytes"]},
+                         "peak_source": peak_src, "kernel": "pack_kernel<store,crc32c> + fold_kernel, device-resident: one launch over all 78,500 ranges per step", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": kern["algo_bytes"],
+                         "in_place_crc_only": {"kernel": "pack_kernel<crc32c only> (the form run on directly landed extents)", "kernel_ms": ip_ms, "algorithmic_bytes_per_launch": kern_ip["algo_bytes"],
+                                               "achieved": kern_ip["algo_bytes"] / ip_ms / 1e6, "frac": kern_ip["algo_bytes"] / ip_ms / 1e6 / hbm_peak},
+                         "pipeline_kernel": pipeline_kernel(val["stats"], hbm_peak)},
             "cpu_baseline": cpu,
-            "parity": {"value_pass_crc_equal_expected": val["crc_ok"], "value_pass_mismatched_bytes": val["mismatched_bytes"],
-                       "e2e_bad_chunks_all_ranks": bad_total, "full_landing": full},
-            "e2e_disk": disk,
-            "codec": codec,
+            "io_roofline": io_roofline,
+            "value_detail": {k: v[k] for k in ("per_rank_gib_s", "bad_chunks", "latency_rank0", "pipeline_rank0", "per_worker_rank0", "read_amplification")}
+                            | {"cuda_event_secs_rank0": val["cuda_event_secs"], "wall_secs_rank0": val["total_secs"]},
+            "null_source": {k: nl[k] for k in ("gib_s", "per_rank_gib_s", "per_worker_rank0")},
+            "parity": parity,
+            **extra,
         }
         traffic_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(traffic_file):
@@ -852,6 +1001,103 @@ def main():
 
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
+    return 0
+
+
+# ---- C3 / C4 / C5 legs (aggregated over ranks like the headline) -------------------------------------------------
+def c3_leg(args, dev, rank, n_gpus, directory):
+    from lsio_b200 import sharding
+
+    d3 = directory + "_c3"
+    if rank == 0:
+        paths, per, size, desc = c3_workload(args, d3)
+        exp = oracle_crc_of_ranges(d3, "c3", paths, per, size)
+    barrier()
+    if rank != 0:
+        paths, per, size, desc = c3_workload(args, d3)
+        exp = oracle_crc_of_ranges(d3, "c3", paths, per, size)
+    base = np.cumsum([0] + [len(p[0]) for p in per])
+    mine = sharding.files_for_rank(len(paths), rank, n_gpus)
+    my_paths = [paths[j] for j in mine]
+    my_per = [per[j] for j in mine]
+    my_exp = np.concatenate([exp[base[j]:base[j + 1]] for j in mine])
+    payload = 0
+    for s, e in my_per:
+        so, eo = resolve(size, s, e)
+        payload += int((eo - so).sum())
+    leg = ranges_leg(args, dev, my_paths, my_per, my_exp, payload, 3, 2)
+    out = leg_summary(leg, dev, args.workers, n_gpus)
+    out.update({"config": desc, "expected_crc_source": "oracle", "ranges_per_step": sum(len(p[0]) for p in my_per)})
+    return out
+
+
+def c4_leg(args, dev, rank, n_gpus, directory, paths):
+    """BASELINE configs[3]: files sharded over the GPUs, 1 MiB ranges (39 per file; the 319,488-byte tail is not read)."""
+    from lsio_b200 import sharding
+
+    k = FILE_SIZE // MIB
+    if rank == 0:
+        exp = oracle_crc_table(directory, "c4", paths, MIB, k)
+    barrier()
+    if rank != 0:
+        exp = oracle_crc_table(directory, "c4", paths, MIB, k)
+    st = np.arange(k, dtype=np.int64) << 20
+    mine = sharding.files_for_rank(len(paths) * n_gpus, rank, n_gpus)
+    my_paths = [paths[j % len(paths)] for j in mine]
+    my_exp = np.concatenate([exp[j % len(paths)] for j in mine])
+    per = [(st, st + MIB)] * len(my_paths)
+    leg = ranges_leg(args, dev, my_paths, per, my_exp, len(my_paths) * k * MIB, 3, 1)
+    out = leg_summary(leg, dev, args.workers, n_gpus)
+    out.update({"config": f"C4: {len(paths)} files x {FILE_SIZE} B per GPU, dealt file_idx mod {n_gpus}, {k} ranges of 1 MiB per file", "expected_crc_source": "oracle"})
+    return out
+
+
+def c5_leg(args, dev, rank, n_gpus, directory):
+    """BASELINE configs[4]: large streaming scan, 4 MiB ranges, fused crc32c checked per chunk; the file set is looped until
+    ~c5_total_gb have landed per step over all ranks."""
+    d5 = directory + "_c5"
+    size = 1 << 30
+    try:
+        st = os.statvfs(os.path.dirname(d5))
+        room = st.f_bavail * st.f_frsize
+    except OSError:
+        room = 0
+    n_files = args.c5_files
+    have = os.path.isdir(d5) and len([f for f in os.listdir(d5) if f.startswith("c5_")]) >= n_files
+    if not have and room < n_files * size + (8 << 30):
+        n_files = max(2, int((room - (8 << 30)) // size))
+    if rank == 0:
+        paths = write_files_cpu(d5, "c5", n_files, size, 200_000)
+        exp = oracle_crc_table(d5, "c5", paths, 4 * MIB, size // (4 * MIB))
+    barrier()
+    if rank != 0:
+        paths = write_files_cpu(d5, "c5", n_files, size, 200_000)
+        exp = oracle_crc_table(d5, "c5", paths, 4 * MIB, size // (4 * MIB))
+    st4 = np.arange(size >> 22, dtype=np.int64) << 22
+    per = [(st4, st4 + 4 * MIB)] * n_files
+    # rank r starts its loop at a different file so that the ranks do not walk the shared set in lockstep
+    order = [(i + rank * max(1, n_files // n_gpus)) % n_files for i in range(n_files)]
+    my_paths = [paths[i] for i in order]
+    my_exp = np.concatenate([exp[i] for i in order])
+    loops = max(1, int(round(args.c5_total_gb * 1e9 / n_gpus / (n_files * size))))
+    leg = ranges_leg(args, dev, my_paths, per, my_exp, n_files * size, 1, 1, loops=loops, arena_bytes=max(args.arena_gib, 12) << 30)
+    out = leg_summary(leg, dev, args.workers, n_gpus)
+    out.update({"config": f"C5: {n_files} files x 1 GiB (shared read-only set), 256 ranges of 4 MiB per file, {loops} loops per rank per step, {n_gpus} ranks",
+                "loops_per_rank": loops, "bytes_landed_all_ranks": out["bytes"], "expected_crc_source": "oracle", "fused_crc32c_checked_per_chunk": True})
+    return out
+
+
+def run_config_only(args, dev, rank, n_gpus, directory, source, paths, hbm_peak):
+    if args.config == "C3":
+        out = c3_leg(args, dev, rank, n_gpus, directory)
+    elif args.config == "C4":
+        out = c4_leg(args, dev, rank, n_gpus, directory, paths)
+    else:
+        out = c5_leg(args, dev, rank, n_gpus, directory)
+    if rank == 0:
+        out.update({"n_gpus": n_gpus, "source": source, "workers_per_gpu": args.workers})
+        print(json.dumps(out), flush=True)
+    barrier()
     return 0
 
 

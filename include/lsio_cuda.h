@@ -61,6 +61,16 @@ void lsio_cuda_pack_plan_destroy(lsio_cuda_pack_plan* plan);
 int lsio_cuda_pack_strip_crc32c(int device, const lsio_cuda_segment* segs, size_t n, uint32_t flags,
                                 uint32_t* crc_out_dev, void* stream);
 
+/* The PULL form of pack_strip_crc32c (pack_crc.cu pull_kernel): `segs[i].src` are HOST addresses inside one
+ * pinned allocation (cudaHostAlloc / cudaHostRegister with the mapped flag): the kernel's warps read them over PCIe
+ * through the mapped alias, checksum what they move and store it at `segs[i].dst` in HBM -- one pass, no copy engine, no
+ * device staging copy.  This is how the backend empties a pinned slot when `direct_landing` = 2.  At most
+ * LSIO_CUDA_PULL_MAX_SEGMENTS segments per call (the descriptors travel as kernel parameters).  `crc_out_dev` may be
+ * NULL (no checksum) or any device-visible address of n words.  Synchronous one-shot (scratch allocated per call); the
+ * backend itself keeps per-slot scratch and launches asynchronously on its workers' streams. */
+#define LSIO_CUDA_PULL_MAX_SEGMENTS 64
+int lsio_cuda_pull_strip_crc32c(int device, const lsio_cuda_segment* segs_host_src, size_t n, uint32_t* crc_out_dev, void* stream);
+
 /* XXH64 (seed 0) of n spans; one 64-bit result per span.  Spans are device addresses. */
 int lsio_cuda_xxh64(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n,
                     uint64_t* out_dev, void* stream);

@@ -70,8 +70,10 @@ typedef struct lsio_uring_cuda_config {
                                    0 = one `staging_bytes` pinned ring mirrored on the device, copied in coalesced
                                    runs by the device thread (needed for zero_copy) */
     uint32_t host_slots_per_worker; /* staging_mode 1: slots per worker (default 4) */
-    uint32_t host_slot_kib;     /* staging_mode 1: slot (extent) size in KiB, >= max_read_bytes (default 2048): the
-                                   granularity of the H2D copies; several reads of max_read_bytes can be in flight in one */
+    uint32_t host_slot_kib;     /* staging_mode 1: slot (extent) size in KiB, >= max_read_bytes (default 1024): the unit that
+                                   leaves the host in one pull launch / H2D copy; several reads of max_read_bytes can be in
+                                   flight in one.  With the pull kernel (direct_landing 2) small slots cost no PCIe bandwidth,
+                                   so the window (slots x slot size) is sized to stay in the worker's L2                  */
     uint32_t pack_threads;      /* threads per CTA of the pipeline's pack launches: 0 = 1024 (one CTA fills an SM: the
                                    configuration the kernel reaches the HBM roofline with); 256 = small footprint for a GPU
                                    shared with the consumer's own kernels (a 1024-thread CTA waits for a whole SM to drain,
@@ -91,17 +93,28 @@ typedef struct lsio_uring_cuda_config {
                                    retry path (get_range.rs:66-68 TODO in the reference) runs; 0 = off                        */
     uint32_t null_source;       /* diagnostic: 1 = workers skip the read itself (slots keep whatever they held; files are still
                                    opened and sized): measures the device stage alone -- bytes delivered are NOT the files'   */
-    uint32_t direct_landing;    /* 1 (default) = an extent whose payload forms at most 4 runs that are contiguous both in the
-                                   slot and in the request buffers is copied by H2D DMA straight into the arena (no device
-                                   staging ring, no pack kernel copy: the kernel only checksums in place, HBM traffic L instead
-                                   of 3L); anything else (small unaligned ranges) goes ring -> pack kernel.  0 = always ring    */
+    uint32_t direct_landing;    /* how an extent leaves its pinned slot.  0 = always H2D copy into the device staging ring, then the
+                                   pack kernel strips / scatters / checksums (HBM traffic 3L).  1 = an extent whose payload forms
+                                   at most 4 runs contiguous both in the slot and in the request buffers is copied by the copy
+                                   engine straight into the arena and checksummed in place (traffic 2L), consecutive slots
+                                   coalesced (copy_coalesce_slots).  2 = an extent of at most 64 segments whose slot addresses are
+                                   congruent to their destinations mod 16 (every 512-aligned block read) is moved by the PULL
+                                   KERNEL: SM loads over PCIe from the mapped slot, CRC fused, stored at the final place -- one
+                                   pass, traffic L, no copy-engine gap per copy, so slots can stay cache-sized.  Extents that do
+                                   not qualify fall back to 1's rule, then to the ring (small unaligned ranges).              */
     uint32_t cpu_first;         /* with cpu_count > 0: this backend's threads (workers + device thread of every group) are     */
     uint32_t cpu_count;         /* pinned to CPUs [cpu_first, cpu_first + cpu_count) instead of the GPU's NUMA node            */
-    uint32_t steal_batch;       /* reads a worker takes from a peer's deque in one steal (default 4 = one extent's worth;
-                                   the reference steals one, worker.rs:58-62)                                                 */
+    uint32_t steal_batch;       /* tasks a worker takes from the BACK of a peer's deque in one steal, kept in order (default 8 =
+                                   two extents' worth of reads: the owner's own sequence keeps no holes and both sides
+                                   fill their slots with consecutive bytes; 1 = the reference's Stealer::steal(), one task
+                                   from the front, worker.rs:58-62)                                                          */
     uint32_t pack_light_below_mib; /* pipeline launches over batches smaller than this use the light kernel variant
                                    (256-thread CTAs, 5 KiB of shared memory, co-resident with a consumer's kernels, fold fused);
                                    larger ones the roofline variant.  default 512; 0 = never light                          */
+    uint32_t copy_coalesce_slots; /* directly landed extents that fill consecutive slots of a worker AND consecutive bytes of one
+                                   request buffer are copied with one cudaMemcpyAsync of up to this many slots (default 2,
+                                   at most 8; 1 = one copy per extent).  The copy engine loses ~3.8 us per copy whatever its
+                                   size (2 MiB copies: 46.9 GiB/s, 4 MiB: 49.2, 8 MiB: 50.4 of 51.6 on this pool's B200s).     */
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {
@@ -121,6 +134,7 @@ typedef struct lsio_uring_cuda_stats {
     uint64_t pack_kernel_bytes; /* algorithmic bytes of those launches (2L for ring segments, L for in-place ones)   */
     uint64_t first_chunk_ns;    /* ns from the first get_ranges after construction / reset to the first chunk sent   */
     uint64_t max_dio_align;     /* largest per-file O_DIRECT alignment seen                                         */
+    uint64_t pull_launches;     /* extents moved by the pull kernel (direct_landing 2), one launch each             */
 } lsio_uring_cuda_stats;
 
 /* Per-chunk latency histogram (submit of the request -> chunk in the channel), log2 buckets of microseconds:

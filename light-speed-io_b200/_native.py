@@ -39,6 +39,10 @@ PACK_STORE = 1
 PACK_CRC32C = 2
 PACK_LIGHT = 4
 
+lib.lsio_cuda_pull_strip_crc32c.restype = ctypes.c_int
+lib.lsio_cuda_pull_strip_crc32c.argtypes = [ctypes.c_int, ctypes.POINTER(CudaSegment), ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+PULL_MAX_SEGMENTS = 64
+
 lib.lsio_cuda_pack_plan_create.restype = ctypes.c_int
 lib.lsio_cuda_pack_plan_create.argtypes = [ctypes.c_int, ctypes.POINTER(CudaSegment), ctypes.c_size_t, ctypes.c_uint32,
                                            ctypes.POINTER(ctypes.c_void_p)]
@@ -144,7 +148,8 @@ class CConfig(ctypes.Structure):
                 ("pack_threads", ctypes.c_uint32),
                 ("inline_reads", ctypes.c_uint32), ("force_align", ctypes.c_uint32), ("debug_short_read_every", ctypes.c_uint32),
                 ("null_source", ctypes.c_uint32), ("direct_landing", ctypes.c_uint32), ("cpu_first", ctypes.c_uint32),
-                ("cpu_count", ctypes.c_uint32), ("steal_batch", ctypes.c_uint32), ("pack_light_below_mib", ctypes.c_uint32)]
+                ("cpu_count", ctypes.c_uint32), ("steal_batch", ctypes.c_uint32), ("pack_light_below_mib", ctypes.c_uint32),
+                ("copy_coalesce_slots", ctypes.c_uint32)]
 
 
 class CStats(ctypes.Structure):
@@ -152,7 +157,7 @@ class CStats(ctypes.Structure):
                                                "pack_launches", "kernel_launches", "payload_bytes", "chunks_ok", "errors",
                                                "staging_stalls", "arena_stalls", "inline_reads", "direct_extents", "direct_copies",
                                                "read_ns", "copy_enqueue_ns", "worker_stall_ns", "worker_busy_ns", "pack_kernel_ns",
-                                               "pack_kernel_bytes", "first_chunk_ns", "max_dio_align")]
+                                               "pack_kernel_bytes", "first_chunk_ns", "max_dio_align", "pull_launches")]
 
 
 for _name, _res, _args in [

@@ -131,7 +131,8 @@ struct Batch {
         uint64_t seq;  // staging extent (holds the request alive until the batch retires)
         uint32_t ref;  // read inside the extent
         uint32_t seg;
-        uint32_t kidx;  // index of its descriptor in the kernel batch (its CRC slot), or UINT32_MAX: landed directly, no checksum wanted
+        uint32_t kidx;  // index of its descriptor in the kernel batch (its CRC slot), or UINT32_MAX: nothing launched for it
+        uint32_t pull_idx;  // index of its CRC in Group::pull_crc_host (moved and checksummed by the pull kernel), or UINT32_MAX
     };
     std::vector<DescRef> desc;  // segment of each descriptor
     std::vector<cudaEvent_t> copy_events;
@@ -155,16 +156,18 @@ struct XxhBatch {
 // staging_mode 1: the private staging window of one io worker.
 struct WorkerSlots {
     uint8_t* base = nullptr;  // host_slots_per_worker slots of slot_bytes, inside Group::slot_block
+    uint8_t* base_dev = nullptr;  // the same memory as the GPU sees it (mapped): the pull kernel reads the slots in place
+    std::vector<void*> scratch;   // per slot: device scratch of the pull kernel (scheduler words, counters, partials)
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> ev;
-    std::vector<uint8_t> busy;  // 0 free, 1 read in flight, 2 H2D copy in flight (touched by the owning worker only)
+    std::vector<uint8_t> busy;  // 0 free, 1 read in flight, 2 H2D copy / pull in flight, 3 filled, copy deferred (touched by the owning worker only)
 };
 
 struct Stats {
     std::atomic<uint64_t> requests{0}, ranges{0}, reads{0}, short_reads{0}, read_bytes{0}, h2d_copies{0}, h2d_bytes{0}, pack_launches{0},
         kernel_launches{0}, payload_bytes{0}, chunks_ok{0}, errors{0}, staging_stalls{0}, arena_stalls{0}, inline_reads{0}, direct_extents{0},
         direct_copies{0}, read_ns{0}, copy_enqueue_ns{0}, worker_stall_ns{0}, worker_busy_ns{0}, pack_kernel_ns{0}, pack_kernel_bytes{0},
-        first_submit_ns{0}, first_chunk_ns{0}, max_dio_align{0}, read_seq{0};
+        first_submit_ns{0}, first_chunk_ns{0}, max_dio_align{0}, read_seq{0}, pull_launches{0};
     std::atomic<uint64_t> latency[32] = {};  // log2(us) buckets: request submitted -> chunk in the channel
 };
 
@@ -181,6 +184,10 @@ struct Group {
     uint8_t* slot_block = nullptr;     // staging_mode 1: all workers' slots, one pinned allocation
     uint64_t slot_bytes = 0;
     std::vector<WorkerSlots> wslots;
+    uint8_t* scratch_block = nullptr;   // all slots' pull scratch, one device allocation
+    uint32_t* pull_crc_host = nullptr;  // pinned + mapped: [n_pull][kPullMaxSegs] CRCs written by the pull kernel, row = extent seq % n_pull
+    uint32_t* pull_crc_dev = nullptr;
+    size_t n_pull = 0;
     StagingLog log;
     cudaStream_t s_copy = nullptr, s_pack = nullptr;
     std::vector<Batch> batches;

@@ -124,7 +124,7 @@ static void retire_batch(Group& g, Batch& b) {
     for (size_t i = 0; i < b.desc.size(); i++) {
         const std::shared_ptr<Request>& rp = g.log.at(b.desc[i].seq).reads[b.desc[i].ref].req;
         SegPlan& sp = rp->segs[b.desc[i].seg];
-        sp.crc = b.desc[i].kidx != UINT32_MAX ? b.crc_host[b.desc[i].kidx] : 0;
+        sp.crc = b.desc[i].kidx != UINT32_MAX ? b.crc_host[b.desc[i].kidx] : (b.desc[i].pull_idx != UINT32_MAX ? g.pull_crc_host[b.desc[i].pull_idx] : 0);
         RangePlan& p = rp->ranges[sp.range];
         if (p.segs_left.fetch_sub(1, std::memory_order_acq_rel) == 1) emit_range(g, rp, sp.range);
     }
@@ -154,19 +154,25 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
     copy_events.clear();
     for (uint64_t s = seq_begin; s < seq_end; s++) {
         StageEntry& e = g.log.at(s);
+        uint32_t pull_j = 0;  // the pull kernel numbered this extent's segments in this same order
         for (uint32_t ri = 0; ri < e.reads.size(); ri++) {
             auto& ref = e.reads[ri];
             if (ref.state != kStageLanded) continue;
             const ReadPlan& rd = ref.req->reads[ref.read];
             for (uint32_t k = 0; k < rd.nsegs; k++) {
                 const SegPlan& sp = ref.req->segs[rd.first_seg + k];
+                if (e.pulled) {  // moved and checksummed already: only its completion is awaited (copy_event below)
+                    b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k, UINT32_MAX, want_crc ? (uint32_t)((e.seq % g.n_pull) * kPullMaxSegs + pull_j) : UINT32_MAX});
+                    pull_j++;
+                    continue;
+                }
                 lsio_cuda_segment seg;
                 seg.dst = (uint64_t)(uintptr_t)(ref.req->buffer->buf + sp.dst_off);
                 // an extent that landed directly is already in place: src == dst tells the kernel to checksum only
                 seg.src = e.direct ? seg.dst : (uint64_t)(uintptr_t)((be->cfg.zero_copy ? g.host_ring_dev : g.dev_ring) + e.log_off % cap + ref.off + sp.head);
                 seg.len = sp.payload_len;
                 if (e.direct && !want_crc) {  // nothing left to do on the device for this segment
-                    b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k, UINT32_MAX});
+                    b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k, UINT32_MAX, UINT32_MAX});
                     continue;
                 }
                 b->algo_bytes += e.direct ? sp.payload_len : 2 * sp.payload_len;
@@ -178,7 +184,7 @@ static int flush_run(Group& g, uint64_t seq_begin, uint64_t seq_end) {
                     p.segs_left.fetch_sub(1, std::memory_order_acq_rel);
                     continue;
                 }
-                b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k, kidx});
+                b->desc.push_back(Batch::DescRef{s, ri, rd.first_seg + k, kidx, UINT32_MAX});
             }
             landed_bytes += rd.read_len;
         }

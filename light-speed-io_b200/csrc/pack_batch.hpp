@@ -35,6 +35,14 @@ bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCo
 // Copies the filled part of a host block (Seg, tile and multi arrays up to the counts) to its device twin.
 int pack_batch_upload(const PackBatchLayout& lay, const void* host_block, void* dev_block, const PackBatchCounts& c, cudaStream_t stream);
 
+// Pull launch (pack_crc.cu pull_kernel): up to kPullMaxSegs segments whose `src` are mapped HOST addresses of one pinned slot are
+// read over PCIe by the kernel itself, checksummed and written at `dst`; descriptors travel in the kernel parameters.
+// `scratch_dev`: pack_pull_scratch_bytes(slot_bytes) of zeroed device memory owned by the slot (re-armed by the kernel);
+// `crc_out_dev`: device-visible address of n words (may be mapped host memory), unused without `crc`.
+constexpr uint32_t kPullMaxSegs = 64;
+size_t pack_pull_scratch_bytes(size_t slot_bytes);
+int pack_pull_launch(int device, const lsio_cuda_segment* segs, uint32_t n, bool crc, void* scratch_dev, uint32_t* crc_out_dev, cudaStream_t stream);
+
 // One-time per-device set-up (GF(2) tables to the device, kernel attributes). 0 or error code.
 int pack_prepare_device(int device);
 // Enqueues the pack kernel (+ fold kernel if any segment spans several tiles). The device must

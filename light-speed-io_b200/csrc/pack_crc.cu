@@ -392,6 +392,80 @@ __device__ __forceinline__ uint32_t fold_segment(const uint32_t* parts, int n, u
 // next to a consumer's kernels; merge tables come from global memory through L1; the warp that finishes a
 // segment's last tile folds the partials itself (one launch per batch); a segment with src == dst (landed
 // directly by DMA) is checksummed in place.
+// The tables a warp needs, wherever the variant keeps them.
+struct TileTables {
+    const char* ltb;       // G: lane-private (roofline variant) or one shared copy (light / pull)
+    const uint32_t* htab;  // six [4][256] merge tables
+    const uint32_t* ftab;  // [16][32] trailing-zero / final operators
+};
+
+// One tile of one segment by one warp: move (unless in place / crc-only), checksum, and finish the segment's CRC if
+// this was its only or -- light variant -- its last tile.  `si`: the segment's index (its CRC slot), `k`: the tile's
+// index counted from the segment's end.
+template <bool kStore, bool kCrc, bool kLight>
+__device__ __forceinline__ void do_tile(const Seg& s, uint32_t si, uint32_t k, int lane, const TileTables& tb, const uint32_t* tables, uint32_t* partials,
+                                        uint32_t* seg_done, uint32_t* crc_out) {
+    const uint64_t dst = kStore ? s.dst : s.src;  // crc-only: checksum in place
+    const bool in_place = kStore && s.src == s.dst;  // landed by DMA: nothing to move
+    if (!kCrc && in_place) return;
+    if (s.len < 4) {  // scalar path (covers empty segments): ntiles == 1 by construction
+        if (lane == 0) {
+            uint8_t b[4];
+            for (int i = 0; i < (int)s.len; i++) b[i] = *(const uint8_t*)(s.src + i);
+            if (kStore && !in_place) for (int i = 0; i < (int)s.len; i++) *(uint8_t*)(s.dst + i) = b[i];
+            if (kCrc) crc_out[si] = crc_bitwise_dev(b, (int)s.len);
+        }
+        return;
+    }
+    Geo g;
+    g.dst = dst; g.len = s.len;
+    g.a0 = dst & ~15ull;
+    const uint64_t a1 = (dst + s.len + 15ull) & ~15ull;
+    g.nvec = (int)((a1 - g.a0) >> 4);
+    g.delta = (int)((s.src - dst) & 15ull);
+    g.sbase = (const uint4*)(g.a0 + (s.src - dst) - (uint64_t)g.delta);
+    g.src_lo = s.src; g.src_hi = s.src + s.len;
+    const int vend = g.nvec - (int)k * kTileVecs;
+    uint32_t part;
+    if (in_place) part = run_tile<-1, false, kCrc, kLight>(g, vend, lane, tb.ltb, tb.htab);
+    else if (g.delta == 0) part = run_tile<-1, kStore, kCrc, kLight>(g, vend, lane, tb.ltb, tb.htab);
+    else switch (g.delta >> 2) {
+        case 0: part = run_tile<0, kStore, kCrc, kLight>(g, vend, lane, tb.ltb, tb.htab); break;
+        case 1: part = run_tile<1, kStore, kCrc, kLight>(g, vend, lane, tb.ltb, tb.htab); break;
+        case 2: part = run_tile<2, kStore, kCrc, kLight>(g, vend, lane, tb.ltb, tb.htab); break;
+        default: part = run_tile<3, kStore, kCrc, kLight>(g, vend, lane, tb.ltb, tb.htab); break;
+    }
+    if (!kCrc) return;
+
+    if (s.ntiles > 1) {
+        if (!kLight) {  // fold_kernel finishes multi-tile segments
+            if (lane == 0) partials[s.tile_base + k] = part;
+            return;
+        }
+        // light: publish the partial; whoever completes the segment folds it.  The fence orders the partial
+        // (and, harmlessly, this warp's data stores) before the count; it costs nothing at pipeline rates.
+        uint32_t before = 0;
+        if (lane == 0) {
+            partials[s.tile_base + k] = part;
+            __threadfence();
+            before = atomicAdd(seg_done + si, 1u);
+        }
+        before = __shfl_sync(0xFFFFFFFFu, before, 0);
+        if (before != s.ntiles - 1) return;
+        __threadfence();
+        const uint32_t crc = fold_segment(partials + s.tile_base, (int)s.ntiles, dst, s.len, tables + kZ32, tables + kZ, tables + kF, lane);
+        if (lane == 0) {
+            crc_out[si] = crc;
+            seg_done[si] = 0;  // re-armed for the next launch of this batch / plan
+        }
+        return;
+    }
+    // undo the z trailing zero bytes of the aligned superset and apply the final x^32
+    const int z = (int)(a1 - (dst + s.len));
+    const uint32_t crc = ~warp_mul(part, tb.ftab + z * 32, lane);
+    if (lane == 0) crc_out[si] = crc;
+}
+
 template <bool kStore, bool kCrc, bool kLight>
 __global__ void __launch_bounds__(kLight ? 256 : kThreads, kLight ? 3 : 1) pack_kernel(const Params p) {
     extern __shared__ __align__(16) uint32_t sh[];
@@ -406,9 +480,7 @@ __global__ void __launch_bounds__(kLight ? 256 : kThreads, kLight ? 3 : 1) pack_
         }
         __syncthreads();
     }
-    const char* ltb = kLight ? (const char*)sh : (const char*)(sh + kSmG) + lane * 4;
-    const uint32_t* htab = kLight ? p.tables + kH : sh + kSmH;
-    const uint32_t* ftab = kLight ? p.tables + kF : sh + kSmF;
+    const TileTables tb{kLight ? (const char*)sh : (const char*)(sh + kSmG) + lane * 4, kLight ? p.tables + kH : sh + kSmH, kLight ? p.tables + kF : sh + kSmF};
 
     // Dynamic tile scheduler: every warp takes the NEXT tile from a global counter, like the hardware
     // block scheduler would.  Measured on a plain copy (tools/copy_pattern_bench.cu): static striding lets
@@ -421,65 +493,7 @@ __global__ void __launch_bounds__(kLight ? 256 : kThreads, kLight ? 3 : 1) pack_
         if (t >= p.ntiles) break;
         const uint2 te = __ldg(p.tiles + t);
         const Seg s = *(p.segs + te.x);  // 32 B, warp-uniform broadcast
-        const uint64_t dst = kStore ? s.dst : s.src;  // crc-only: checksum in place
-        const bool in_place = kStore && s.src == s.dst;  // landed by DMA: nothing to move
-        if (!kCrc && in_place) continue;
-        if (s.len < 4) {  // scalar path (covers empty segments): ntiles == 1 by construction
-            if (lane == 0) {
-                uint8_t b[4];
-                for (int i = 0; i < (int)s.len; i++) b[i] = *(const uint8_t*)(s.src + i);
-                if (kStore && !in_place) for (int i = 0; i < (int)s.len; i++) *(uint8_t*)(s.dst + i) = b[i];
-                if (kCrc) p.crc_out[te.x] = crc_bitwise_dev(b, (int)s.len);
-            }
-            continue;
-        }
-        Geo g;
-        g.dst = dst; g.len = s.len;
-        g.a0 = dst & ~15ull;
-        const uint64_t a1 = (dst + s.len + 15ull) & ~15ull;
-        g.nvec = (int)((a1 - g.a0) >> 4);
-        g.delta = (int)((s.src - dst) & 15ull);
-        g.sbase = (const uint4*)(g.a0 + (s.src - dst) - (uint64_t)g.delta);
-        g.src_lo = s.src; g.src_hi = s.src + s.len;
-        const int vend = g.nvec - (int)te.y * kTileVecs;
-        uint32_t part;
-        if (in_place) part = run_tile<-1, false, kCrc, kLight>(g, vend, lane, ltb, htab);
-        else if (g.delta == 0) part = run_tile<-1, kStore, kCrc, kLight>(g, vend, lane, ltb, htab);
-        else switch (g.delta >> 2) {
-            case 0: part = run_tile<0, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
-            case 1: part = run_tile<1, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
-            case 2: part = run_tile<2, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
-            default: part = run_tile<3, kStore, kCrc, kLight>(g, vend, lane, ltb, htab); break;
-        }
-        if (!kCrc) continue;
-
-        if (s.ntiles > 1) {
-            if (!kLight) {  // fold_kernel finishes multi-tile segments
-                if (lane == 0) p.partials[s.tile_base + te.y] = part;
-                continue;
-            }
-            // light: publish the partial; whoever completes the segment folds it.  The fence orders the partial
-            // (and, harmlessly, this warp's data stores) before the count; it costs nothing at pipeline rates.
-            uint32_t before = 0;
-            if (lane == 0) {
-                p.partials[s.tile_base + te.y] = part;
-                __threadfence();
-                before = atomicAdd(p.seg_done + te.x, 1u);
-            }
-            before = __shfl_sync(0xFFFFFFFFu, before, 0);
-            if (before != s.ntiles - 1) continue;
-            __threadfence();
-            const uint32_t crc = fold_segment(p.partials + s.tile_base, (int)s.ntiles, dst, s.len, p.tables + kZ32, p.tables + kZ, p.tables + kF, lane);
-            if (lane == 0) {
-                p.crc_out[te.x] = crc;
-                p.seg_done[te.x] = 0;  // re-armed for the next launch of this batch / plan
-            }
-            continue;
-        }
-        // undo the z trailing zero bytes of the aligned superset and apply the final x^32
-        const int z = (int)(a1 - (dst + s.len));
-        const uint32_t crc = ~warp_mul(part, ftab + z * 32, lane);
-        if (lane == 0) p.crc_out[te.x] = crc;
+        do_tile<kStore, kCrc, kLight>(s, te.x, te.y, lane, tb, p.tables, p.partials, p.seg_done, p.crc_out);
     }
     // the last warp to run dry re-arms the scheduler for the next launch of this batch / plan
     if (lane == 0) {
@@ -487,6 +501,50 @@ __global__ void __launch_bounds__(kLight ? 256 : kThreads, kLight ? 3 : 1) pack_
         if (done == gridDim.x * (blockDim.x >> 5) - 1) {
             p.sched[0] = 0;
             p.sched[1] = 0;
+        }
+    }
+}
+
+// ---- pull kernel: one extent straight from its pinned host slot into the request buffers ----------------------------
+// The segments' `src` are MAPPED HOST addresses: the warps read the slot over PCIe themselves (no copy engine, no device
+// staging ring, no second pass), checksum what they move and write it at its final place: PCIe traffic L, HBM traffic L.
+// Why a kernel and not cudaMemcpyAsync: the copy engine loses ~3.8 us per copy whatever its size, so cache-sized slots
+// cost bandwidth (512 KiB copies 36.5 GiB/s, 2 MiB 46.9 of 51.6); SM loads reach 47-47.8 GiB/s from 512 KiB up
+// (tools/h2d_probe.cu), which lets the slots shrink until the worker's whole window stays in its cache.
+// The descriptors travel in the kernel parameters (no upload); partials / counters are per-slot device scratch.
+struct PullParams {
+    Seg segs[kPullMaxSegs];
+    uint32_t nsegs, ntiles;
+    uint32_t* scratch;  // [0] next tile, [1] warps finished, [2..2+kPullMaxSegs) tiles done per segment, then partials
+    uint32_t* crc_out;  // one per segment (mapped host memory)
+    const uint32_t* tables;
+};
+template <bool kCrc>
+__global__ void __launch_bounds__(256, 3) pull_kernel(const __grid_constant__ PullParams p) {
+    __shared__ __align__(16) uint32_t sh[1024];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (kCrc) {
+        for (int i = tid; i < 1024; i += blockDim.x) sh[i] = __ldg(p.tables + kG + i);
+        __syncthreads();
+    }
+    const TileTables tb{(const char*)sh, p.tables + kH, p.tables + kF};
+    uint32_t* const seg_done = p.scratch + 2;
+    uint32_t* const partials = p.scratch + 2 + kPullMaxSegs;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(p.scratch, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= p.ntiles) break;
+        uint32_t si = 0;
+        while (si + 1 < p.nsegs && t >= p.segs[si + 1].tile_base) si++;  // warp-uniform scan of at most kPullMaxSegs entries
+        const Seg s = p.segs[si];
+        do_tile<true, kCrc, true>(s, si, s.ntiles - 1 - (t - s.tile_base), lane, tb, p.tables, partials, seg_done, p.crc_out);
+    }
+    if (lane == 0) {
+        const uint32_t done = atomicAdd(p.scratch + 1, 1u);
+        if (done == gridDim.x * (blockDim.x >> 5) - 1) {
+            p.scratch[0] = 0;
+            p.scratch[1] = 0;
         }
     }
 }
@@ -583,6 +641,34 @@ bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCo
     c->nsegs++;
     c->payload += seg.len;
     return true;
+}
+
+size_t pack_pull_scratch_bytes(size_t slot_bytes) { return (2 + kPullMaxSegs + slot_bytes / kTileBytes + 2 * kPullMaxSegs) * sizeof(uint32_t); }
+
+int pack_pull_launch(int device, const lsio_cuda_segment* segs, uint32_t n, bool crc, void* scratch_dev, uint32_t* crc_out_dev, cudaStream_t st) {
+    if (!segs || n == 0 || n > kPullMaxSegs || !scratch_dev) return -EINVAL;
+    const uint32_t* tables;
+    int sms;
+    int rc = get_device_tables(device, &tables, &sms);
+    if (rc) return rc;
+    PullParams p;
+    uint32_t ntiles = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t nt = (uint32_t)pack_tile_count(segs[i].dst, segs[i].len);
+        p.segs[i] = Seg{segs[i].src, segs[i].dst, segs[i].len, ntiles, nt};
+        ntiles += nt;
+    }
+    p.nsegs = n;
+    p.ntiles = ntiles;
+    p.scratch = (uint32_t*)scratch_dev;
+    p.crc_out = crc_out_dev;
+    p.tables = tables;
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)sms * 3, (ntiles + 7) / 8);
+    if (crc) pull_kernel<true><<<grid, 256, 0, st>>>(p);
+    else pull_kernel<false><<<grid, 256, 0, st>>>(p);
+    launch_counter().fetch_add(1, std::memory_order_relaxed);
+    LSIO_CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 int pack_batch_upload(const PackBatchLayout& lay, const void* host_block, void* dev_block, const PackBatchCounts& c, cudaStream_t st) {
@@ -719,6 +805,32 @@ int lsio_cuda_pack_strip_crc32c(int device, const lsio_cuda_segment* segs, size_
     }
     lsio_cuda_pack_plan_destroy(plan);
     return rc;
+}
+
+int lsio_cuda_pull_strip_crc32c(int device, const lsio_cuda_segment* segs, size_t n, uint32_t* crc_out_dev, void* stream) {
+    using namespace lsio;
+    static_assert(LSIO_CUDA_PULL_MAX_SEGMENTS == kPullMaxSegs, "header and kernel disagree");
+    if (!segs || n == 0 || n > kPullMaxSegs) return -EINVAL;
+    DeviceGuard dg(device);
+    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+    lsio_cuda_segment dev_view[kPullMaxSegs];
+    uint64_t bytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        void* alias = nullptr;
+        LSIO_CUDA_TRY(cudaHostGetDevicePointer(&alias, (void*)(uintptr_t)segs[i].src, 0));  // fails for memory that is not pinned + mapped
+        dev_view[i] = lsio_cuda_segment{(uint64_t)(uintptr_t)alias, segs[i].dst, segs[i].len};
+        bytes += segs[i].len;
+    }
+    void* scratch = nullptr;
+    const size_t sb = pack_pull_scratch_bytes(bytes + 64 * 32768);
+    LSIO_CUDA_TRY(cudaMalloc(&scratch, sb));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = (int)cudaMemsetAsync(scratch, 0, sb, st);
+    if (!rc) rc = pack_pull_launch(device, dev_view, (uint32_t)n, crc_out_dev != nullptr, scratch, crc_out_dev, st);
+    const cudaError_t se = cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (rc) return rc;
+    return se == cudaSuccess ? 0 : cuda_fail(se, "pull_kernel", __FILE__, __LINE__);
 }
 
 uint64_t lsio_cuda_launch_count(void) { return lsio::launch_counter().load(std::memory_order_relaxed); }

@@ -46,6 +46,8 @@ struct StageEntryT {
     uint32_t used = 0;           // staging_mode 1: bytes of the extent actually filled (= copied)
     uint32_t nsegs = 0, ntiles = 0;  // pack descriptors / kernel tiles its landed reads need (set before `state` is published)
     bool direct = false;         // its payload was copied straight into the request buffers (the kernel checksums in place)
+    bool pulled = false;         // ... by the pull kernel, which also checksummed it: CRC of its j-th segment in Group::pull_crc_host
+    uint64_t seq = 0;            // its sequence number in the log
 };
 
 template <class R>
@@ -78,6 +80,8 @@ class StagingLogT {
         e.used = 0;
         e.nsegs = e.ntiles = 0;
         e.direct = false;
+        e.pulled = false;
+        e.seq = alloc_seq_;
         e.copy_event = nullptr;
         alloc_off_ = off + len;
         alloc_seq_pub_.store(++alloc_seq_, std::memory_order_release);

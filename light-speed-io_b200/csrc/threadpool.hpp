@@ -62,14 +62,15 @@ class WorkerThread {
                 if (auto t = pop(victim)) return t;
                 continue;
             }
-            // take up to steal_batch CONSECUTIVE tasks (reads that fill one extent stay together)
+            // take the LAST steal_batch tasks, in their order: the owner keeps walking its queue from the front without
+            // holes (consecutive reads of a request fill consecutive extents of one worker, which is what lets their
+            // copies be coalesced), the thief gets a run of consecutive reads of its own
             std::vector<T> got;
             {
                 std::lock_guard<std::mutex> lk(victim.mu);
-                while (!victim.q.empty() && got.size() < s_->steal_batch) {
-                    got.push_back(std::move(victim.q.front()));
-                    victim.q.pop_front();
-                }
+                const size_t take = std::min<size_t>(victim.q.size(), s_->steal_batch);
+                for (size_t i = victim.q.size() - take; i < victim.q.size(); i++) got.push_back(std::move(victim.q[i]));
+                victim.q.erase(victim.q.end() - (std::ptrdiff_t)take, victim.q.end());
             }
             if (got.empty()) continue;
             if (got.size() > 1) {

@@ -1,6 +1,7 @@
 // worker.cpp -- one io worker: private io_uring, tracker of in-flight ops, the GetRanges / Read / Close state
 // machines and the staging of landed reads (crates/lsio_uring/src/worker.rs:24-135, get_ranges.rs, get_range.rs,
 // close.rs, sqe.rs builders, open_file.rs).
+#include <sys/prctl.h>
 #include <sys/uio.h>
 
 #include <unordered_map>
@@ -30,6 +31,7 @@ struct Worker {
         if (grp.be->cfg.staging_mode == 1) {
             slots = &grp.wslots[w.id()];
             extents.resize(slots->busy.size());
+            slot_ev.assign(slots->busy.size(), 0);
         }
     }
 
@@ -52,6 +54,120 @@ struct Worker {
     };
     std::vector<Extent> extents;  // one per slot
     int cur = -1;                 // slot of the extent being filled, or -1
+
+    // Direct single-run extents that fill consecutive slots and consecutive bytes of one request buffer are copied with
+    // ONE cudaMemcpyAsync (copy_coalesce_slots): the copy engine loses ~3.8 us per copy whatever its size (measured,
+    // tools/h2d_probe.cu: 2 MiB copies 46.9 GiB/s, 4 MiB 49.2, 8 MiB 50.4, 64 MiB 51.6), the slots stay cache-sized.
+    struct PendingCopy {
+        int first_slot = -1, last_slot = -1, n = 0;
+        uint32_t src = 0;  // offset of the run in the first slot
+        uint8_t* dst = nullptr;
+        uint64_t len = 0;
+        StageEntry* ents[8] = {};
+        int slot_of[8] = {};
+    } pend;
+    std::vector<int> slot_ev;  // event that frees each slot (a coalesced copy records one event for all of its slots)
+    int next_slot = 0;
+
+    void fail_extent(StageEntry* ent, cudaError_t ce) {
+        for (auto& r : ent->reads) {
+            if (r.state != kStageLanded) continue;
+            r.state = kStageFailed;
+            const ReadPlan& rd = r.req->reads[r.read];
+            for (uint32_t k = 0; k < rd.nsegs; k++) {
+                const uint32_t range = r.req->segs[rd.first_seg + k].range;
+                if (!r.req->ranges[range].failed.exchange(true)) send_error(g.be, (int)ce, 0, *r.req, (int)range, "cudaMemcpyAsync (H2D) failed");
+            }
+        }
+        ent->nsegs = ent->ntiles = 0;
+    }
+    void publish(StageEntry* ent) {
+        ent->landed_ns = now_ns();
+        ent->state.store(kStageLanded, std::memory_order_release);
+    }
+
+    // Issue the deferred copy (if any) and publish its extents.  Called whenever the worker is about to wait for
+    // anything (a free slot, a completion, new work) -- a deferred slot is never held across a wait.
+    void flush_pending() {
+        if (pend.n == 0) return;
+        Backend* be = g.be;
+        const uint64_t t0 = now_ns();
+        cudaError_t ce = cudaMemcpyAsync(pend.dst, slots->base + (uint64_t)pend.first_slot * g.slot_bytes + pend.src, pend.len, cudaMemcpyHostToDevice, slots->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(slots->ev[pend.last_slot], slots->stream);
+        c_copy_ns += now_ns() - t0;
+        if (ce != cudaSuccess) cudaGetLastError();
+        for (int i = 0; i < pend.n; i++) {
+            StageEntry* ent = pend.ents[i];
+            const int slot = pend.slot_of[i];
+            if (ce != cudaSuccess) {
+                fail_extent(ent, ce);
+                slots->busy[slot] = 0;
+            } else {
+                slots->busy[slot] = 2;
+                slot_ev[slot] = pend.last_slot;
+                ent->copy_event = slots->ev[pend.last_slot];
+                ent->owner = (uint32_t)wt.id();
+                ent->direct = true;
+                be->stats.direct_extents++;
+            }
+            publish(ent);
+        }
+        if (ce == cudaSuccess) {
+            be->stats.direct_copies++;
+            be->stats.h2d_copies++;
+            be->stats.h2d_bytes += pend.len;
+        }
+        pend = PendingCopy{};
+    }
+
+    // direct_landing 2: the extent is moved by the pull kernel, launched here on this worker's stream: its warps read the
+    // pinned slot over PCIe through the mapped address, checksum the bytes and write them at their final place in the
+    // request buffers -- one pass, no copy engine, no device staging ring (pack_crc.cu pull_kernel).  Needs every segment's
+    // slot address congruent to its destination mod 16 (a vector is loaded once; otherwise each would cross PCIe twice)
+    // and at most kPullMaxSegs segments (the descriptors travel as kernel parameters); anything else takes the other paths.
+    bool try_pull(int slot, StageEntry* ent, uint32_t nsegs) {
+        Backend* be = g.be;
+        lsio_cuda_segment segs[kPullMaxSegs];
+        uint32_t n = 0;
+        uint64_t payload = 0;
+        uint8_t* sdev = slots->base_dev + (uint64_t)slot * g.slot_bytes;
+        for (auto& r : ent->reads) {
+            if (r.state != kStageLanded) continue;
+            const ReadPlan& rd = r.req->reads[r.read];
+            for (uint32_t k = 0; k < rd.nsegs; k++) {
+                const SegPlan& sp = r.req->segs[rd.first_seg + k];
+                lsio_cuda_segment& sg = segs[n++];
+                sg.src = (uint64_t)(uintptr_t)(sdev + r.off + sp.head);
+                sg.dst = (uint64_t)(uintptr_t)(r.req->buffer->buf + sp.dst_off);
+                sg.len = sp.payload_len;
+                if ((sg.src - sg.dst) & 15) return false;
+                payload += sp.payload_len;
+            }
+        }
+        flush_pending();
+        const bool want_crc = be->cfg.checksum & LSIO_CHECKSUM_CRC32C;
+        const uint64_t t0 = now_ns();
+        int rc = pack_pull_launch(g.device, segs, n, want_crc, slots->scratch[slot], g.pull_crc_dev + (ent->seq % g.n_pull) * kPullMaxSegs, slots->stream);
+        cudaError_t ce = rc ? cudaErrorLaunchFailure : cudaEventRecord(slots->ev[slot], slots->stream);
+        c_copy_ns += now_ns() - t0;
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            fail_extent(ent, ce);
+            slots->busy[slot] = 0;
+        } else {
+            slots->busy[slot] = 2;
+            slot_ev[slot] = slot;
+            ent->copy_event = slots->ev[slot];
+            ent->owner = (uint32_t)wt.id();
+            ent->direct = ent->pulled = true;
+            be->stats.direct_extents++;
+            be->stats.pull_launches++;
+            be->stats.kernel_launches++;
+            be->stats.h2d_bytes += payload;
+        }
+        publish(ent);
+        return true;
+    }
 
     // The extent's reads have all landed (or failed) and nothing more will be added: copy it to the device
     // while it is still in this core's cache, then publish it to the device thread.  Two ways:
@@ -94,6 +210,35 @@ struct Worker {
         direct = direct && nruns > 0 && (nruns == 1 || payload >= (uint64_t)nruns * (128u << 10));
         ent->nsegs = nsegs;
         ent->ntiles = ntiles;
+        x.entry = nullptr;
+        if (nsegs && cfg.direct_landing == 2 && nsegs <= kPullMaxSegs && try_pull(slot, ent, nsegs)) return;
+        const uint32_t coalesce = std::min<uint32_t>(cfg.copy_coalesce_slots, 8);
+        if (nsegs && direct && nruns == 1 && coalesce > 1) {
+            const bool to_slot_end = runs[0].src + runs[0].len == g.slot_bytes;
+            if (pend.n && slot == pend.last_slot + 1 && runs[0].src == 0 && runs[0].dst == pend.dst + pend.len) {
+                pend.ents[pend.n] = ent;
+                pend.slot_of[pend.n++] = slot;
+                pend.last_slot = slot;
+                pend.len += runs[0].len;
+                slots->busy[slot] = 3;
+                if (!to_slot_end || pend.n == (int)coalesce || slot + 1 == (int)slots->busy.size()) flush_pending();
+                return;
+            }
+            flush_pending();
+            if (to_slot_end && slot + 1 < (int)slots->busy.size()) {  // may be continued by the next slot
+                pend.first_slot = pend.last_slot = slot;
+                pend.n = 1;
+                pend.src = runs[0].src;
+                pend.dst = runs[0].dst;
+                pend.len = runs[0].len;
+                pend.ents[0] = ent;
+                pend.slot_of[0] = slot;
+                slots->busy[slot] = 3;
+                return;
+            }
+        } else {
+            flush_pending();
+        }
         if (nsegs) {
             const uint64_t t0 = now_ns();
             uint8_t* sbase = slots->base + (uint64_t)slot * g.slot_bytes;
@@ -108,19 +253,11 @@ struct Worker {
             c_copy_ns += now_ns() - t0;
             if (ce != cudaSuccess) {
                 cudaGetLastError();
-                for (auto& r : ent->reads) {
-                    if (r.state != kStageLanded) continue;
-                    r.state = kStageFailed;
-                    const ReadPlan& rd = r.req->reads[r.read];
-                    for (uint32_t k = 0; k < rd.nsegs; k++) {
-                        const uint32_t range = r.req->segs[rd.first_seg + k].range;
-                        if (!r.req->ranges[range].failed.exchange(true)) send_error(be, (int)ce, 0, *r.req, (int)range, "cudaMemcpyAsync (H2D) failed");
-                    }
-                }
-                ent->nsegs = ent->ntiles = 0;
+                fail_extent(ent, ce);
                 slots->busy[slot] = 0;
             } else {
                 slots->busy[slot] = 2;
+                slot_ev[slot] = slot;
                 ent->copy_event = slots->ev[slot];
                 ent->owner = (uint32_t)wt.id();
                 ent->direct = direct;
@@ -137,9 +274,7 @@ struct Worker {
         } else {
             slots->busy[slot] = 0;
         }
-        x.entry = nullptr;
-        ent->landed_ns = now_ns();
-        ent->state.store(kStageLanded, std::memory_order_release);
+        publish(ent);
     }
     void close_current_extent() {
         if (cur < 0) return;
@@ -151,10 +286,17 @@ struct Worker {
 
     // staging_mode 1: a free slot of this worker, recycling slots whose H2D copy has finished; -1 if none
     int acquire_slot() {
-        for (size_t i = 0; i < slots->busy.size(); i++)
-            if (slots->busy[i] == 2 && cudaEventQuery(slots->ev[i]) != cudaErrorNotReady) slots->busy[i] = 0;
-        for (size_t i = 0; i < slots->busy.size(); i++)
-            if (slots->busy[i] == 0) return (int)i;
+        const int n = (int)slots->busy.size();
+        for (int i = 0; i < n; i++)
+            if (slots->busy[i] == 2 && cudaEventQuery(slots->ev[slot_ev[i]]) != cudaErrorNotReady) slots->busy[i] = 0;
+        // consecutive extents go to consecutive slots, so that their copies can be coalesced
+        for (int k = 0; k < n; k++) {
+            const int i = (next_slot + k) % n;
+            if (slots->busy[i] == 0) {
+                next_slot = (i + 1) % n;
+                return i;
+            }
+        }
         return -1;
     }
 
@@ -333,11 +475,14 @@ struct Worker {
                 if (cur < 0) {
                     const int free_slot = acquire_slot();
                     if (free_slot < 0) {  // all of this worker's slots are still being read or copied
+                        flush_pending();  // a deferred copy holds slots: it must be under way before this worker waits for one
                         be->stats.staging_stalls++;
                         return Start::Retry;
                     }
                     StageEntry* fresh = g.log.alloc((uint32_t)g.slot_bytes);
                     if (!fresh) {
+                        flush_pending();
+                        next_slot = free_slot;
                         be->stats.staging_stalls++;
                         return Start::Retry;
                     }
@@ -509,13 +654,17 @@ struct Worker {
         }
         const bool ring_ok = rc == 0;
         const unsigned sq = ring_ok ? ring.sq_entries() : 0;
+        prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // short sleeps stay short (default slack: 50 us on top of every sleep)
         uint64_t t_awake = now_ns();
         while (true) {
             const bool running = wt.keep_running();
             if (!running) {
                 // shutting down: the partly filled extent must still be published (the device thread waits for every
                 // extent that was reserved in the log) -- with inline reads it can be open while the tracker is empty
-                if (slots) close_current_extent();
+                if (slots) {
+                    close_current_extent();
+                    flush_pending();
+                }
                 if (tracker.is_empty()) break;
             }
             unsigned started = 0, inline_done = 0;
@@ -576,6 +725,7 @@ struct Worker {
             }
             if (ring_ok && ring.unsubmitted()) ring.submit();
             if (got || started || inline_done) continue;
+            if (slots) flush_pending();  // about to wait (for work, a completion, a slot, HBM): nothing stays deferred
             if (tracker.is_empty() && stalled_reads.empty() && stalled_plans.empty()) {
                 if (running) {
                     c_busy_ns += now_ns() - t_awake;
@@ -589,7 +739,7 @@ struct Worker {
                 ring.submit(1, 200);  // submit_and_wait(1), bounded so new tasks are noticed
             } else {  // only waiting for staging / HBM space
                 const uint64_t t0 = now_ns();
-                std::this_thread::sleep_for(std::chrono::microseconds(50));
+                std::this_thread::sleep_for(std::chrono::microseconds(20));  // precise: the thread's timer slack is 1 us (run())
                 c_stall_ns += now_ns() - t0;
             }
         }

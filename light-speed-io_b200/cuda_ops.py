@@ -87,6 +87,20 @@ def pack_strip_crc32c(src, dst, src_off, dst_off, lens, store=True, crc32c=True,
     return out[: len(lens)]
 
 
+def pull_strip_crc32c(src_pinned, dst, src_off, dst_off, lens, crc32c=True, stream=None):
+    """The pull form (lsio_cuda_pull_strip_crc32c): `src_pinned` is a pinned HOST uint8 tensor, read over PCIe by the
+    kernel itself; dst a CUDA tensor.  At most 64 segments.  Returns the per-segment CRC-32C (uint32 CUDA tensor) or None."""
+    import torch
+
+    assert src_pinned.is_pinned() and not src_pinned.is_cuda
+    s = np.asarray(src_off, dtype=np.uint64) + np.uint64(src_pinned.data_ptr())
+    d = np.asarray(dst_off, dtype=np.uint64) + np.uint64(dst.data_ptr())
+    segs, n = _segments(s, d, lens)
+    out = torch.empty(max(n, 1), dtype=torch.int32, device=dst.device) if crc32c else None
+    N.check(N.lib.lsio_cuda_pull_strip_crc32c(dst.device.index, segs, n, out.data_ptr() if crc32c else None, _stream_ptr(stream)), "pull_strip_crc32c")
+    return out
+
+
 def xxh64(buf, offs, lens, stream=None):
     import torch
 

@@ -828,6 +828,57 @@ def test_dio_alignment_from_statx(lsio, oracle, cuda_dev, data_dir):
         os.close(fd)
 
 
+@pytest.mark.parametrize("checksum", [0, 1, 3])
+@pytest.mark.parametrize("slot_kib,coalesce", [(512, 1), (2048, 4)])
+def test_pull_and_coalesced_landing_of_block_reads(lsio, oracle, cuda_dev, data_dir, checksum, slot_kib, coalesce):
+    """Whole files read as aligned blocks (C2 / C4 / C5 shape) with small and large slots: pull kernel (direct_landing 2) and
+    coalesced copy-engine landing (direct_landing 1, several slots per cudaMemcpyAsync) deliver the oracle's bytes, CRC-32C
+    and XXH64; many workers so that reads are stolen mid-file."""
+    fns = []
+    for i in range(6):
+        fn = os.path.join(data_dir, f"blk{i}")
+        oracle.write_file(fn, 900 + i, 9 * MIB + 256 * KIB)
+        fns.append(fn)
+    per = [[(k * 256 * KIB, (k + 1) * 256 * KIB) for k in range(37)] for _ in fns]
+    for landing in (2, 1):
+        with lsio.IoUringCuda(5, arena_bytes=256 << 20, staging_bytes=64 << 20, direct_landing=landing, host_slot_kib=slot_kib, host_slots_per_worker=8,
+                              copy_coalesce_slots=coalesce, checksum=checksum) as u:
+            for rep in range(2):  # slots, scratch and CRC rows are reused
+                for i, (fn, rs) in enumerate(zip(fns, per)):
+                    u.get_ranges(fn, rs, [(i << 32) | k for k in range(len(rs))])
+                items = _drain(u.completion(), sum(len(r) for r in per), 30.0)
+                for c in items:
+                    assert c.is_ok(), c
+                    want = oracle.pread_range(fns[c.user_data >> 32], *per[c.user_data >> 32][c.user_data & 0xFFFFFFFF])
+                    assert np.array_equal(c.buffer.as_slice(), want)
+                    if checksum & 1:
+                        assert c.crc32c == oracle.crc32c(want)
+                    if checksum & 2:
+                        assert c.xxh64 == oracle.xxh64(want)
+                del items
+            st = u.stats()
+            assert st["errors"] == 0
+            if landing == 2:
+                assert st["pull_launches"] > 0 and st["h2d_copies"] == 0
+            else:
+                assert st["direct_extents"] > 0 and st["pull_launches"] == 0
+
+
+def test_consecutive_slots_are_copied_with_one_call(lsio, oracle, cuda_dev, data_dir):
+    """direct_landing 1: one worker walking one file fills consecutive slots with consecutive bytes of the request buffer;
+    copy_coalesce_slots of them leave with ONE cudaMemcpyAsync (the copy engine loses a fixed ~3.8 us per copy)."""
+    fn = os.path.join(data_dir, "seq")
+    oracle.write_file(fn, 950, 16 * MIB)
+    rs = [(k * 256 * KIB, (k + 1) * 256 * KIB) for k in range(64)]
+    for coalesce, want_copies in ((1, 16), (4, 4)):
+        with lsio.IoUringCuda(1, arena_bytes=64 << 20, staging_bytes=64 << 20, direct_landing=1, host_slot_kib=1024, host_slots_per_worker=8,
+                              copy_coalesce_slots=coalesce) as u:
+            u.get_ranges(fn, rs, range(len(rs)))
+            _check_chunks(oracle, _drain(u.completion(), len(rs)), lambda ud: fn, lambda ud: rs[ud])
+            st = u.stats()
+            assert st["direct_extents"] == 16 and st["direct_copies"] == want_copies, st
+
+
 @pytest.mark.parametrize("inline_reads,staging_mode", [(0, 1), (2, 1), (0, 0), (2, 0)])
 def test_short_reads_are_retried(lsio, oracle, cuda_dev, data_dir, inline_reads, staging_mode):
     """The reference leaves short reads as a TODO (get_range.rs:66-68) and would deliver stale bytes.  Every third read is
@@ -852,7 +903,7 @@ def test_inline_reads_for_files_the_kernel_cannot_read_asynchronously(lsio, orac
         assert st["inline_reads"] == st["reads"] > 0
 
 
-@pytest.mark.parametrize("direct_landing,light_mib", [(1, 512), (0, 512), (1, 0), (0, 0)])
+@pytest.mark.parametrize("direct_landing,light_mib", [(1, 512), (0, 512), (1, 0), (0, 0), (2, 512)])
 def test_direct_landing_and_light_kernel_same_bytes(lsio, oracle, cuda_dev, data_dir, direct_landing, light_mib):
     """Aligned block reads (the README workload's shape) and whole-shard contiguous ranges land by DMA straight in the
     request buffer and are checksummed in place; scattered small ranges go ring -> pack kernel.  Both paths, with the
@@ -868,9 +919,12 @@ def test_direct_landing_and_light_kernel_same_bytes(lsio, oracle, cuda_dev, data
     fns = [fn, fn] + fns2
     per = [blocks, shard] + per2
     st = _land_and_check(lsio, oracle, fns, per, direct_landing=direct_landing, pack_light_below_mib=light_mib)
-    if direct_landing:
-        assert st["direct_extents"] > 0 and st["direct_copies"] >= st["direct_extents"]
+    if direct_landing == 1:
+        assert st["direct_extents"] > 0 and st["direct_copies"] > 0 and st["pull_launches"] == 0
         assert st["h2d_bytes"] < st["read_bytes"] + 4096  # direct runs carry payload only, never more than was read
+    elif direct_landing == 2:
+        assert st["pull_launches"] > 0  # the aligned blocks were moved by the pull kernel; the unaligned shard and the C3 ranges took the other paths
+        assert st["direct_extents"] >= st["pull_launches"]
     else:
         assert st["direct_extents"] == 0
     assert st["pack_kernel_ns"] > 0 and st["pack_kernel_bytes"] > 0

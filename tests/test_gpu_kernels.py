@@ -210,3 +210,37 @@ def test_aligned_bytes_pinned_and_device_views(lsio, cuda_dev):
     assert t.is_cuda and t.numel() == 512 and t.data_ptr() == a2.as_ptr() + 512
     t.fill_(9)
     assert a2.clone().set_slice(512, 1024).as_slice().tolist() == [9] * 512
+
+
+def test_pull_kernel_reads_pinned_host_memory_bit_exact(lsio, oracle, cuda_dev):
+    """The pull form (direct_landing = 2): the source is a pinned HOST buffer that the kernel's warps read over PCIe, the
+    destination is HBM.  Same bytes and CRCs as the oracle's pack for empty / tiny / single-tile / multi-tile segments at
+    every relative shift mod 16 (the backend only pulls shift 0, the kernel itself takes any), and nothing outside the
+    destination ranges is touched."""
+    rng = np.random.default_rng(77)
+    for case in range(6):
+        n = [1, 5, 16, 33, 64, 64][case]
+        lens = rng.choice([0, 1, 3, 4, 15, 16, 17, 511, 512, 4096, 32768, 32769, 70000, 262144, 300001], size=n).astype(np.uint64)
+        if case == 4:
+            lens[:] = 262144  # the README workload's extent: aligned 256 KiB blocks
+        so, do, spos, dpos = [], [], 64, 64
+        for i, ln in enumerate(lens):
+            shift = 0 if case == 4 else int(rng.integers(0, 16))
+            spos = (spos + 15) // 16 * 16 + int(rng.integers(0, 16))
+            dpos = (dpos + 15) // 16 * 16 + (spos + shift) % 16
+            so.append(spos); do.append(dpos)
+            spos += int(ln) + int(rng.integers(0, 600)); dpos += int(ln) + int(rng.integers(0, 40))
+        so, do = np.array(so, dtype=np.uint64), np.array(do, dtype=np.uint64)
+        ssz, dsz = (spos + 4096) // 16 * 16, (dpos + 4096) // 16 * 16
+        src = rng.integers(0, 256, ssz, dtype=np.uint8)
+        want_dst, want_crc, _ = oracle.pack(src, so, do, lens, dsz)
+        hsrc = torch.from_numpy(src).pin_memory()
+        tdst = torch.zeros(dsz, dtype=torch.uint8, device=cuda_dev)
+        crc = lsio.cuda_ops.pull_strip_crc32c(hsrc, tdst, so, do, lens)
+        assert np.array_equal(tdst.cpu().numpy(), want_dst), case
+        assert np.array_equal(crc[:n].cpu().numpy().view(np.uint32), want_crc), case
+        tdst2 = torch.zeros(dsz, dtype=torch.uint8, device=cuda_dev)
+        assert lsio.cuda_ops.pull_strip_crc32c(hsrc, tdst2, so, do, lens, crc32c=False) is None
+        assert np.array_equal(tdst2.cpu().numpy(), want_dst), case
+    with pytest.raises(Exception):  # more segments than travel in the kernel parameters
+        lsio.cuda_ops.pull_strip_crc32c(hsrc, tdst, np.zeros(65, dtype=np.uint64), np.zeros(65, dtype=np.uint64), np.ones(65, dtype=np.uint64))

@@ -24,8 +24,10 @@ def _worker(rank, world, port, q):
         mine = sharding.files_for_rank(11, rank, world)
         # pretend each file carries (idx + 1) MiB and this rank took (rank + 1) seconds
         nbytes = sum((i + 1) << 20 for i in mine)
-        total_bytes, max_secs = bench.reduce_bytes_and_time(nbytes, float(rank + 1), device=torch.device("cpu"))
-        q.put((rank, mine, total_bytes, max_secs))
+        total_bytes, max_secs = bench.reduce_sum_max(nbytes, float(rank + 1), device=torch.device("cpu"))
+        rates = bench.gather_floats(10.0 * (rank + 1), torch.device("cpu"))
+        first, count, per = bench.cpu_slice(rank, world)
+        q.put((rank, mine, total_bytes, max_secs, rates, (first, count, per)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -45,5 +47,11 @@ def test_two_ranks_shard_and_aggregate():
     files = sorted(res[0][1] + res[1][1])
     assert files == list(range(11))                          # disjoint and complete
     want_bytes = sum((i + 1) << 20 for i in range(11))
-    for _, _, total_bytes, max_secs in res:
+    for _, _, total_bytes, max_secs, rates, _ in res:
         assert total_bytes == want_bytes and max_secs == 2.0  # sum of units, max of time
+        assert rates == [10.0, 20.0]                          # per-rank rates, in rank order, on every rank
+    # every rank pins its backend threads to its own slice of the CPUs: disjoint, equal share
+    (f0, c0, per0), (f1, c1, per1) = res[0][5], res[1][5]
+    assert per0 == per1 == len(os.sched_getaffinity(0)) // 2
+    if c0 and c1:
+        assert c0 == c1 == per0 and set(range(f0, f0 + c0)).isdisjoint(range(f1, f1 + c1))
