@@ -235,6 +235,19 @@ def evict_page_cache(paths):
             pass
 
 
+def llc_bytes():
+    best = 0
+    for idx in (3, 4, 2):
+        try:
+            v = open(f"/sys/devices/system/cpu/cpu0/cache/index{idx}/size").read().strip()
+            n = int(v[:-1]) << (10 if v[-1] == "K" else 20) if v[-1] in "KM" else int(v)
+            if idx >= 3 or not best:
+                best = max(best, n)
+        except (OSError, ValueError):
+            pass
+    return best or (32 << 20)
+
+
 # ---- backend construction ----------------------------------------------------------------------------
 def cpu_slice(rank, world):
     """Disjoint CPU slice of this rank (one process per GPU on a shared box), or (0, 0) when alone / not contiguous."""
@@ -256,20 +269,20 @@ def backend(args, dev, workers=None, **over):
               merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us, staging_mode=args.staging_mode,
               host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib, statx_via_ring=args.statx_via_ring,
               inline_reads=args.inline_reads, direct_landing=args.direct_landing, steal_batch=args.steal_batch,
-              pack_light_below_mib=args.pack_light_below_mib, completion_bound=args.completion_bound, copy_coalesce_slots=args.copy_coalesce_slots)
+              pack_light_below_mib=args.pack_light_below_mib, completion_bound=args.completion_bound, copy_coalesce_slots=args.copy_coalesce_slots, window_budget_kib=args.window_budget_kib)
     if args.pin and args.cpu_count:
         kw.update(cpu_first=args.cpu_first, cpu_count=args.cpu_count)
     kw.update(over)
     return L.IoUringCuda(workers or args.workers, **kw)
 
 
-PIPE_KEYS = ("requests", "reads", "read_bytes", "short_reads", "inline_reads", "h2d_copies", "h2d_bytes", "direct_extents", "pack_launches", "kernel_launches",
+PIPE_KEYS = ("pull_launches", "requests", "reads", "read_bytes", "short_reads", "inline_reads", "h2d_copies", "h2d_bytes", "direct_extents", "pack_launches", "kernel_launches",
              "staging_stalls", "arena_stalls", "read_ns", "copy_enqueue_ns", "worker_stall_ns", "worker_busy_ns", "pack_kernel_ns", "pack_kernel_bytes",
              "max_dio_align", "payload_bytes")
 
 
 def stats_delta(a, b):
-    return {k: b[k] - a[k] for k in PIPE_KEYS if k != "max_dio_align"} | {"max_dio_align": b["max_dio_align"]}
+    return {k: b[k] - a[k] for k in PIPE_KEYS if k != "max_dio_align"} | {k: b[k] for k in ("max_dio_align", "slot_bytes", "slots_per_worker")}
 
 
 def per_worker(st, workers, secs):
@@ -507,7 +520,7 @@ def leg_summary(leg, dev, workers, n_gpus):
     return {"gib_s": b / t / GIB, "bytes": b, "secs": t, "steps": len(leg["secs"]), "ms_per_step": 1e3 * t / len(leg["secs"]), "bad_chunks": bad,
             "per_rank_gib_s": [round(x, 2) for x in per_rank], "latency_rank0": leg["latency"],
             "pipeline_rank0": {k: st[k] for k in ("reads", "read_bytes", "short_reads", "inline_reads", "h2d_copies", "h2d_bytes", "direct_extents",
-                                                  "pack_launches", "kernel_launches", "staging_stalls", "arena_stalls", "max_dio_align")},
+                                                  "pull_launches", "pack_launches", "kernel_launches", "staging_stalls", "arena_stalls", "max_dio_align", "slot_bytes", "slots_per_worker")},
             "read_amplification": st["read_bytes"] / max(1, st["payload_bytes"]),
             "per_worker_rank0": per_worker(st, workers, leg["total_secs"])}
 
@@ -783,13 +796,14 @@ def main():
     ap.add_argument("--merge-ranges", type=int, default=1)
     ap.add_argument("--poll-sleep-us", type=int, default=50, help="device-thread poll interval in microseconds (0 = spin)")
     ap.add_argument("--staging-mode", type=int, default=1, help="1 = per-worker cache-sized pinned slots (default), 0 = one big pinned ring")
-    ap.add_argument("--host-slots", type=int, default=4, help="staging mode 1: pinned slots per worker")
-    ap.add_argument("--host-slot-kib", type=int, default=1024, help="staging mode 1: slot (extent, H2D copy) size")
+    ap.add_argument("--host-slots", type=int, default=0, help="staging mode 1: pinned slots per worker (0 = automatic, from the window budget)")
+    ap.add_argument("--host-slot-kib", type=int, default=0, help="staging mode 1: slot (extent, H2D copy) size")
     ap.add_argument("--inline-reads", type=int, default=1)
     ap.add_argument("--direct-landing", type=int, default=2, help="0 = ring + pack kernel, 1 = copy engine straight into the arena, 2 = pull kernel")
     ap.add_argument("--steal-batch", type=int, default=8)
     ap.add_argument("--completion-bound", type=int, default=0)
     ap.add_argument("--copy-coalesce-slots", type=int, default=2)
+    ap.add_argument("--window-budget-kib", type=int, default=0, help="pinned slot windows of one rank together (0 = 60 %% of the L3 / number of ranks)")
     ap.add_argument("--pin", type=int, default=1, help="N > 1: pin every rank's backend threads to its own slice of the CPUs")
     ap.add_argument("--zero-copy", type=int, default=0, help="1 = the pack kernel reads the pinned ring over PCIe (no H2D memcpy)")
     ap.add_argument("--statx-via-ring", type=int, default=0, help="1 = the reference's openat+statx SQE pair per file")
@@ -826,6 +840,8 @@ def main():
         # reads of memory-backed files run ON the worker (inline preadv2): one worker per CPU of this rank's share;
         # alone on the box a couple of CPUs stay free for the consumer and the device thread
         args.workers = max(2, min(12, cpus_per_rank - 4)) if n_gpus == 1 else max(2, min(12, cpus_per_rank))
+    if args.window_budget_kib <= 0:  # this rank's share of the last-level cache (all ranks share one host)
+        args.window_budget_kib = max(1024, int(llc_bytes() * 0.6 / n_gpus) >> 10)
     if args.completion_bound <= 0:
         args.completion_bound = 1 << 16
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"

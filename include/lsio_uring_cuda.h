@@ -69,8 +69,9 @@ typedef struct lsio_uring_cuda_config {
                                    (measured: tmpfs reads 69 GiB/s into <= 2 MiB/thread buffers vs 40 into a big one).
                                    0 = one `staging_bytes` pinned ring mirrored on the device, copied in coalesced
                                    runs by the device thread (needed for zero_copy) */
-    uint32_t host_slots_per_worker; /* staging_mode 1: slots per worker (default 4) */
-    uint32_t host_slot_kib;     /* staging_mode 1: slot (extent) size in KiB, >= max_read_bytes (default 1024): the unit that
+    uint32_t host_slots_per_worker; /* staging_mode 1: slots per worker; 0 (default) = 2..4, as many as window_budget_kib allows */
+    uint32_t host_slot_kib;     /* staging_mode 1: slot (extent) size in KiB, >= max_read_bytes; 0 (default) = 512, or 256 when two of those per worker
+                                   would not fit window_budget_kib: the unit that
                                    leaves the host in one pull launch / H2D copy; several reads of max_read_bytes can be in
                                    flight in one.  With the pull kernel (direct_landing 2) small slots cost no PCIe bandwidth,
                                    so the window (slots x slot size) is sized to stay in the worker's L2                  */
@@ -115,6 +116,11 @@ typedef struct lsio_uring_cuda_config {
                                    request buffer are copied with one cudaMemcpyAsync of up to this many slots (default 2,
                                    at most 8; 1 = one copy per extent).  The copy engine loses ~3.8 us per copy whatever its
                                    size (2 MiB copies: 46.9 GiB/s, 4 MiB: 49.2, 8 MiB: 50.4 of 51.6 on this pool's B200s).     */
+    uint32_t window_budget_kib; /* staging_mode 1, automatic slot geometry: the pinned windows of ALL workers of one device group
+                                   together stay within this many KiB, so that a slot is still in the last-level cache when the
+                                   GPU reads it back (otherwise each payload byte costs three extra DRAM transfers).
+                                   0 (default) = 60 % of the L3 reported by sysfs, divided by the number of devices of this
+                                   backend; one process per GPU on a shared host: pass this process's share                  */
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {
@@ -135,6 +141,8 @@ typedef struct lsio_uring_cuda_stats {
     uint64_t first_chunk_ns;    /* ns from the first get_ranges after construction / reset to the first chunk sent   */
     uint64_t max_dio_align;     /* largest per-file O_DIRECT alignment seen                                         */
     uint64_t pull_launches;     /* extents moved by the pull kernel (direct_landing 2), one launch each             */
+    uint64_t slot_bytes;        /* staging_mode 1: the slot geometry in use (after automatic sizing)                */
+    uint64_t slots_per_worker;
 } lsio_uring_cuda_stats;
 
 /* Per-chunk latency histogram (submit of the request -> chunk in the channel), log2 buckets of microseconds:

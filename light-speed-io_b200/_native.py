@@ -149,7 +149,7 @@ class CConfig(ctypes.Structure):
                 ("inline_reads", ctypes.c_uint32), ("force_align", ctypes.c_uint32), ("debug_short_read_every", ctypes.c_uint32),
                 ("null_source", ctypes.c_uint32), ("direct_landing", ctypes.c_uint32), ("cpu_first", ctypes.c_uint32),
                 ("cpu_count", ctypes.c_uint32), ("steal_batch", ctypes.c_uint32), ("pack_light_below_mib", ctypes.c_uint32),
-                ("copy_coalesce_slots", ctypes.c_uint32)]
+                ("copy_coalesce_slots", ctypes.c_uint32), ("window_budget_kib", ctypes.c_uint32)]
 
 
 class CStats(ctypes.Structure):
@@ -157,7 +157,7 @@ class CStats(ctypes.Structure):
                                                "pack_launches", "kernel_launches", "payload_bytes", "chunks_ok", "errors",
                                                "staging_stalls", "arena_stalls", "inline_reads", "direct_extents", "direct_copies",
                                                "read_ns", "copy_enqueue_ns", "worker_stall_ns", "worker_busy_ns", "pack_kernel_ns",
-                                               "pack_kernel_bytes", "first_chunk_ns", "max_dio_align", "pull_launches")]
+                                               "pack_kernel_bytes", "first_chunk_ns", "max_dio_align", "pull_launches", "slot_bytes", "slots_per_worker")]
 
 
 for _name, _res, _args in [

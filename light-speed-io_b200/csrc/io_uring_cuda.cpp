@@ -69,6 +69,26 @@ static std::vector<int> numa_cpus_of_device(int device) {
     return cpus;
 }
 
+// Size of the last-level cache shared by this process's CPUs (sysfs), or 32 MiB if it cannot be read.
+static uint64_t llc_bytes() {
+    uint64_t best = 0;
+    for (int idx = 2; idx <= 4; idx++) {
+        char path[128];
+        snprintf(path, sizeof path, "/sys/devices/system/cpu/cpu0/cache/index%d/size", idx);
+        FILE* f = fopen(path, "r");
+        if (!f) continue;
+        unsigned long long v = 0;
+        char unit = 0;
+        if (fscanf(f, "%llu%c", &v, &unit) >= 1) {
+            if (unit == 'K') v <<= 10;
+            else if (unit == 'M') v <<= 20;
+            if (idx >= 3 || !best) best = std::max<uint64_t>(best, v);
+        }
+        fclose(f);
+    }
+    return best ? best : (32ull << 20);
+}
+
 static void free_group_cuda(Group& g) {
     DeviceGuard dg(g.device);
     for (Batch& b : g.batches) {
@@ -239,8 +259,8 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->statx_via_ring = 0;
     cfg->zero_copy = 0;
     cfg->staging_mode = 1;
-    cfg->host_slots_per_worker = 4;
-    cfg->host_slot_kib = 1024;
+    cfg->host_slots_per_worker = 0;  // auto: see window_budget_kib
+    cfg->host_slot_kib = 0;          // auto
     cfg->pack_threads = 0;
     cfg->poll_sleep_us = 50;  // measured: same throughput as spinning (33-34 GiB/s C2, 27.7 vs 28.1 C3) without burning a core per GPU
     cfg->inline_reads = 1;
@@ -252,6 +272,7 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->steal_batch = 8;
     cfg->pack_light_below_mib = 512;
     cfg->copy_coalesce_slots = 2;
+    cfg->window_budget_kib = 0;
 }
 
 int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {
@@ -263,6 +284,22 @@ int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uri
         cfg.min_copy_bytes = std::min<uint64_t>(cfg.min_copy_bytes, cfg.staging_bytes / 4);
     }
     if (cfg.zero_copy) cfg.staging_mode = 0;  // the kernel needs the whole pinned ring mapped
+    if (cfg.staging_mode == 1 && (cfg.host_slots_per_worker == 0 || cfg.host_slot_kib == 0)) {
+        // Size the pinned windows so that ALL of them stay in the last-level cache: a slot is written by the reading core
+        // and read back by the GPU a moment later; if it has been evicted in between, every payload byte costs three more
+        // DRAM transfers (write-back, re-fetch for ownership, DMA read) on top of the read of the source.  Measured on
+        // this pool (60 MiB L3): 24 workers x 2 MiB windows 91.6 GiB/s, x 4 MiB 59.4; 32 workers x 2 MiB 77, x 1.5 MiB 80.6.
+        uint64_t budget = (uint64_t)cfg.window_budget_kib << 10;
+        if (!budget) budget = llc_bytes() * 6 / 10 / std::max<uint32_t>(1, cfg.n_devices);
+        const uint64_t per_worker = budget / std::max<uint32_t>(1, cfg.n_worker_threads);
+        uint64_t slot = cfg.host_slot_kib ? (uint64_t)cfg.host_slot_kib << 10 : 512u << 10;
+        if (!cfg.host_slot_kib && per_worker < 2 * slot) slot = 256u << 10;  // two slots must fit: halve them
+        if (!cfg.host_slot_kib) {
+            cfg.host_slot_kib = (uint32_t)(slot >> 10);
+            cfg.max_read_bytes = std::min<uint64_t>(cfg.max_read_bytes, slot);
+        }
+        if (!cfg.host_slots_per_worker) cfg.host_slots_per_worker = (uint32_t)std::min<uint64_t>(4, std::max<uint64_t>(2, per_worker / slot));
+    }
     if (cfg.staging_mode == 1) {
         // every worker must be able to hold two extents in the device log at once, and a slot holds at least one read
         const uint64_t slot_bytes = std::max<uint64_t>((uint64_t)cfg.host_slot_kib << 10, (cfg.max_read_bytes + 4095) / 4096 * 4096);
@@ -417,6 +454,7 @@ int lsio_uring_cuda_get_stats(const lsio_uring_cuda* self, lsio_uring_cuda_stats
     o->copy_enqueue_ns = s.copy_enqueue_ns; o->worker_stall_ns = s.worker_stall_ns; o->worker_busy_ns = s.worker_busy_ns;
     o->pack_kernel_ns = s.pack_kernel_ns; o->pack_kernel_bytes = s.pack_kernel_bytes; o->first_chunk_ns = s.first_chunk_ns;
     o->max_dio_align = s.max_dio_align; o->pull_launches = s.pull_launches;
+    o->slot_bytes = self->be->groups.empty() ? 0 : self->be->groups[0]->slot_bytes; o->slots_per_worker = self->be->cfg.staging_mode == 1 ? self->be->cfg.host_slots_per_worker : 0;
     return 0;
 }
 
