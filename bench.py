@@ -525,14 +525,26 @@ def leg_summary(leg, dev, workers, n_gpus):
             "per_worker_rank0": per_worker(st, workers, leg["total_secs"])}
 
 
-def pipeline_kernel(st, hbm_peak):
-    if not st["pack_kernel_ns"]:
-        return None
-    ach = st["pack_kernel_bytes"] / st["pack_kernel_ns"]  # bytes per ns = GB/s
-    return {"launches": st["pack_launches"], "algorithmic_bytes_per_launch": st["pack_kernel_bytes"] / max(1, st["pack_launches"]),
-            "us_per_launch": st["pack_kernel_ns"] / 1e3 / max(1, st["pack_launches"]), "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-            "is": "event pairs around every pack/checksum launch of the timed region (launch gaps included); batches are small because the pipeline is PCIe-bound: "
-                  "the kernel is busy for well under 2 % of the step"}
+def pipeline_kernel(st, hbm_peak, secs=None, pcie_gib_s=None):
+    """The kernel launches INSIDE the timed region.  Extents moved by the pull kernel: one launch per extent on the workers'
+    streams, bound by the PCIe link it reads through (its 'roofline' is the link, not HBM); extents that went ring -> pack
+    kernel: event pairs around every pack launch of the region."""
+    out = {}
+    if st.get("pull_launches"):
+        per = st["h2d_bytes"] / max(1, st["pull_launches"] + st["h2d_copies"])
+        out["pull_kernel"] = {"launches": st["pull_launches"], "bytes_per_launch": per, "bound": "pcie",
+                              "is": "pull_kernel<crc32c>: SM loads from the mapped pinned slot over PCIe + fused CRC-32C + store at the final place in HBM; "
+                                    "PCIe traffic L, HBM traffic L (write only); launches of different workers overlap, so the link stays busy between them"}
+        if secs and pcie_gib_s:
+            ach = st["h2d_bytes"] / secs / GIB
+            out["pull_kernel"].update({"achieved": ach, "peak": pcie_gib_s, "unit": "GiB/s", "frac": ach / pcie_gib_s,
+                                       "peak_is": "cudaMemcpyAsync of 64 MiB from pinned memory (the link's best case; SM loads themselves top out at 47.8 GiB/s, tools/h2d_probe.cu)"})
+    if st["pack_kernel_ns"]:
+        ach = st["pack_kernel_bytes"] / st["pack_kernel_ns"]  # bytes per ns = GB/s
+        out["pack_kernel"] = {"launches": st["pack_launches"], "algorithmic_bytes_per_launch": st["pack_kernel_bytes"] / max(1, st["pack_launches"]),
+                              "us_per_launch": st["pack_kernel_ns"] / 1e3 / max(1, st["pack_launches"]), "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                              "is": "event pairs around every pack/checksum launch of the timed region (launch gaps included); batches are small because the pipeline is I/O-bound"}
+    return out or None
 
 
 # ---- ceilings ----------------------------------------------------------------------------------------------
@@ -561,13 +573,13 @@ def source_ceiling(paths, thread_counts, o_direct=True, reps=1):
 
     best, shapes = 0.0, []
     for nthr in sorted(set(thread_counts)):
-        for block, qd, inl in ((512 << 10, 4, 1), (512 << 10, 4, 0), (1 << 20, 32, 0), (256 << 10, 64, 0), (2 << 20, 2, 1)):
+        for block, qd, inl, fif in ((512 << 10, 4, 1, 1), (512 << 10, 4, 0, 1), (512 << 10, 8, 0, 4), (1 << 20, 32, 0, 4), (256 << 10, 64, 0, 8), (2 << 20, 2, 1, 1)):
             try:
-                v = max(cuda_ops.probe_read_ceiling(paths, block, nthr, qd, o_direct, inl) for _ in range(reps))
+                v = max(cuda_ops.probe_read_ceiling(paths, block, nthr, qd, o_direct, inl, fif) for _ in range(reps))
             except Exception as ex:
-                shapes.append({"threads": nthr, "block": block, "qd": qd, "inline": inl, "error": repr(ex)})
+                shapes.append({"threads": nthr, "block": block, "qd": qd, "inline": inl, "files_in_flight": fif, "error": repr(ex)})
                 continue
-            shapes.append({"threads": nthr, "block": block, "qd": qd, "inline": inl, "gib_s": round(v, 2)})
+            shapes.append({"threads": nthr, "block": block, "qd": qd, "inline": inl, "files_in_flight": fif, "gib_s": round(v, 2)})
             best = max(best, v)
     return best, shapes
 
@@ -804,6 +816,7 @@ def main():
     ap.add_argument("--completion-bound", type=int, default=0)
     ap.add_argument("--copy-coalesce-slots", type=int, default=2)
     ap.add_argument("--window-budget-kib", type=int, default=0, help="pinned slot windows of one rank together (0 = 60 %% of the L3 / number of ranks)")
+    ap.add_argument("--deal", type=int, default=1, help="1 = ranks own disjoint physical files (default), 0 = logical file j is physical file j %% files")
     ap.add_argument("--pin", type=int, default=1, help="N > 1: pin every rank's backend threads to its own slice of the CPUs")
     ap.add_argument("--zero-copy", type=int, default=0, help="1 = the pack kernel reads the pinned ring over PCIe (no H2D memcpy)")
     ap.add_argument("--statx-via-ring", type=int, default=0, help="1 = the reference's openat+statx SQE pair per file")
@@ -860,11 +873,19 @@ def main():
         paths = write_files_cpu(directory, "lsio_bench", args.files, FILE_SIZE)  # already there
         expect = oracle_crc_table(directory, "c2", paths, BLOCK, N_CHUNKS)        # cached by rank 0
     t_gen = time.time() - t_gen
-    # weak scaling: n_gpus * files logical files dealt file_idx mod n_gpus; logical file j is
-    # physical file j % files (the file set is shared read-only to bound storage; nothing is cached between passes)
-    mine = sharding.files_for_rank(args.files * n_gpus, rank, n_gpus)
-    my_paths = [paths[j % args.files] for j in mine]
-    my_ids = [j % args.files for j in mine]
+    # weak scaling: every rank lands `files` files per step (20.6 GB).  Storage is bounded by re-using the one physical file
+    # set: the physical files are DEALT file_idx mod n_gpus and a rank walks its own share files/n_gpus times
+    # per step, so that no two ranks ever read the same file (two cores hammering the same page-cache folios' reference
+    # counts is an artefact a real, n_gpus times larger data set would not have).  --deal 0: the round-1 dealing (logical
+    # file j = physical file j % files), which at 8 ranks makes ranks r and r+4 walk the same files in lockstep.
+    if args.deal == 2:  # experiment: every rank walks ALL files in the same order (worst case of sharing)
+        my_ids = list(range(args.files))
+    elif args.deal:
+        phys = sharding.files_for_rank(args.files, rank, n_gpus)
+        my_ids = [phys[i % len(phys)] for i in range(args.files)]
+    else:
+        my_ids = [j % args.files for j in sharding.files_for_rank(args.files * n_gpus, rank, n_gpus)]
+    my_paths = [paths[j] for j in my_ids]
 
     peaks = {}
     try:
@@ -984,7 +1005,7 @@ def main():
                 "e2e_is": "the same through the Python mirror of the reference API (get_ranges + recv_batch), CRCs compared in numpy",
                 "l2": "inputs larger than L2 (20.6 GB land per step vs 126 MB)", "worker_threads_per_gpu": args.workers,
                 "cpu_pinning": {"cpu_first": args.cpu_first, "cpu_count": args.cpu_count} if args.pin and args.cpu_count else None, "nproc": os.cpu_count(),
-                "multi_gpu": "files dealt file_idx mod n_gpus, no collective on the data path; each rank lands 500 files (shared read-only file set)",
+                "multi_gpu": "physical files dealt file_idx mod n_gpus, no collective on the data path; each rank lands 500 files per step by walking its own share n_gpus times (no file is read by two ranks)",
                 "file_generation_s": round(t_gen, 1), "files_written_by": "oracle.write_file",
             },
             "e2e": {"value": e["gib_s"], "unit": "GiB/s", "h2d_bytes_per_step": per_step, "d2h_bytes_per_step": 4 * len(my_paths) * N_CHUNKS,
@@ -996,7 +1017,7 @@ def main():
                          "algorithmic_bytes_per_launch": kern["algo_bytes"],
                          "in_place_crc_only": {"kernel": "pack_kernel<crc32c only> (the form run on directly landed extents)", "kernel_ms": ip_ms, "algorithmic_bytes_per_launch": kern_ip["algo_bytes"],
                                                "achieved": kern_ip["algo_bytes"] / ip_ms / 1e6, "frac": kern_ip["algo_bytes"] / ip_ms / 1e6 / hbm_peak},
-                         "pipeline_kernel": pipeline_kernel(val["stats"], hbm_peak)},
+                         "pipeline_kernel": pipeline_kernel(val["stats"], hbm_peak, val["total_secs"], ceil["pcie_h2d_gib_s_one_gpu_alone"])},
             "cpu_baseline": cpu,
             "io_roofline": io_roofline,
             "value_detail": {k: v[k] for k in ("per_rank_gib_s", "bad_chunks", "latency_rank0", "pipeline_rank0", "per_worker_rank0", "read_amplification")}
@@ -1058,13 +1079,14 @@ def c4_leg(args, dev, rank, n_gpus, directory, paths):
     if rank != 0:
         exp = oracle_crc_table(directory, "c4", paths, MIB, k)
     st = np.arange(k, dtype=np.int64) << 20
-    mine = sharding.files_for_rank(len(paths) * n_gpus, rank, n_gpus)
-    my_paths = [paths[j % len(paths)] for j in mine]
-    my_exp = np.concatenate([exp[j % len(paths)] for j in mine])
+    phys = sharding.files_for_rank(len(paths), rank, n_gpus)  # ranks own disjoint physical files, walked n_gpus times per step
+    mine = [phys[i % len(phys)] for i in range(len(paths))]
+    my_paths = [paths[j] for j in mine]
+    my_exp = np.concatenate([exp[j] for j in mine])
     per = [(st, st + MIB)] * len(my_paths)
     leg = ranges_leg(args, dev, my_paths, per, my_exp, len(my_paths) * k * MIB, 3, 1)
     out = leg_summary(leg, dev, args.workers, n_gpus)
-    out.update({"config": f"C4: {len(paths)} files x {FILE_SIZE} B per GPU, dealt file_idx mod {n_gpus}, {k} ranges of 1 MiB per file", "expected_crc_source": "oracle"})
+    out.update({"config": f"C4: {len(paths)} files x {FILE_SIZE} B landed per GPU per step (physical files dealt file_idx mod {n_gpus}, each rank walks its share {n_gpus} times), {k} ranges of 1 MiB per file", "expected_crc_source": "oracle"})
     return out
 
 
@@ -1091,14 +1113,15 @@ def c5_leg(args, dev, rank, n_gpus, directory):
         exp = oracle_crc_table(d5, "c5", paths, 4 * MIB, size // (4 * MIB))
     st4 = np.arange(size >> 22, dtype=np.int64) << 22
     per = [(st4, st4 + 4 * MIB)] * n_files
-    # rank r starts its loop at a different file so that the ranks do not walk the shared set in lockstep
-    order = [(i + rank * max(1, n_files // n_gpus)) % n_files for i in range(n_files)]
+    # every rank scans its own files (dealt file_idx mod n_gpus), looped
+    order = [i for i in range(n_files) if i % n_gpus == rank] or [rank % n_files]
     my_paths = [paths[i] for i in order]
     my_exp = np.concatenate([exp[i] for i in order])
-    loops = max(1, int(round(args.c5_total_gb * 1e9 / n_gpus / (n_files * size))))
-    leg = ranges_leg(args, dev, my_paths, per, my_exp, n_files * size, 1, 1, loops=loops, arena_bytes=max(args.arena_gib, 12) << 30)
+    per = per[:len(order)]
+    loops = max(1, int(round(args.c5_total_gb * 1e9 / n_gpus / (len(order) * size))))
+    leg = ranges_leg(args, dev, my_paths, per, my_exp, len(order) * size, 1, 1, loops=loops, arena_bytes=max(args.arena_gib, 12) << 30)
     out = leg_summary(leg, dev, args.workers, n_gpus)
-    out.update({"config": f"C5: {n_files} files x 1 GiB (shared read-only set), 256 ranges of 4 MiB per file, {loops} loops per rank per step, {n_gpus} ranks",
+    out.update({"config": f"C5: {n_files} files x 1 GiB dealt file_idx mod {n_gpus} ({len(order)} per rank), 256 ranges of 4 MiB per file, {loops} loops per rank per step",
                 "loops_per_rank": loops, "bytes_landed_all_ranks": out["bytes"], "expected_crc_source": "oracle", "fused_crc32c_checked_per_chunk": True})
     return out
 

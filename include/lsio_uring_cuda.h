@@ -199,9 +199,11 @@ int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t b
  * through the ring, 1 = files the kernel cannot read asynchronously are read with preadv2 on the probing thread (cycling
  * through the same queue_depth * block_bytes window), 2 = always preadv2.  The I/O ceiling bench.py reports is the best
  * of several shapes of this probe, so that it bounds what the pipeline -- which does strictly more work per byte --
- * can reach on the same files. */
+ * can reach on the same files.  `files_in_flight`: files each thread keeps open at once, their blocks issued round robin
+ * (the queue stays full across file boundaries, as the backend keeps it); 1 = one file after the other. */
 int lsio_probe_read_ceiling_ex(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads,
-                               uint32_t queue_depth, uint32_t o_direct, uint32_t inline_reads, double* gib_per_s);
+                               uint32_t queue_depth, uint32_t o_direct, uint32_t inline_reads, uint32_t files_in_flight,
+                               double* gib_per_s);
 
 /* Test aid: host-logic self tests of the shipped components (tracker, user_data, channel, staging
  * log, arena, GF(2) combine), no GPU needed; see csrc/selftest.cpp. 0 = pass. */

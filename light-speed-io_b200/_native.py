@@ -205,7 +205,7 @@ lib.lsio_probe_read_ceiling.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.
 
 lib.lsio_probe_read_ceiling_ex.restype = ctypes.c_int
 lib.lsio_probe_read_ceiling_ex.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
-                                           ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
+                                           ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
 
 
 # ---- include/lsio_bench.h -------------------------------------------------------------------------

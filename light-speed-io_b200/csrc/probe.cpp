@@ -10,11 +10,11 @@ extern "C" {
 
 int lsio_probe_read_ceiling(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads, uint32_t queue_depth,
                             uint32_t o_direct, double* gib_per_s) {
-    return lsio_probe_read_ceiling_ex(paths, n_paths, block_bytes, n_threads, queue_depth, o_direct, 0, gib_per_s);
+    return lsio_probe_read_ceiling_ex(paths, n_paths, block_bytes, n_threads, queue_depth, o_direct, 0, 1, gib_per_s);
 }
 
 int lsio_probe_read_ceiling_ex(const char* const* paths, size_t n_paths, uint64_t block_bytes, uint32_t n_threads, uint32_t queue_depth,
-                               uint32_t o_direct, uint32_t inline_reads, double* gib_per_s) {
+                               uint32_t o_direct, uint32_t inline_reads, uint32_t files_in_flight, double* gib_per_s) {
     if (!paths || !n_paths || !gib_per_s || !n_threads || !queue_depth || block_bytes < kAlign || block_bytes % kAlign) return -EINVAL;
     const uint64_t slot_bytes = block_bytes * queue_depth;
     uint8_t* pinned = nullptr;
@@ -34,59 +34,92 @@ int lsio_probe_read_ceiling_ex(const char* const* paths, size_t n_paths, uint64_
             if (rc == 0) rc = ring.register_buffers(&iv, 1);
             if (rc) { err.store(rc); return; }
             uint64_t bytes = 0;
-            for (size_t f; (f = next_file.fetch_add(1)) < n_paths;) {
-                int fd = open(paths[f], O_RDONLY | (o_direct ? O_DIRECT : 0));
-                if (fd < 0) { err.store(-errno); break; }
-                struct stat st;
-                fstat(fd, &st);
-                const uint64_t nblk = ((uint64_t)st.st_size + block_bytes - 1) / block_bytes;
-                // the product's own rule (worker.cpp configure_request): a file the kernel cannot read asynchronously is
-                // read with preadv2 on this thread instead of being handed to an io-wq thread by io_uring
-                bool inl = inline_reads == 2;
-                if (inline_reads == 1) {
-                    uint8_t byte;
-                    iovec iv{&byte, 1};
-                    inl = preadv2(fd, &iv, 1, 0, RWF_NOWAIT) < 0 && errno == EOPNOTSUPP;
-                }
-                if (inl) {
-                    uint8_t* base = pinned + (uint64_t)t * slot_bytes;
-                    for (uint64_t k = 0; k < nblk; k++) {
-                        iovec iv{base + (k % queue_depth) * block_bytes, (size_t)block_bytes};
-                        const ssize_t n = preadv2(fd, &iv, 1, (off_t)(k * block_bytes), 0);
-                        if (n < 0) { err.store(-errno); break; }
-                        bytes += (uint64_t)n;
-                    }
-                    close(fd);
-                    continue;
-                }
-                uint64_t issued = 0, done = 0;
-                std::vector<unsigned> free_slots;
-                for (unsigned i = 0; i < queue_depth; i++) free_slots.push_back(i);
-                while (done < nblk) {
-                    while (issued < nblk && !free_slots.empty()) {
-                        io_uring_sqe* e = ring.get_sqe();
-                        if (!e) break;
-                        const unsigned slot = free_slots.back();
-                        free_slots.pop_back();
-                        e->opcode = IORING_OP_READ_FIXED;
-                        e->fd = fd;
-                        e->addr = (uint64_t)(uintptr_t)(pinned + (uint64_t)t * slot_bytes + (uint64_t)slot * block_bytes);
-                        e->len = (uint32_t)block_bytes;
-                        e->off = issued * block_bytes;
-                        e->buf_index = 0;
-                        e->user_data = slot;
-                        issued++;
-                    }
-                    ring.submit(1);
-                    io_uring_cqe c;
-                    while (ring.pop_cqe(&c)) {
-                        if (c.res < 0) err.store(c.res);
-                        else bytes += (uint64_t)c.res;
-                        free_slots.push_back((unsigned)c.user_data);
-                        done++;
+            // the product's own rule (worker.cpp configure_request): a file the kernel cannot read asynchronously is
+            // read with preadv2 on this thread instead of being handed to an io-wq thread by io_uring
+            auto is_inline = [&](int fd) {
+                if (inline_reads == 2) return true;
+                if (inline_reads != 1) return false;
+                uint8_t byte;
+                iovec iv{&byte, 1};
+                return preadv2(fd, &iv, 1, 0, RWF_NOWAIT) < 0 && errno == EOPNOTSUPP;
+            };
+            // Asynchronous reads: up to `files_in_flight` files open at once, their blocks issued round robin, so that the
+            // queue stays full across file boundaries (as the backend keeps it).
+            struct OpenFile {
+                int fd = -1;
+                uint64_t nblk = 0, issued = 0, done = 0;
+            };
+            std::vector<OpenFile> of(files_in_flight ? files_in_flight : 1);
+            std::vector<unsigned> free_slots;
+            for (unsigned i = 0; i < queue_depth; i++) free_slots.push_back(i);
+            bool more = true;
+            unsigned inflight = 0, rr = 0;
+            uint8_t* base = pinned + (uint64_t)t * slot_bytes;
+            for (;;) {
+                for (auto& o : of) {
+                    while (o.fd < 0 && more) {
+                        const size_t f = next_file.fetch_add(1);
+                        if (f >= n_paths) { more = false; break; }
+                        int fd = open(paths[f], O_RDONLY | (o_direct ? O_DIRECT : 0));
+                        if (fd < 0) { err.store(-errno); more = false; break; }
+                        struct stat st;
+                        fstat(fd, &st);
+                        const uint64_t nblk = ((uint64_t)st.st_size + block_bytes - 1) / block_bytes;
+                        if (is_inline(fd)) {
+                            for (uint64_t k = 0; k < nblk; k++) {
+                                iovec iv{base + (k % queue_depth) * block_bytes, (size_t)block_bytes};
+                                const ssize_t n = preadv2(fd, &iv, 1, (off_t)(k * block_bytes), 0);
+                                if (n < 0) { err.store(-errno); break; }
+                                bytes += (uint64_t)n;
+                            }
+                            close(fd);
+                            continue;
+                        }
+                        o = OpenFile{fd, nblk, 0, 0};
+                        if (nblk == 0) { close(fd); o.fd = -1; }
                     }
                 }
-                close(fd);
+                bool any_open = false;
+                for (auto& o : of) any_open |= o.fd >= 0;
+                if (!any_open && inflight == 0) break;
+                while (!free_slots.empty()) {
+                    OpenFile* pick = nullptr;
+                    for (size_t k = 0; k < of.size(); k++) {
+                        OpenFile& o = of[(rr + k) % of.size()];
+                        if (o.fd >= 0 && o.issued < o.nblk) { pick = &o; rr = (unsigned)((rr + k + 1) % of.size()); break; }
+                    }
+                    if (!pick) break;
+                    io_uring_sqe* e = ring.get_sqe();
+                    if (!e) break;
+                    const unsigned slot = free_slots.back();
+                    free_slots.pop_back();
+                    e->opcode = IORING_OP_READ_FIXED;
+                    e->fd = pick->fd;
+                    e->addr = (uint64_t)(uintptr_t)(base + (uint64_t)slot * block_bytes);
+                    e->len = (uint32_t)block_bytes;
+                    e->off = pick->issued * block_bytes;
+                    e->buf_index = 0;
+                    e->user_data = ((uint64_t)(pick - of.data()) << 32) | slot;
+                    pick->issued++;
+                    inflight++;
+                }
+                if (inflight == 0) continue;
+                ring.submit(1);
+                io_uring_cqe c;
+                while (ring.pop_cqe(&c)) {
+                    if (c.res < 0) err.store(c.res);
+                    else bytes += (uint64_t)c.res;
+                    free_slots.push_back((unsigned)(c.user_data & 0xFFFFFFFFu));
+                    OpenFile& o = of[c.user_data >> 32];
+                    inflight--;
+                    if (++o.done == o.nblk) { close(o.fd); o.fd = -1; }
+                }
+                if (err.load()) {
+                    // drain what is in flight, then stop
+                    more = false;
+                    for (auto& o : of) o.issued = o.nblk;
+                    if (inflight == 0) { for (auto& o : of) if (o.fd >= 0) { close(o.fd); o.fd = -1; } }
+                }
             }
             total.fetch_add(bytes);
         });

@@ -132,7 +132,7 @@ def fill_pattern(buf, file_id, file_off=0, stream=None):
                                          _stream_ptr(stream)), "fill_pattern")
 
 
-def probe_read_ceiling(paths, block_bytes=1 << 20, n_threads=8, queue_depth=32, o_direct=True, inline_reads=0):
+def probe_read_ceiling(paths, block_bytes=1 << 20, n_threads=8, queue_depth=32, o_direct=True, inline_reads=0, files_in_flight=1):
     """GiB/s of raw reads over `paths` with no GPU work (stand-in for benches/fio.ini): READ_FIXED through io_uring, or
     -- inline_reads=1, the backend's own default rule -- preadv2 on the probing thread for files the kernel cannot read
     asynchronously (tmpfs)."""
@@ -140,7 +140,7 @@ def probe_read_ceiling(paths, block_bytes=1 << 20, n_threads=8, queue_depth=32, 
 
     arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
     out = ctypes.c_double(0)
-    N.check(N.lib.lsio_probe_read_ceiling_ex(arr, len(paths), block_bytes, n_threads, queue_depth, int(o_direct), int(inline_reads), ctypes.byref(out)),
+    N.check(N.lib.lsio_probe_read_ceiling_ex(arr, len(paths), block_bytes, n_threads, queue_depth, int(o_direct), int(inline_reads), int(files_in_flight), ctypes.byref(out)),
             "probe_read_ceiling")
     return out.value
 

@@ -876,7 +876,11 @@ def test_consecutive_slots_are_copied_with_one_call(lsio, oracle, cuda_dev, data
             u.get_ranges(fn, rs, range(len(rs)))
             _check_chunks(oracle, _drain(u.completion(), len(rs)), lambda ud: fn, lambda ud: rs[ud])
             st = u.stats()
-            assert st["direct_extents"] == 16 and st["direct_copies"] == want_copies, st
+            assert st["direct_extents"] == 16
+            if st["inline_reads"]:  # memory-backed file: the worker reads slot after slot itself, so the slots fill in order
+                assert st["direct_copies"] == want_copies, st
+            else:  # asynchronous reads complete in any order; a copy is never held back across a wait for completions
+                assert want_copies <= st["direct_copies"] <= 16, st
 
 
 @pytest.mark.parametrize("inline_reads,staging_mode", [(0, 1), (2, 1), (0, 0), (2, 0)])
@@ -931,17 +935,20 @@ def test_direct_landing_and_light_kernel_same_bytes(lsio, oracle, cuda_dev, data
 
 
 def test_direct_landing_without_checksum_needs_no_kernel(lsio, oracle, cuda_dev, data_dir):
+    """checksum = 0: copy-engine landing (direct_landing 1) launches nothing at all; the pull kernel (2) is the only launch."""
     size = 4 * MIB
     fn = os.path.join(data_dir, "blocks")
     oracle.write_file(fn, 78, size)
     blocks = [(i * 512 * KIB, (i + 1) * 512 * KIB) for i in range(8)]
-    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20, checksum=0) as u:
-        u.get_ranges(fn, blocks, range(8))
-        for c in _drain(u.completion(), 8):
-            assert c.is_ok() and c.crc32c is None
-            assert np.array_equal(c.buffer.as_slice(), oracle.pread_range(fn, *blocks[c.user_data]))
-        st = u.stats()
-        assert st["direct_extents"] > 0 and st["kernel_launches"] == 0
+    for landing in (1, 2):
+        with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20, checksum=0, direct_landing=landing) as u:
+            u.get_ranges(fn, blocks, range(8))
+            for c in _drain(u.completion(), 8):
+                assert c.is_ok() and c.crc32c is None
+                assert np.array_equal(c.buffer.as_slice(), oracle.pread_range(fn, *blocks[c.user_data]))
+            st = u.stats()
+            assert st["direct_extents"] > 0 and st["pack_launches"] == 0
+            assert st["kernel_launches"] == st["pull_launches"] and (st["pull_launches"] > 0) == (landing == 2)
 
 
 def test_null_source_and_latency_counters(lsio, oracle, cuda_dev, data_dir):
@@ -964,3 +971,16 @@ def test_null_source_and_latency_counters(lsio, oracle, cuda_dev, data_dir):
         assert u.stats()["worker_busy_ns"] >= 0
         u.reset_latency()
         assert u.latency_summary()["chunks"] == 0
+
+
+@pytest.mark.parametrize("inline_reads,files_in_flight", [(0, 1), (0, 4), (1, 1), (2, 3)])
+def test_read_ceiling_probe_reads_every_byte(lsio, oracle, cuda_dev, data_dir, inline_reads, files_in_flight):
+    """The I/O ceiling probe (stand-in for benches/fio.ini): every shape must read the whole file set -- ragged sizes, more
+    files than threads, several files in flight per thread -- and report a positive rate."""
+    fns = []
+    for i in range(7):
+        fn = os.path.join(data_dir, f"p{i}")
+        oracle.write_file(fn, 40 + i, 3 * MIB + i * 4096 * 5)
+        fns.append(fn)
+    v = lsio.cuda_ops.probe_read_ceiling(fns, 256 * KIB, 3, 4, True, inline_reads, files_in_flight)
+    assert v > 0

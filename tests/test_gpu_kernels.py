@@ -217,6 +217,8 @@ def test_pull_kernel_reads_pinned_host_memory_bit_exact(lsio, oracle, cuda_dev):
     destination is HBM.  Same bytes and CRCs as the oracle's pack for empty / tiny / single-tile / multi-tile segments at
     every relative shift mod 16 (the backend only pulls shift 0, the kernel itself takes any), and nothing outside the
     destination ranges is touched."""
+    import torch
+
     rng = np.random.default_rng(77)
     for case in range(6):
         n = [1, 5, 16, 33, 64, 64][case]
