@@ -663,6 +663,17 @@ int check_device(int device) {
 
 using namespace lsio;
 
+namespace {
+// A cudaMallocAsync block that is returned to the pool on every path out of the synchronous helpers.
+struct AsyncBlock {
+    void* p;
+    cudaStream_t st;
+    ~AsyncBlock() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+}  // namespace
+
 extern "C" {
 
 int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_dev, size_t n, lsio_codec_result* results_dev, void* stream) {
@@ -680,7 +691,8 @@ int lsio_codecs_lz4_decompress_async(int device, const lsio_codec_item* items_de
     // 256 x 1 MiB, 34.6 vs 16.4 at 1,024 x 1 MiB, 53.4 vs 31.8 at 2,048 x 64 KiB, 56.0 vs 53.1 at 4,096 x 64 KiB); the
     // warp-per-block variant stays selectable (32).
     int variant = n > 24576 ? 88 : n > 6144 ? 8 : 1;  // 88 / 8: teams of 8 at 8 / 5 CTAs per SM; 1 (2): parallel parse, 32 (64) positions per batch; 32: a warp per block
-    if (const char* e = getenv("LSIO_LZ4_VARIANT")) variant = atoi(e);  // measurement knob (tools/codec_bench.py)
+    static const int forced = [] { const char* e = getenv("LSIO_LZ4_VARIANT"); return e ? atoi(e) : 0; }();  // measurement knob (tools/codec_bench.py), read once
+    if (forced) variant = forced;
     cudaStream_t st = (cudaStream_t)stream;
     if (variant == 88) lz4_kernel<8, 8><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
     else if (variant == 8) lz4_kernel<8, 5><<<(unsigned)((n + 31) / 32), kLzThreads, 0, st>>>(items_dev, (uint32_t)n, results_dev);
@@ -701,13 +713,13 @@ int lsio_codecs_lz4_decompress(int device, const lsio_codec_item* items, size_t 
     cudaStream_t st = (cudaStream_t)stream;
     char* d = nullptr;
     LSIO_CUDA_TRY(cudaMallocAsync((void**)&d, n * (sizeof(lsio_codec_item) + sizeof(lsio_codec_result)), st));
+    AsyncBlock guard{d, st};  // freed on every return path
     lsio_codec_item* d_items = reinterpret_cast<lsio_codec_item*>(d);
     lsio_codec_result* d_res = reinterpret_cast<lsio_codec_result*>(d + n * sizeof(lsio_codec_item));
     LSIO_CUDA_TRY(cudaMemcpyAsync(d_items, items, n * sizeof(lsio_codec_item), cudaMemcpyHostToDevice, st));
     int rc = lsio_codecs_lz4_decompress_async(device, d_items, n, d_res, stream);
     if (rc) return rc;
     LSIO_CUDA_TRY(cudaMemcpyAsync(results, d_res, n * sizeof(lsio_codec_result), cudaMemcpyDeviceToHost, st));
-    LSIO_CUDA_TRY(cudaFreeAsync(d, st));
     LSIO_CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
@@ -762,13 +774,13 @@ static int shuffle_host_items(int device, const lsio_codec_item* items, size_t n
     cudaStream_t st = (cudaStream_t)stream;
     char* d = nullptr;
     LSIO_CUDA_TRY(cudaMallocAsync((void**)&d, n * sizeof(lsio_codec_item) + map.size() * sizeof(uint32_t), st));
+    AsyncBlock guard{d, st};  // freed on every return path
     lsio_codec_item* d_items = reinterpret_cast<lsio_codec_item*>(d);
     uint32_t* d_map = reinterpret_cast<uint32_t*>(d + n * sizeof(lsio_codec_item));
     LSIO_CUDA_TRY(cudaMemcpyAsync(d_items, items, n * sizeof(lsio_codec_item), cudaMemcpyHostToDevice, st));
     LSIO_CUDA_TRY(cudaMemcpyAsync(d_map, map.data(), map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     int rc = lsio_codecs_unshuffle_async(device, d_items, d_map, (uint32_t)total, elem_size, forward, stream);
     if (rc) return rc;
-    LSIO_CUDA_TRY(cudaFreeAsync(d, st));
     LSIO_CUDA_TRY(cudaStreamSynchronize(st));  // `map` and `items` are pageable host memory: keep the call self-contained
     return 0;
 }

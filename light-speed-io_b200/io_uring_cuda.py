@@ -184,6 +184,7 @@ class IoUringCuda:
             raise N.LsioCudaError(f"IoUringCuda::new failed (rc={rc}): {N.lib.lsio_uring_cuda_last_error().decode(errors='replace')}")
         self._rx = Receiver(N.lib.lsio_uring_cuda_completion(self._h))
         self.devices = devices
+        self.arena_bytes = int(cfg.arena_bytes)
 
     @classmethod
     def new(cls, n_worker_threads, **kw):

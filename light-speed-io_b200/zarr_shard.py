@@ -61,16 +61,27 @@ def read_shards(uring, paths, n_inner, wanted=None, index_crc32c=True, index_loc
     for i, p in enumerate(paths):
         uring.get_ranges(p, [index_range(n_inner, index_crc32c, index_location)], [i])
     uring.next_group()  # chunk reads start only after every index has been delivered
-    tables = {}
-    for _ in paths:
+    tables, first_error = {}, None
+    for _ in paths:  # every index item is received and dropped even if one of them is bad: nothing is left on the backend
         c = rx.recv_timeout(timeout)
-        tables[c.user_data] = parse_index(c, n_inner, index_crc32c)
-        c.buffer.drop()
+        try:
+            tables[c.user_data] = parse_index(c, n_inner, index_crc32c)
+        except ShardIndexError as ex:
+            first_error = first_error or ex
+        finally:
+            if c.is_ok():
+                c.buffer.drop()
+    if first_error is not None:
+        uring.next_group()
+        raise first_error
     total, present = 0, []
     for i, p in enumerate(paths):
         off, nb = tables[i]
         sel = np.arange(n_inner) if wanted is None else np.asarray(wanted[i], dtype=np.int64)
         sel = sel[(off[sel] != MISSING) | (nb[sel] != MISSING)]
+        if np.any(nb[sel] == 0):
+            uring.next_group()
+            raise ShardIndexError(f"{p}: the index holds a zero-length entry for a chunk that is not marked missing")
         present.append(sel)
         if len(sel):
             uring.get_ranges_arrays(p, off[sel].astype(np.int64), (off[sel] + nb[sel]).astype(np.int64), (np.uint64(i) << np.uint64(32)) | sel.astype(np.uint64))

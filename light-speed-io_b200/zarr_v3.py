@@ -69,6 +69,9 @@ class ShardedArray:
         self.inner_per_shard = tuple(s // i for s, i in zip(self.shard_shape, self.inner_shape))
         self.n_inner = int(np.prod(self.inner_per_shard))
         self.inner_nbytes = int(np.prod(self.inner_shape)) * self.dtype.itemsize
+        if self.inner_nbytes % 16:
+            raise UnsupportedZarr(f"inner chunks of {self.inner_nbytes} bytes: the codec pipeline works in 16-byte vectors (decoded size must be a multiple of 16)")
+        self.is_bool = meta["data_type"] == "bool"
         self.pipeline_codecs = self._inner_codecs(cfg["codecs"])
 
     def _inner_codecs(self, chain):
@@ -135,26 +138,42 @@ class ShardedArray:
         torch_dtype = getattr(torch, self.dtype.name)
         out = torch.full((n, self.inner_nbytes // self.dtype.itemsize), self.fill_value, dtype=torch_dtype, device=f"cuda:{uring.devices[0]}")
         if paths:
-            total, _ = Z.read_shards(uring, paths, self.n_inner, wanted=wanted, index_crc32c=self.index_crc32c,
-                                     index_location=self.index_location, timeout=timeout)
-            if total:
-                rx = uring.completion()
-                recs = []
-                while sum(len(r) for r in recs) < total:
-                    recs.append(rx.recv_batch(total - sum(len(r) for r in recs), timeout=timeout))
-                rec = np.concatenate(recs)
-                pipe = C.CodecPipeline(self.pipeline_codecs, self.inner_nbytes, device=uring.devices[0], max_batch=total)
+            rx = uring.completion()
+            dev = out.device
+            # Shards are read and decoded in bounded sub-batches: the compressed chunks of one sub-batch are all resident at
+            # once (they are dropped only after decoding), so a sub-batch never asks for more than a fraction of the arena.
+            per_shard = [len(w) for w in wanted]
+            max_chunks = max(1, int(getattr(uring, "arena_bytes", 1 << 30) // 2 // max(1, self.inner_nbytes)))
+            start = 0
+            while start < len(paths):
+                stop, cnt = start, 0
+                while stop < len(paths) and (stop == start or cnt + per_shard[stop] <= max_chunks):
+                    cnt += per_shard[stop]
+                    stop += 1
+                got = []
                 try:
-                    decoded = pipe.decode_records(rec)
+                    total, _ = Z.read_shards(uring, paths[start:stop], self.n_inner, wanted=wanted[start:stop], index_crc32c=self.index_crc32c,
+                                             index_location=self.index_location, timeout=timeout)
+                    if total:
+                        while sum(len(r) for r in got) < total:
+                            got.append(rx.recv_batch(total - sum(len(r) for r in got), timeout=timeout).copy())
+                        rec = np.concatenate(got)
+                        pipe = C.CodecPipeline(self.pipeline_codecs, self.inner_nbytes, device=uring.devices[0], max_batch=total)
+                        try:
+                            decoded = pipe.decode_records(rec)
+                        finally:
+                            pipe.close()
+                        # rows of `out` for every decoded chunk: user_data = shard number (in this sub-batch) << 32 | index within the shard
+                        src, dest = [], []
+                        for k, u in enumerate(rec["chunk"]["user_data"].tolist()):
+                            r = rows[start + (u >> 32)][u & 0xFFFFFFFF]
+                            src += [k] * len(r)
+                            dest += r.tolist()
+                        out[torch.tensor(dest, dtype=torch.long, device=dev)] = decoded.view(torch_dtype)[torch.tensor(src, dtype=torch.long, device=dev)]
                 finally:
-                    pipe.close()
-                    type(rx).drop_buffers(rec)
-                # rows of `out` for every decoded chunk: user_data = shard number (in `paths`) << 32 | index within the shard
-                src, dest = [], []
-                for k, u in enumerate(rec["chunk"]["user_data"].tolist()):
-                    r = rows[u >> 32][u & 0xFFFFFFFF]
-                    src += [k] * len(r)
-                    dest += r.tolist()
-                dev = out.device
-                out[torch.tensor(dest, dtype=torch.long, device=dev)] = decoded.view(torch_dtype)[torch.tensor(src, dtype=torch.long, device=dev)]
+                    for r in got:  # also on errors: nothing of this sub-batch stays on the backend
+                        type(rx).drop_buffers(r)
+                start = stop
+        if self.is_bool:
+            out = out != 0
         return out.reshape(n, *self.inner_shape)

@@ -469,3 +469,20 @@ def test_zarr_v3_sharded_array_by_chunk_coordinates(lsio, oracle, cuda_dev, data
         # a second read on the same backend (groups keep counting), a single chunk
         one = arr.read_inner_chunks(u, [(0, 0)])
         assert np.array_equal(one[0].cpu().numpy(), expect[0:8, 0:16])
+    # a small arena forces the read into several sub-batches of shards (compressed chunks stay resident until decoded)
+    with lsio.IoUringCuda(2, arena_bytes=1 << 20, staging_bytes=16 << 20) as u:
+        u.arena_bytes = 4096  # pretend: at most 4 inner chunks (512 B each) per sub-batch
+        tiles = arr.read_inner_chunks(u, ask)
+        for t, (i, j) in zip(tiles.cpu().numpy(), ask):
+            assert np.array_equal(t, expect[i * 8:(i + 1) * 8, j * 16:(j + 1) * 16]), (i, j)
+    # a corrupted shard index: refused with ShardIndexError, and the backend is left clean (the next read works)
+    bad = os.path.join(root, "c", "0", "1")
+    blob = bytearray(open(bad, "rb").read())
+    blob[-10] ^= 0x40
+    with open(bad, "wb") as fh:
+        fh.write(blob)
+    with lsio.IoUringCuda(2, arena_bytes=64 << 20, staging_bytes=16 << 20) as u:
+        with pytest.raises(lsio.zarr_shard.ShardIndexError):
+            arr.read_inner_chunks(u, ask)
+        again = arr.read_inner_chunks(u, [(0, 0), (1, 1)])
+        assert np.array_equal(again[0].cpu().numpy(), expect[0:8, 0:16]) and np.array_equal(again[1].cpu().numpy(), expect[8:16, 16:32])

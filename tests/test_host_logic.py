@@ -389,3 +389,11 @@ def test_zarr_v3_sharded_array_metadata(lsio, tmp_path):
     _write_zarr_json(d, codecs=meta["codecs"])
     with pytest.raises(ZV.UnsupportedZarr, match="zstd"):
         ZV.ShardedArray(d)
+    # inner chunks whose decoded size is not a multiple of 16 bytes are refused by name (the pipeline works in 16-byte vectors)
+    meta = _write_zarr_json(d)
+    meta["codecs"][0]["configuration"]["chunk_shape"] = [2, 3]
+    _write_zarr_json(d, data_type="uint8", codecs=meta["codecs"], chunk_grid={"name": "regular", "configuration": {"chunk_shape": [32, 48]}})
+    with pytest.raises(ZV.UnsupportedZarr, match="multiple of 16"):
+        ZV.ShardedArray(d)
+    _write_zarr_json(d, data_type="bool")
+    assert ZV.ShardedArray(d).is_bool

@@ -1,57 +1,82 @@
-// Micro-benchmark (not product code): which global access pattern gets closest to the HBM copy peak?
-//   A: each warp streams its own contiguous TILE (what pack_kernel does), tiles dealt round-robin
-//   B: the warps of a CTA take adjacent 512 B rows of one CTA-wide region (interleaved rows)
-//   C: classic grid-stride vector copy with a huge grid (what the library copy kernels do)
+// copy_pattern_bench.cu -- micro-benchmark (not product code): which way of walking memory gets a plain 8 GiB copy closest to
+// the HBM copy peak?  The finding behind pack_kernel's tile scheduler.  One file, four patterns:
+//   grid    classic grid-stride vector copy over a huge grid (what library copy kernels do)
+//   chunk   the same body launched once per chunk: the HARDWARE block scheduler hands out chunks in order      (106 % of peak)
+//   static  persistent (148 x 1024 threads), every warp streams 32 KiB tiles dealt round robin                 (91-95 %)
+//   dynamic persistent, every warp takes the NEXT tile from a global counter, tile size swept                   (101 % at 32 KiB)
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a tools/copy_pattern_bench.cu -o tools/copy_pattern_bench && tools/copy_pattern_bench [pattern ...]
 #include <cuda_runtime.h>
-#include <cstdio>
+
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
 __device__ __forceinline__ uint4 ld(const uint4* p) { uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r; }
 __device__ __forceinline__ void st(uint4* p, uint4 v) { asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
-template <int U> __device__ __forceinline__ void copy_rows(const uint4* s, uint4* d, size_t v0, size_t stride_vec, int nrows, int lane) {
-    for (int r = 0; r + U <= nrows; r += U) {
+__global__ void fill(uint4* p, size_t n) { for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { uint32_t x = (uint32_t)(i * 2654435761u); p[i] = make_uint4(x, x * 3 + 1, x ^ 0x9e3779b9u, x * 7); } }
+
+template <int ROWS, int U> __device__ __forceinline__ void copy_tile(const uint4* s, uint4* d, size_t v0, int lane) {
+    for (int r = 0; r < ROWS; r += U) {
         uint4 x[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) x[u] = ld(s + v0 + (size_t)(r + u) * stride_vec + lane);
+        for (int u = 0; u < U; u++) x[u] = ld(s + v0 + (size_t)(r + u) * 32 + lane);
 #pragma unroll
-        for (int u = 0; u < U; u++) st(d + v0 + (size_t)(r + u) * stride_vec + lane, x[u]);
+        for (int u = 0; u < U; u++) st(d + v0 + (size_t)(r + u) * 32 + lane, x[u]);
     }
 }
-template <int ROWS> __global__ void __launch_bounds__(1024, 1) pat_a(const uint4* s, uint4* d, size_t ntiles) {
+// dynamic: each warp grabs tiles of ROWS rows (512 B each) from a global counter
+template <int ROWS, int U> __global__ void __launch_bounds__(1024, 1) warp_dyn(const uint4* s, uint4* d, unsigned ntiles, unsigned* counter) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(counter, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= ntiles) break;
+        copy_tile<ROWS, U>(s, d, (size_t)t * ROWS * 32, lane);
+    }
+}
+// static: tiles dealt round robin over the persistent warps
+template <int ROWS, int U> __global__ void __launch_bounds__(1024, 1) warp_static(const uint4* s, uint4* d, unsigned ntiles) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (size_t t = blockIdx.x + (size_t)warp * gridDim.x; t < ntiles; t += (size_t)gridDim.x * 32) copy_rows<4>(s, d, t * ROWS * 32, 32, ROWS, lane);
+    for (unsigned t = blockIdx.x + warp * gridDim.x; t < ntiles; t += gridDim.x * 32) copy_tile<ROWS, U>(s, d, (size_t)t * ROWS * 32, lane);
 }
-template <int ROWS> __global__ void __launch_bounds__(1024, 1) pat_b(const uint4* s, uint4* d, size_t nregions) {  // region = 32 warps x ROWS rows
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (size_t t = blockIdx.x; t < nregions; t += gridDim.x) copy_rows<4>(s, d, t * ROWS * 32 * 32 + (size_t)warp * 32, 32 * 32, ROWS, lane);
+// chunk: one CTA per 1 MiB chunk (32 warps x one 32 KiB tile), handed out by the hardware block scheduler
+template <int U> __global__ void __launch_bounds__(1024, 1) cta_chunk(const uint4* s, uint4* d) {
+    copy_tile<64, U>(s, d, ((size_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * 64 * 32, threadIdx.x & 31);
 }
-__global__ void __launch_bounds__(256) pat_c(const uint4* s, uint4* d, size_t nvec) {
-    size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x);
-    const size_t base = (size_t)blockIdx.x * 256 * 4 + threadIdx.x;
-    uint4 x[4];
+// grid: grid-stride copy, 4 vectors in flight per thread
+__global__ void __launch_bounds__(256) grid_stride(const uint4* s, uint4* d, size_t nvec) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 3 * stride < nvec; i += 4 * stride) {
+        uint4 x[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) x[u] = base + u * 256 < nvec ? ld(s + base + u * 256) : make_uint4(0, 0, 0, 0);
+        for (int u = 0; u < 4; u++) x[u] = ld(s + i + u * stride);
 #pragma unroll
-    for (int u = 0; u < 4; u++) if (base + u * 256 < nvec) st(d + base + u * 256, x[u]);
-    (void)i;
+        for (int u = 0; u < 4; u++) st(d + i + u * stride, x[u]);
+    }
 }
-int main() {
+int main(int argc, char** argv) {
     const size_t bytes = 8ull << 30, nvec = bytes / 16;
-    uint4 *s, *d; cudaMalloc(&s, bytes); cudaMalloc(&d, bytes); cudaMemset(s, 1, bytes); cudaMemset(d, 0, bytes);
+    uint4 *s, *d; cudaMalloc(&s, bytes); cudaMalloc(&d, bytes); fill<<<148 * 8, 256>>>(s, nvec); cudaMemset(d, 0, bytes);
+    unsigned* ctr; cudaMalloc(&ctr, 4);
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    auto want = [&](const char* p) { if (argc < 2) return true; for (int i = 1; i < argc; i++) if (!strcmp(argv[i], p)) return true; return false; };
     auto report = [&](const char* name, auto launch) {
         for (int i = 0; i < 3; i++) launch();
         cudaEventRecord(a); for (int i = 0; i < 10; i++) launch(); cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b); ms /= 10;
-        printf("%-34s %7.3f ms  %7.1f GB/s  %5.1f%% of 6538.9\n", name, ms, 2.0 * bytes / ms / 1e6, 2.0 * bytes / ms / 1e6 / 6538.9 * 100);
+        cudaError_t e = cudaGetLastError();
+        printf("%-44s %7.3f ms  %7.1f GB/s  %5.1f%% of 6538.9  %s\n", name, ms, 2.0 * bytes / ms / 1e6, 2.0 * bytes / ms / 1e6 / 6538.9 * 100, e ? cudaGetErrorString(e) : "");
     };
-    report("cudaMemcpy D2D", [&] { cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice); });
-    report("A per-warp 16 KiB tiles", [&] { pat_a<32><<<148, 1024>>>(s, d, nvec / (32 * 32)); });
-    report("A per-warp 32 KiB tiles", [&] { pat_a<64><<<148, 1024>>>(s, d, nvec / (64 * 32)); });
-    report("A per-warp 128 KiB tiles", [&] { pat_a<256><<<148, 1024>>>(s, d, nvec / (256 * 32)); });
-    report("B CTA-interleaved, 4 rows/warp", [&] { pat_b<4><<<148, 1024>>>(s, d, nvec / (4 * 32 * 32)); });
-    report("B CTA-interleaved, 16 rows/warp", [&] { pat_b<16><<<148, 1024>>>(s, d, nvec / (16 * 32 * 32)); });
-    report("B CTA-interleaved, 64 rows/warp", [&] { pat_b<64><<<148, 1024>>>(s, d, nvec / (64 * 32 * 32)); });
-    report("B x2 CTAs/SM? (grid 296)", [&] { pat_b<16><<<296, 1024>>>(s, d, nvec / (16 * 32 * 32)); });
-    report("C grid-stride 256 thr, huge grid", [&] { pat_c<<<(unsigned)(nvec / 1024), 256>>>(s, d, nvec); });
+    const unsigned nt64 = (unsigned)(nvec / (64 * 32));
+    if (want("grid")) report("grid-stride, 148*32 CTAs of 256", [&] { grid_stride<<<148 * 32, 256>>>(s, d, nvec); });
+    if (want("chunk")) report("one CTA per 1 MiB chunk (hardware scheduler)", [&] { cta_chunk<4><<<nt64 / 32, 1024>>>(s, d); });
+    if (want("static")) report("static  64 rows (32 KiB tiles), U=4", [&] { warp_static<64, 4><<<148, 1024>>>(s, d, nt64); });
+    if (want("dynamic")) {
+        report("dynamic 64 rows (32 KiB tiles), U=4", [&] { cudaMemsetAsync(ctr, 0, 4); warp_dyn<64, 4><<<148, 1024>>>(s, d, nt64, ctr); });
+        report("dynamic 16 rows (8 KiB tiles), U=4", [&] { cudaMemsetAsync(ctr, 0, 4); warp_dyn<16, 4><<<148, 1024>>>(s, d, (unsigned)(nvec / (16 * 32)), ctr); });
+        report("dynamic 4 rows (2 KiB tiles), U=4", [&] { cudaMemsetAsync(ctr, 0, 4); warp_dyn<4, 4><<<148, 1024>>>(s, d, (unsigned)(nvec / (4 * 32)), ctr); });
+        report("dynamic 256 rows (128 KiB tiles), U=4", [&] { cudaMemsetAsync(ctr, 0, 4); warp_dyn<256, 4><<<148, 1024>>>(s, d, (unsigned)(nvec / (256 * 32)), ctr); });
+        report("dynamic 64 rows, U=8", [&] { cudaMemsetAsync(ctr, 0, 4); warp_dyn<64, 8><<<148, 1024>>>(s, d, nt64, ctr); });
+    }
     return 0;
 }
