@@ -269,7 +269,7 @@ def backend(args, dev, workers=None, **over):
               merge_ranges=args.merge_ranges, zero_copy=args.zero_copy, poll_sleep_us=args.poll_sleep_us, staging_mode=args.staging_mode,
               host_slots_per_worker=args.host_slots, host_slot_kib=args.host_slot_kib, statx_via_ring=args.statx_via_ring,
               inline_reads=args.inline_reads, direct_landing=args.direct_landing, steal_batch=args.steal_batch,
-              pack_light_below_mib=args.pack_light_below_mib, completion_bound=args.completion_bound, copy_coalesce_slots=args.copy_coalesce_slots, window_budget_kib=args.window_budget_kib)
+              pack_light_below_mib=args.pack_light_below_mib, completion_bound=args.completion_bound, copy_coalesce_slots=args.copy_coalesce_slots, window_budget_kib=args.window_budget_kib, pull_any_shift=args.pull_any_shift)
     if args.pin and args.cpu_count:
         kw.update(cpu_first=args.cpu_first, cpu_count=args.cpu_count)
     kw.update(over)
@@ -815,6 +815,7 @@ def main():
     ap.add_argument("--steal-batch", type=int, default=8)
     ap.add_argument("--completion-bound", type=int, default=0)
     ap.add_argument("--copy-coalesce-slots", type=int, default=2)
+    ap.add_argument("--pull-any-shift", type=int, default=1)
     ap.add_argument("--window-budget-kib", type=int, default=0, help="pinned slot windows of one rank together (0 = 60 %% of the L3 / number of ranks)")
     ap.add_argument("--deal", type=int, default=1, help="1 = ranks own disjoint physical files (default), 0 = logical file j is physical file j %% files")
     ap.add_argument("--pin", type=int, default=1, help="N > 1: pin every rank's backend threads to its own slice of the CPUs")

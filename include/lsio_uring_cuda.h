@@ -121,6 +121,10 @@ typedef struct lsio_uring_cuda_config {
                                    GPU reads it back (otherwise each payload byte costs three extra DRAM transfers).
                                    0 (default) = 60 % of the L3 reported by sysfs, divided by the number of devices of this
                                    backend; one process per GPU on a shared host: pass this process's share                  */
+    uint32_t pull_any_shift;    /* direct_landing 2: 1 (default) = extents whose segments sit at a different offset mod 16 in the slot than
+                                   in the request buffer (unaligned ranges) are pulled too: each destination vector then needs two
+                                   source loads, but the second one hits the L2 line the first one brought in, so the bytes still
+                                   cross PCIe once; 0 = only congruent segments are pulled, the rest goes ring -> pack kernel          */
 } lsio_uring_cuda_config;
 
 typedef struct lsio_uring_cuda_stats {

@@ -149,7 +149,7 @@ class CConfig(ctypes.Structure):
                 ("inline_reads", ctypes.c_uint32), ("force_align", ctypes.c_uint32), ("debug_short_read_every", ctypes.c_uint32),
                 ("null_source", ctypes.c_uint32), ("direct_landing", ctypes.c_uint32), ("cpu_first", ctypes.c_uint32),
                 ("cpu_count", ctypes.c_uint32), ("steal_batch", ctypes.c_uint32), ("pack_light_below_mib", ctypes.c_uint32),
-                ("copy_coalesce_slots", ctypes.c_uint32), ("window_budget_kib", ctypes.c_uint32)]
+                ("copy_coalesce_slots", ctypes.c_uint32), ("window_budget_kib", ctypes.c_uint32), ("pull_any_shift", ctypes.c_uint32)]
 
 
 class CStats(ctypes.Structure):

@@ -273,6 +273,7 @@ void lsio_uring_cuda_config_default(lsio_uring_cuda_config* cfg) {
     cfg->pack_light_below_mib = 512;
     cfg->copy_coalesce_slots = 2;
     cfg->window_budget_kib = 0;
+    cfg->pull_any_shift = 1;
 }
 
 int lsio_uring_cuda_new_with_config(const lsio_uring_cuda_config* cfgp, lsio_uring_cuda** out) {

@@ -140,7 +140,7 @@ struct Worker {
                 sg.src = (uint64_t)(uintptr_t)(sdev + r.off + sp.head);
                 sg.dst = (uint64_t)(uintptr_t)(r.req->buffer->buf + sp.dst_off);
                 sg.len = sp.payload_len;
-                if ((sg.src - sg.dst) & 15) return false;
+                if (((sg.src - sg.dst) & 15) && !be->cfg.pull_any_shift) return false;
                 payload += sp.payload_len;
             }
         }

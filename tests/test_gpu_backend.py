@@ -864,6 +864,19 @@ def test_pull_and_coalesced_landing_of_block_reads(lsio, oracle, cuda_dev, data_
                 assert st["direct_extents"] > 0 and st["pull_launches"] == 0
 
 
+@pytest.mark.parametrize("pull_any_shift", [1, 0])
+def test_unaligned_ranges_through_the_pull_kernel(lsio, oracle, cuda_dev, data_dir, pull_any_shift):
+    """C3-shaped ranges (arbitrary offsets and lengths, EOF and negative ranges): with pull_any_shift the extents are pulled
+    although their bytes sit at another offset mod 16 in the slot than in the request buffer; without it they go ring -> pack
+    kernel.  Same bytes and CRCs as the oracle either way."""
+    fns, per = _c3_sample(oracle, data_dir)
+    st = _land_and_check(lsio, oracle, fns, per, direct_landing=2, pull_any_shift=pull_any_shift)
+    if pull_any_shift:
+        assert st["pull_launches"] > 0 and st["pack_launches"] == 0
+    else:
+        assert st["pack_launches"] > 0
+
+
 def test_consecutive_slots_are_copied_with_one_call(lsio, oracle, cuda_dev, data_dir):
     """direct_landing 1: one worker walking one file fills consecutive slots with consecutive bytes of the request buffer;
     copy_coalesce_slots of them leave with ONE cudaMemcpyAsync (the copy engine loses a fixed ~3.8 us per copy)."""
