@@ -770,6 +770,33 @@ def disk_leg(args, dev):
     return out
 
 
+def unloaded_latency(args, dev, paths, expect, n_requests=300):
+    """What one request costs when nothing else is in flight (what a data loader that asks for one sample at a time sees):
+    get_ranges of 8 consecutive 256 KiB blocks (2 MiB) of one file, wait for its 8 chunks, check their CRCs, drop them, next."""
+    from lsio_b200.io_uring_cuda import Receiver
+
+    starts, ends = chunk_ranges()
+    lat = []
+    with backend(args, dev) as u:
+        rx = u.completion()
+        for i in range(n_requests + 20):
+            f, k0 = i % len(paths), (7 * i) % (N_CHUNKS - 8)
+            ud = (np.uint64(f) << np.uint64(32)) | np.arange(k0, k0 + 8, dtype=np.uint64)
+            t0 = time.perf_counter()
+            u.get_ranges_arrays(paths[f], starts[k0:k0 + 8], ends[k0:k0 + 8], ud)
+            got = 0
+            while got < 8:
+                rec = rx.recv_batch(8 - got, 30.0)
+                assert (rec["status"] == 0).all() and (rec["crc32c"] == expect[f, (rec["chunk"]["user_data"] & np.uint64(0xFFFFFFFF)).astype(np.int64)]).all()
+                got += len(rec)
+                Receiver.drop_buffers(rec)
+            if i >= 20:
+                lat.append(time.perf_counter() - t0)
+    lat = np.sort(np.array(lat)) * 1e3
+    return {"requests": n_requests, "bytes_per_request": 8 * BLOCK, "mean_ms": float(lat.mean()), "p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]),
+            "min_ms": float(lat[0]), "is": "one get_ranges of 8 x 256 KiB at a time through the Python mirror: submit -> 8 chunks received, CRC-checked and dropped"}
+
+
 def two_device_check(args, n_files, paths, expect):
     """Single-process multi-device mode (one backend, two worker groups, files dealt round robin) on GPUs 0 and 1."""
     import torch
@@ -966,6 +993,10 @@ def main():
                     extra["two_devices_one_process"] = {"error": repr(ex)}
             barrier()
         if n_gpus == 1:
+            try:
+                extra["unloaded_latency"] = unloaded_latency(args, dev, paths, expect)
+            except Exception as ex:
+                extra["unloaded_latency"] = {"error": repr(ex)}
             try:
                 extra["c3"] = c3_leg(args, dev, rank, n_gpus, directory)
             except Exception as ex:

@@ -1,6 +1,8 @@
 // device_stage.cpp -- the per-GPU device thread: batches published extents in log order, launches
 // pack_strip_crc32c (+ the optional XXH64 stage), retires batches and emits one Chunk per range.
 // No counterpart in the reference: this is the stage inserted after the read CQE.
+#include <sys/prctl.h>
+
 #include "backend.hpp"
 
 namespace lsio {
@@ -236,6 +238,7 @@ void device_main(Group& g) {
         pthread_setaffinity_np(pthread_self(), sizeof set, &set);
     }
     cudaSetDevice(g.device);
+    prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // poll_sleep_us means what it says (default slack: +50 us per sleep)
     const uint64_t cap = g.log.capacity();
     const size_t max_segs = g.batches[0].lay.max_segs, max_tiles = g.batches[0].lay.max_tiles;  // >= 2 extents' worth: see backend.hpp
     const uint64_t max_batch_bytes = std::max<uint64_t>(cfg.min_copy_bytes * 4, 64ull << 20);
@@ -286,7 +289,7 @@ void device_main(Group& g) {
             uint64_t s = g.copy_seq, bytes = 0, run_phys0 = g.log.at(s).log_off % cap;
             size_t nsegs = 0, ntiles = 0;
             uint64_t oldest = 0, newest = 0;
-            bool hit_limit = false;
+            bool hit_limit = false, needs_kernel = false;
             for (; s < avail; s++) {
                 StageEntry& e = g.log.at(s);
                 const uint32_t st = e.state.load(std::memory_order_acquire);
@@ -305,12 +308,16 @@ void device_main(Group& g) {
                 }
                 nsegs += ns;
                 ntiles += t;
+                needs_kernel |= ns && !e.pulled && !(e.direct && !(cfg.checksum & LSIO_CHECKSUM_CRC32C));
                 bytes = e.log_off + e.len - g.log.at(g.copy_seq).log_off;
             }
             if (s > g.copy_seq) {
                 const bool draining = g.stop_device.load(std::memory_order_relaxed);
                 const uint64_t now = now_ns();
-                const bool timed_out = oldest && now - oldest > (uint64_t)cfg.flush_us * 1000;
+                // a run that launches nothing (every extent was moved and checksummed by the pull kernel) gains nothing from
+                // growing: it only waits long enough to share its event waits and its wake-up of the consumer
+                const uint64_t wait_us = needs_kernel ? cfg.flush_us : std::min<uint32_t>(cfg.flush_us, 200);
+                const bool timed_out = oldest && now - oldest > wait_us * 1000;
                 // Nothing else is being read and nothing has landed for a moment: the burst is over, do not make a
                 // lone request wait out flush_us (batches are kept large only while extents keep arriving).
                 const bool idle = s == avail && newest && now - newest > (uint64_t)std::min<uint32_t>(cfg.flush_us, 100) * 1000;
