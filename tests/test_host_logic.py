@@ -43,6 +43,18 @@ def test_backend_fails_loudly_without_a_gpu(lsio):
         lsio.IoUringCuda(2)
 
 
+@pytest.mark.parametrize("bad,what", [
+    (dict(direct_landing=3), "direct_landing"), (dict(inline_reads=3), "inline_reads"), (dict(copy_coalesce_slots=9), "copy_coalesce_slots"),
+    (dict(force_align=1000), "force_align"), (dict(force_align=256), "force_align"), (dict(force_align=1 << 20), "force_align"),
+    (dict(host_slot_kib=8192, staging_bytes=4 << 20), "staging_bytes / 2"), (dict(host_slots_per_worker=300), "host_slots_per_worker"),
+    (dict(sq_entries=48), "invalid"), (dict(max_read_bytes=100), "invalid"), (dict(pack_threads=100), "invalid")])
+def test_config_is_validated_before_any_device_is_touched(lsio, bad, what):
+    """Round-2 knobs: values that cannot work are refused with EINVAL and a message that names the field -- with or without a GPU
+    (validation comes first); a slot larger than half the staging ring used to stall every read silently."""
+    with pytest.raises(lsio._native.LsioCudaError, match=what):
+        lsio.IoUringCuda(2, **bad)
+
+
 def test_product_never_references_the_oracle():
     """The oracle is test infrastructure: nothing under the package may import, link or load it."""
     pkg = os.path.join(ROOT, "light-speed-io_b200")
