@@ -249,12 +249,15 @@ def llc_bytes():
 
 
 # ---- backend construction ----------------------------------------------------------------------------
-def cpu_slice(rank, world):
-    """Disjoint CPU slice of this rank (one process per GPU on a shared box), or (0, 0) when alone / not contiguous."""
+def cpu_slice(rank, world, reverse=False):
+    """Disjoint CPU slice of this rank (one process per GPU on a shared box), or (0, 0) when alone / not contiguous.
+    reverse: rank r takes the slice of rank world-1-r (experiment: does a rank's speed follow its GPU or its CPUs?)."""
     cpus = sorted(os.sched_getaffinity(0))
     if world <= 1:
         return 0, 0, len(cpus)
     per = len(cpus) // world
+    if reverse:
+        rank = world - 1 - rank
     mine = cpus[rank * per:(rank + 1) * per]
     if not mine or mine != list(range(mine[0], mine[0] + len(mine))):
         return 0, 0, per
@@ -845,7 +848,7 @@ def main():
     ap.add_argument("--pull-any-shift", type=int, default=1)
     ap.add_argument("--window-budget-kib", type=int, default=0, help="pinned slot windows of one rank together (0 = 60 %% of the L3 / number of ranks)")
     ap.add_argument("--deal", type=int, default=1, help="1 = ranks own disjoint physical files (default), 0 = logical file j is physical file j %% files")
-    ap.add_argument("--pin", type=int, default=1, help="N > 1: pin every rank's backend threads to its own slice of the CPUs")
+    ap.add_argument("--pin", type=int, default=1, help="N > 1: 1 = pin every rank's backend threads to its own slice of the CPUs, 2 = slices handed out in reverse rank order, 0 = no pinning")
     ap.add_argument("--zero-copy", type=int, default=0, help="1 = the pack kernel reads the pinned ring over PCIe (no H2D memcpy)")
     ap.add_argument("--statx-via-ring", type=int, default=0, help="1 = the reference's openat+statx SQE pair per file")
     ap.add_argument("--disk-dir", default="/tmp/lsio_bench_disk", help="secondary e2e leg on a disk-backed directory ('' disables)")
@@ -876,7 +879,7 @@ def main():
 
     rank, world, local = dist_env()
     n_gpus = max(world, 1)
-    args.cpu_first, args.cpu_count, cpus_per_rank = cpu_slice(rank, n_gpus)
+    args.cpu_first, args.cpu_count, cpus_per_rank = cpu_slice(rank, n_gpus, args.pin == 2)
     if args.workers <= 0:
         # reads of memory-backed files run ON the worker (inline preadv2): one worker per CPU of this rank's share;
         # alone on the box a couple of CPUs stay free for the consumer and the device thread
