@@ -9,7 +9,7 @@ for l in open(sys.argv[1]):
         d = json.loads(l); pw = d["per_worker_rank0"]; pr = d["pipeline_rank0"]
         print("   gib_s=%.2f  read/thr=%s reading=%.2f wait=%.2f  copies=%d direct=%d stalls=%s/%s p50=%s pk=%s" % (d["gib_s"], pw.get("inline_read_gib_s_per_thread") and round(pw["inline_read_gib_s_per_thread"], 2),
               pw["frac_of_awake_time_reading"], pw["frac_of_awake_time_waiting_for_slots_or_hbm"], pr["h2d_copies"], pr["direct_extents"], pr["staging_stalls"], pr["arena_stalls"],
-              d["latency_rank0"].get("p50_ms"), d.get("pipeline_kernel") and round(d["pipeline_kernel"]["frac"], 3)))
+              d["latency_rank0"].get("p50_ms"), (d.get("pipeline_kernel") or {}).get("pack_kernel", {}).get("frac")))
     except Exception as e: print("   ??", l[:200])
 PY
 exit 0; fi
