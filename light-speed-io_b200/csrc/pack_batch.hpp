@@ -41,7 +41,10 @@ int pack_batch_upload(const PackBatchLayout& lay, const void* host_block, void* 
 // `crc_out_dev`: device-visible address of n words (may be mapped host memory), unused without `crc`.
 constexpr uint32_t kPullMaxSegs = 64;
 size_t pack_pull_scratch_bytes(size_t slot_bytes);
-int pack_pull_launch(int device, const lsio_cuda_segment* segs, uint32_t n, bool crc, void* scratch_dev, uint32_t* crc_out_dev, cudaStream_t stream);
+uint32_t pack_pull_max_tiles(size_t slot_bytes);  // tiles (partials) that scratch holds; segments may overlap in the slot, so payload > slot is possible
+// -E2BIG when the segments need more than `max_tiles` tiles (nothing is launched: take another path).
+int pack_pull_launch(int device, const lsio_cuda_segment* segs, uint32_t n, bool crc, void* scratch_dev, uint32_t max_tiles, uint32_t* crc_out_dev,
+                     cudaStream_t stream);
 
 // One-time per-device set-up (GF(2) tables to the device, kernel attributes). 0 or error code.
 int pack_prepare_device(int device);

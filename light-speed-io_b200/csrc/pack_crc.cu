@@ -643,10 +643,17 @@ bool pack_batch_append(const PackBatchLayout& lay, void* host_block, PackBatchCo
     return true;
 }
 
-size_t pack_pull_scratch_bytes(size_t slot_bytes) { return (2 + kPullMaxSegs + slot_bytes / kTileBytes + 2 * kPullMaxSegs) * sizeof(uint32_t); }
+// Tiles one pull launch may carry: the segments of an extent can overlap in the SLOT (many ranges over the same bytes), so the payload
+// -- and with it the number of tiles and partials -- is not bounded by the slot size.  Four times the slot plus the per-segment edge
+// tiles, at least 1024; a launch that needs more is refused (-E2BIG) and the caller takes the ring path.
+uint32_t pack_pull_max_tiles(size_t slot_bytes) { return (uint32_t)std::max<size_t>(1024, 4 * (slot_bytes / kTileBytes) + 2 * kPullMaxSegs); }
+size_t pack_pull_scratch_bytes(size_t slot_bytes) { return (2 + kPullMaxSegs + (size_t)pack_pull_max_tiles(slot_bytes)) * sizeof(uint32_t); }
 
-int pack_pull_launch(int device, const lsio_cuda_segment* segs, uint32_t n, bool crc, void* scratch_dev, uint32_t* crc_out_dev, cudaStream_t st) {
+int pack_pull_launch(int device, const lsio_cuda_segment* segs, uint32_t n, bool crc, void* scratch_dev, uint32_t max_tiles, uint32_t* crc_out_dev, cudaStream_t st) {
     if (!segs || n == 0 || n > kPullMaxSegs || !scratch_dev) return -EINVAL;
+    uint64_t want_tiles = 0;
+    for (uint32_t i = 0; i < n; i++) want_tiles += pack_tile_count(segs[i].dst, segs[i].len);
+    if (want_tiles > max_tiles) return -E2BIG;
     const uint32_t* tables;
     int sms;
     int rc = get_device_tables(device, &tables, &sms);
@@ -826,7 +833,7 @@ int lsio_cuda_pull_strip_crc32c(int device, const lsio_cuda_segment* segs, size_
     LSIO_CUDA_TRY(cudaMalloc(&scratch, sb));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = (int)cudaMemsetAsync(scratch, 0, sb, st);
-    if (!rc) rc = pack_pull_launch(device, dev_view, (uint32_t)n, crc_out_dev != nullptr, scratch, crc_out_dev, st);
+    if (!rc) rc = pack_pull_launch(device, dev_view, (uint32_t)n, crc_out_dev != nullptr, scratch, pack_pull_max_tiles(bytes + 64 * 32768), crc_out_dev, st);
     const cudaError_t se = cudaStreamSynchronize(st);
     cudaFree(scratch);
     if (rc) return rc;

@@ -129,7 +129,8 @@ struct Worker {
         Backend* be = g.be;
         lsio_cuda_segment segs[kPullMaxSegs];
         uint32_t n = 0;
-        uint64_t payload = 0;
+        uint64_t payload = 0, tiles = 0;
+        const uint32_t max_tiles = pack_pull_max_tiles(g.slot_bytes);
         uint8_t* sdev = slots->base_dev + (uint64_t)slot * g.slot_bytes;
         for (auto& r : ent->reads) {
             if (r.state != kStageLanded) continue;
@@ -142,12 +143,16 @@ struct Worker {
                 sg.len = sp.payload_len;
                 if (((sg.src - sg.dst) & 15) && !be->cfg.pull_any_shift) return false;
                 payload += sp.payload_len;
+                // ranges that overlap in the file share the slot's bytes: the extent's payload can be many times the slot;
+                // beyond what the slot's scratch holds it goes ring -> pack kernel (whose batches are sized for it)
+                tiles += pack_tile_count(sg.dst, sg.len);
+                if (tiles > max_tiles) return false;
             }
         }
         flush_pending();
         const bool want_crc = be->cfg.checksum & LSIO_CHECKSUM_CRC32C;
         const uint64_t t0 = now_ns();
-        int rc = pack_pull_launch(g.device, segs, n, want_crc, slots->scratch[slot], g.pull_crc_dev + (ent->seq % g.n_pull) * kPullMaxSegs, slots->stream);
+        int rc = pack_pull_launch(g.device, segs, n, want_crc, slots->scratch[slot], max_tiles, g.pull_crc_dev + (ent->seq % g.n_pull) * kPullMaxSegs, slots->stream);
         cudaError_t ce = rc ? cudaErrorLaunchFailure : cudaEventRecord(slots->ev[slot], slots->stream);
         c_copy_ns += now_ns() - t0;
         if (ce != cudaSuccess) {

@@ -511,6 +511,12 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                 min_copy_bytes=int(rng.choice([1 << 20, 8 << 20, 64 << 20])), flush_us=int(rng.choice([50, 200, 2000])),
                 pack_threads=int(rng.choice([0, 32, 256, 512, 1024])),
             )
+            rng2 = np.random.default_rng(777 + it)  # round-2 knobs from a second stream: the first stream's sequence stays what it was
+            cfg.update(direct_landing=int(rng2.integers(0, 3)), inline_reads=int(rng2.integers(0, 3)), pull_any_shift=int(rng2.integers(0, 2)),
+                       copy_coalesce_slots=int(rng2.choice([1, 2, 4])), steal_batch=int(rng2.choice([1, 8])), pack_light_below_mib=int(rng2.choice([0, 512])),
+                       force_align=int(rng2.choice([0, 0, 4096])), debug_short_read_every=int(rng2.choice([0, 0, 5])))
+            if rng2.integers(0, 3) == 0:  # automatic slot geometry from a window budget
+                cfg.update(host_slots_per_worker=0, host_slot_kib=0, window_budget_kib=int(rng2.choice([512, 4096, 0])))
             expect, group_of = {}, {}
             with lsio.IoUringCuda(int(rng.integers(1, 5)), **cfg) as u:
                 ud = 0
@@ -559,7 +565,12 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
                     assert c.is_ok() == valid, (it, cfg, (s, e), size, c)
                     if valid:
                         want = oracle.pread_range(fn, s, e)
-                        assert np.array_equal(c.buffer.as_slice(), want), (cfg, fn, (s, e))
+                        got_bytes = c.buffer.as_slice()
+                        if not np.array_equal(got_bytes, want):
+                            bad = np.flatnonzero(got_bytes != want) if len(got_bytes) == len(want) else np.array([-1])
+                            raise AssertionError(f"it={it} cfg={cfg} file={fn} size={size} range={(s, e)} resolved={(rr.start_off, rr.end_off)} wrong_bytes={len(bad)} "
+                                                 f"first={int(bad[0])} last={int(bad[-1])} got_at_first={got_bytes[bad[0]:bad[0] + 8].tolist()} stats={u.stats()} "
+                                                 f"request_ranges={[r for k, (f2, _, r) in expect.items() if f2 == fn][:60]}")
                         if cfg["checksum"] & 1:
                             assert c.crc32c == oracle.crc32c(want), (cfg, (s, e))
                         if cfg["checksum"] & 2:
@@ -862,6 +873,29 @@ def test_pull_and_coalesced_landing_of_block_reads(lsio, oracle, cuda_dev, data_
                 assert st["pull_launches"] > 0 and st["h2d_copies"] == 0
             else:
                 assert st["direct_extents"] > 0 and st["pull_launches"] == 0
+
+
+@pytest.mark.parametrize("direct_landing", [2, 1, 0])
+def test_many_overlapping_ranges_over_the_same_bytes(lsio, oracle, cuda_dev, data_dir, direct_landing):
+    """Ranges that overlap in the file share the bytes of one read, so an extent's PAYLOAD can be many times its slot: 33 large
+    overlapping ranges + duplicates of the whole file over two 512 KiB reads (found by the randomised soak: the pull kernel's
+    per-slot scratch was sized by the slot, a launch with more tiles overran it and tiles went missing).  Whatever path such an
+    extent takes, every range holds the oracle's bytes."""
+    fn = os.path.join(data_dir, "overlap")
+    size = 1 << 20
+    oracle.write_file(fn, 960, size)
+    rng = np.random.default_rng(39)
+    rs = [(0, -1), (0, -1), (0, -1), (-2345, -1)]
+    for _ in range(60):
+        n = int(rng.integers(100_000, size))
+        s = int(rng.integers(0, size - n + 1))
+        rs.append((s, s + n))
+    with lsio.IoUringCuda(2, arena_bytes=256 << 20, staging_bytes=32 << 20, direct_landing=direct_landing, host_slot_kib=512, host_slots_per_worker=3,
+                          max_read_bytes=512 << 10) as u:
+        for rep in range(3):
+            u.get_ranges(fn, rs, range(len(rs)))
+            _check_chunks(oracle, _drain(u.completion(), len(rs), 30.0), lambda ud: fn, lambda ud: rs[ud])
+        assert u.stats()["errors"] == 0
 
 
 @pytest.mark.parametrize("pull_any_shift", [1, 0])
