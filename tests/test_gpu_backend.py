@@ -501,7 +501,7 @@ def test_randomized_configurations_stress(lsio, oracle, cuda_dev):
             fn = os.path.join(dirs[i % len(dirs)], f"s{i}")
             oracle.write_file(fn, 5000 + i, size)
             files.append((fn, size))
-        for it in range(int(os.environ.get("LSIO_STRESS_ITERS", 14))):
+        for it in range(int(os.environ.get("LSIO_STRESS_ITERS", 40))):
             cfg = dict(
                 staging_mode=int(rng.integers(0, 2)), host_slots_per_worker=int(rng.integers(1, 6)), host_slot_kib=int(rng.choice([128, 512, 2048])),
                 max_read_bytes=int(rng.choice([4096, 65536, 524288, 4 << 20])), merge_ranges=int(rng.integers(0, 2)),
