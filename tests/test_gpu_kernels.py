@@ -246,3 +246,26 @@ def test_pull_kernel_reads_pinned_host_memory_bit_exact(lsio, oracle, cuda_dev):
         assert np.array_equal(tdst2.cpu().numpy(), want_dst), case
     with pytest.raises(Exception):  # more segments than travel in the kernel parameters
         lsio.cuda_ops.pull_strip_crc32c(hsrc, tdst, np.zeros(65, dtype=np.uint64), np.zeros(65, dtype=np.uint64), np.ones(65, dtype=np.uint64))
+
+
+def test_xxh64_staged_kernel_many_chunks(lsio, oracle, cuda_dev):
+    """Launches of >= 4096 chunks take the bulk-copy (TMA) staged XXH64 kernel: chunks of every length class (empty, < 32 B,
+    exact multiples of the 1 KiB piece and of the 32 B stripe, ragged) at every start alignment mod 16, all compared with the oracle."""
+    import torch
+
+    rng = np.random.default_rng(64)
+    n = 6000
+    lens = rng.choice([0, 1, 31, 32, 33, 63, 64, 1023, 1024, 1025, 1056, 2047, 2048, 2049, 3000, 4096, 20000, 65536, 70001], size=n).astype(np.uint64)
+    lens[:16] = 40000 + np.arange(16, dtype=np.uint64)
+    offs, pos = [], 0
+    for i, ln in enumerate(lens):
+        pos = (pos + 15) // 16 * 16 + (i % 16)  # every alignment mod 16
+        offs.append(pos)
+        pos += int(ln)
+    offs = np.array(offs, dtype=np.uint64)
+    data = rng.integers(0, 256, pos + 64, dtype=np.uint8)
+    buf = torch.from_numpy(data).to(cuda_dev)
+    got = lsio.cuda_ops.xxh64(buf, offs, lens).cpu().numpy().view(np.uint64)
+    want = np.array([oracle.xxh64(data[int(o):int(o + l)]) for o, l in zip(offs, lens)], dtype=np.uint64)
+    bad = np.flatnonzero(got != want)
+    assert len(bad) == 0, (len(bad), [(int(i), int(lens[i]), int(offs[i]) % 16) for i in bad[:10]])
