@@ -248,6 +248,21 @@ def llc_bytes():
     return best or (32 << 20)
 
 
+def deal_files(n_files, rank, n_gpus, mode=1):
+    """Physical file ids rank `rank` lands in one step (always n_files of them: weak scaling).  mode 1: the physical files are dealt
+    file_idx mod n_gpus and a rank walks its own share n_gpus times (no file is read by two ranks); mode 0: logical file j of
+    n_files * n_gpus is physical file j % n_files (round 1; at 8 ranks r and r+4 walk the same files); mode 2: every rank walks all
+    files in the same order (experiment: worst case of sharing)."""
+    from lsio_b200 import sharding
+
+    if mode == 2:
+        return list(range(n_files))
+    if mode:
+        phys = sharding.files_for_rank(n_files, rank, n_gpus)
+        return [phys[i % len(phys)] for i in range(n_files)]
+    return [j % n_files for j in sharding.files_for_rank(n_files * n_gpus, rank, n_gpus)]
+
+
 # ---- backend construction ----------------------------------------------------------------------------
 def cpu_slice(rank, world, reverse=False):
     """Disjoint CPU slice of this rank (one process per GPU on a shared box), or (0, 0) when alone / not contiguous.
@@ -911,13 +926,7 @@ def main():
     # per step, so that no two ranks ever read the same file (two cores hammering the same page-cache folios' reference
     # counts is an artefact a real, n_gpus times larger data set would not have).  --deal 0: the round-1 dealing (logical
     # file j = physical file j % files), which at 8 ranks makes ranks r and r+4 walk the same files in lockstep.
-    if args.deal == 2:  # experiment: every rank walks ALL files in the same order (worst case of sharing)
-        my_ids = list(range(args.files))
-    elif args.deal:
-        phys = sharding.files_for_rank(args.files, rank, n_gpus)
-        my_ids = [phys[i % len(phys)] for i in range(args.files)]
-    else:
-        my_ids = [j % args.files for j in sharding.files_for_rank(args.files * n_gpus, rank, n_gpus)]
+    my_ids = deal_files(args.files, rank, n_gpus, args.deal)
     my_paths = [paths[j] for j in my_ids]
 
     peaks = {}

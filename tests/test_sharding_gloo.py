@@ -55,3 +55,28 @@ def test_two_ranks_shard_and_aggregate():
     assert per0 == per1 == len(os.sched_getaffinity(0)) // 2
     if c0 and c1:
         assert c0 == c1 == per0 and set(range(f0, f0 + c0)).isdisjoint(range(f1, f1 + c1))
+
+
+@pytest.mark.parametrize("n_gpus", [1, 2, 4, 8])
+def test_bench_deals_disjoint_physical_files(n_gpus):
+    """bench.py's weak-scaling shard: every rank lands the same number of files per step, no physical file is read by two ranks,
+    together the ranks cover the whole set, and a rank's walk over its share is balanced (each of its files the same number of
+    times, give or take one)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    n_files = 500
+    shares = [bench.deal_files(n_files, r, n_gpus) for r in range(n_gpus)]
+    assert all(len(s) == n_files for s in shares)
+    sets = [set(s) for s in shares]
+    assert set().union(*sets) == set(range(n_files))
+    for a in range(n_gpus):
+        for b in range(a + 1, n_gpus):
+            assert sets[a].isdisjoint(sets[b])
+    for s in shares:
+        counts = [s.count(f) for f in set(s)]
+        assert max(counts) - min(counts) <= 1
+    # the round-1 dealing, kept selectable, makes ranks r and r+4 share files at 8 ranks -- the reason it was replaced
+    if n_gpus == 8:
+        old = [set(bench.deal_files(n_files, r, 8, mode=0)) for r in range(8)]
+        assert old[0] == old[4] and old[0].isdisjoint(old[1])
