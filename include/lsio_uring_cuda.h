@@ -209,6 +209,15 @@ int lsio_probe_read_ceiling_ex(const char* const* paths, size_t n_paths, uint64_
                                uint32_t queue_depth, uint32_t o_direct, uint32_t inline_reads, uint32_t files_in_flight,
                                double* gib_per_s);
 
+/* Measurement aid: the minimum any host-staged path must do for a memory-backed source, and nothing else -- `n_threads` threads read
+ * the files block by block with preadv2 into a cycle of `slots_per_thread` pinned slots of `slot_kib` and ship every filled slot to
+ * `device` (pull kernel without checksum; use_copy_engine = 1: one cudaMemcpyAsync) into scratch memory.  No requests, planning, arena,
+ * channel or checksums.  cpu_count > 0 pins the threads to [cpu_first, cpu_first + cpu_count).  Returns the wall time and the bytes
+ * shipped; several ranks on one host call it between the same two barriers and add up: what the host can stage AND ship at once. */
+int lsio_probe_staged_ceiling(const char* const* paths, size_t n_paths, int device, uint32_t n_threads, uint32_t slot_kib,
+                              uint32_t slots_per_thread, uint32_t use_copy_engine, uint32_t cpu_first, uint32_t cpu_count, double* seconds,
+                              uint64_t* bytes_out);
+
 /* Test aid: host-logic self tests of the shipped components (tracker, user_data, channel, staging
  * log, arena, GF(2) combine), no GPU needed; see csrc/selftest.cpp. 0 = pass. */
 int lsio_uring_cuda_selftest(int which);

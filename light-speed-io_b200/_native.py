@@ -208,6 +208,11 @@ lib.lsio_probe_read_ceiling_ex.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctyp
                                            ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
 
 
+lib.lsio_probe_staged_ceiling.restype = ctypes.c_int
+lib.lsio_probe_staged_ceiling.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                          ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+
+
 # ---- include/lsio_bench.h -------------------------------------------------------------------------
 class CBenchResult(ctypes.Structure):
     _fields_ = [("seconds", ctypes.c_double), ("chunks_ok", ctypes.c_uint64), ("chunks_bad", ctypes.c_uint64), ("payload_bytes", ctypes.c_uint64)]

@@ -132,4 +132,95 @@ int lsio_probe_read_ceiling_ex(const char* const* paths, size_t n_paths, uint64_
     return 0;
 }
 
+// The minimum any host-staged path must do for a memory-backed source, and nothing else: every thread reads its files block by block
+// with preadv2 into a small cycle of pinned, mapped slots and sends each filled slot to the GPU (pull kernel without checksum, or one
+// cudaMemcpyAsync) into a scratch buffer, waiting only for the slot's previous transfer.  No requests, no planning, no arena, no
+// completion channel, no checksums, nothing is kept.  With several ranks on one host every rank runs it at the same time: the sum is what
+// the host can stage AND ship at once -- the ceiling the pipeline is compared with where the source probe alone (no DMA sharing the
+// memory system) over-promises.
+int lsio_probe_staged_ceiling(const char* const* paths, size_t n_paths, int device, uint32_t n_threads, uint32_t slot_kib, uint32_t slots_per_thread,
+                              uint32_t use_copy_engine, uint32_t cpu_first, uint32_t cpu_count, double* seconds, uint64_t* bytes_out) {
+    if (!paths || !n_paths || !seconds || !bytes_out || !n_threads || !slot_kib || !slots_per_thread || slots_per_thread > 64) return -EINVAL;
+    DeviceGuard dg(device);
+    if (!dg.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice", __FILE__, __LINE__);
+    int rc = pack_prepare_device(device);
+    if (rc) return rc;
+    const uint64_t slot = (uint64_t)slot_kib << 10;
+    const size_t n_slots = (size_t)n_threads * slots_per_thread;
+    uint8_t *pinned = nullptr, *pinned_dev = nullptr, *dev = nullptr, *scratch = nullptr;
+    const size_t sb = (pack_pull_scratch_bytes(slot) + 255) & ~size_t(255);
+    LSIO_CUDA_TRY(cudaHostAlloc((void**)&pinned, slot * n_slots, cudaHostAllocPortable | cudaHostAllocMapped));
+    LSIO_CUDA_TRY(cudaHostGetDevicePointer((void**)&pinned_dev, pinned, 0));
+    LSIO_CUDA_TRY(cudaMalloc((void**)&dev, slot * n_slots));
+    LSIO_CUDA_TRY(cudaMalloc((void**)&scratch, sb * n_slots));
+    LSIO_CUDA_TRY(cudaMemset(scratch, 0, sb * n_slots));
+    std::atomic<size_t> next_file{0};
+    std::atomic<uint64_t> total{0};
+    std::atomic<int> err{0};
+    std::atomic<uint32_t> ready{0};
+    std::atomic<bool> go{false};
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_threads; t++)
+        th.emplace_back([&, t] {
+            if (cpu_count) {
+                cpu_set_t set;
+                CPU_ZERO(&set);
+                for (uint32_t c = 0; c < cpu_count; c++) CPU_SET((int)(cpu_first + c), &set);
+                pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+            }
+            cudaSetDevice(device);
+            cudaStream_t st;
+            std::vector<cudaEvent_t> ev(slots_per_thread);
+            std::vector<char> busy(slots_per_thread, 0);
+            bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+            for (auto& e : ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) err.store(-EIO);
+            ready.fetch_add(1);
+            while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+            uint64_t bytes = 0;
+            uint32_t k = 0;
+            for (size_t f; ok && !err.load() && (f = next_file.fetch_add(1)) < n_paths;) {
+                int fd = open(paths[f], O_RDONLY);
+                if (fd < 0) { err.store(-errno); break; }
+                for (uint64_t off = 0;; off += slot, k = (k + 1) % slots_per_thread) {
+                    const size_t si = (size_t)t * slots_per_thread + k;
+                    if (busy[k]) while (cudaEventQuery(ev[k]) == cudaErrorNotReady) __builtin_ia32_pause();
+                    iovec iv{pinned + si * slot, (size_t)slot};
+                    const ssize_t n = preadv2(fd, &iv, 1, (off_t)off, 0);
+                    if (n < 0) { err.store(-errno); break; }
+                    if (n == 0) break;
+                    cudaError_t ce = cudaSuccess;
+                    int prc = 0;
+                    if (use_copy_engine) {
+                        ce = cudaMemcpyAsync(dev + si * slot, pinned + si * slot, (size_t)n, cudaMemcpyHostToDevice, st);
+                    } else {
+                        lsio_cuda_segment sg{(uint64_t)(uintptr_t)(pinned_dev + si * slot), (uint64_t)(uintptr_t)(dev + si * slot), (uint64_t)n};
+                        prc = pack_pull_launch(device, &sg, 1, false, scratch + si * sb, pack_pull_max_tiles(slot), nullptr, st);
+                    }
+                    if (ce == cudaSuccess && !prc) ce = cudaEventRecord(ev[k], st);
+                    if (ce != cudaSuccess || prc) { err.store(prc ? prc : (int)ce); break; }
+                    busy[k] = 1;
+                    bytes += (uint64_t)n;
+                    if ((uint64_t)n < slot) { k = (k + 1) % slots_per_thread; break; }
+                }
+                close(fd);
+            }
+            if (ok) cudaStreamSynchronize(st);
+            for (auto& e : ev) cudaEventDestroy(e);
+            cudaStreamDestroy(st);
+            total.fetch_add(bytes);
+        });
+    while (ready.load() < n_threads) std::this_thread::yield();
+    const uint64_t t0 = now_ns();
+    go.store(true, std::memory_order_release);
+    for (auto& x : th) x.join();
+    cudaDeviceSynchronize();
+    *seconds = (double)(now_ns() - t0) * 1e-9;
+    *bytes_out = total.load();
+    cudaFreeHost(pinned);
+    cudaFree(dev);
+    cudaFree(scratch);
+    return err.load();
+}
+
 }  // extern "C"

@@ -145,5 +145,17 @@ def probe_read_ceiling(paths, block_bytes=1 << 20, n_threads=8, queue_depth=32, 
     return out.value
 
 
+def probe_staged_ceiling(paths, device=0, n_threads=8, slot_kib=512, slots_per_thread=4, use_copy_engine=False, cpu_first=0, cpu_count=0):
+    """(seconds, bytes) of the minimal staged path over `paths`: preadv2 into pinned slots + pull kernel (or one cudaMemcpyAsync) per slot,
+    nothing else (lsio_probe_staged_ceiling).  Ranks sharing a host call it between the same barriers and add up their bytes."""
+    import os
+
+    arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    secs, nbytes = ctypes.c_double(0), ctypes.c_uint64(0)
+    N.check(N.lib.lsio_probe_staged_ceiling(arr, len(paths), int(device), n_threads, slot_kib, slots_per_thread, int(use_copy_engine), cpu_first, cpu_count,
+                                            ctypes.byref(secs), ctypes.byref(nbytes)), "probe_staged_ceiling")
+    return secs.value, nbytes.value
+
+
 def launch_count():
     return int(N.lib.lsio_cuda_launch_count())

@@ -1033,3 +1033,18 @@ def test_read_ceiling_probe_reads_every_byte(lsio, oracle, cuda_dev, data_dir, i
         fns.append(fn)
     v = lsio.cuda_ops.probe_read_ceiling(fns, 256 * KIB, 3, 4, True, inline_reads, files_in_flight)
     assert v > 0
+
+
+@pytest.mark.parametrize("use_copy_engine", [False, True])
+def test_staged_ceiling_probe_ships_every_byte(lsio, oracle, cuda_dev, data_dir, use_copy_engine):
+    """lsio_probe_staged_ceiling (the minimal staged path bench.py compares the pipeline with): ragged files, more files than threads;
+    every byte is read and shipped."""
+    fns, total = [], 0
+    for i in range(7):
+        fn = os.path.join(data_dir, f"sc{i}")
+        size = 3 * MIB + i * 4096 * 5 + (512 if i % 2 else 0)
+        oracle.write_file(fn, 60 + i, size)
+        fns.append(fn)
+        total += size
+    secs, nbytes = lsio.cuda_ops.probe_staged_ceiling(fns, 0, 3, 256, 3, use_copy_engine)
+    assert nbytes == total and secs > 0
