@@ -983,14 +983,13 @@ def main():
         ceil["source_read_gib_s"], ceil["source_read_shapes"] = source_ceiling(paths[: min(len(paths), 250)], [args.workers * n_gpus, ncpu], True)
     barrier()
     # what the host can stage AND ship at once: the minimal staged program (preadv2 into pinned slots + pull kernel, nothing else), every
-    # rank at the same time with the product's thread count, slot geometry and CPU slice; best of two rounds
+    # rank at the same time with the product's thread count, slot geometry and CPU slice, over the rank's whole shard; best of three rounds
     staged = 0.0
     geo = val["stats"]
-    sample = my_paths[: min(len(my_paths), 250)]
-    for _ in range(2):
+    for _ in range(3):
         barrier()
         try:
-            t, b = cuda_ops.probe_staged_ceiling(sample, dev.index, args.workers, max(64, int(geo["slot_bytes"]) >> 10), max(2, int(geo["slots_per_worker"])), False,
+            t, b = cuda_ops.probe_staged_ceiling(my_paths, dev.index, args.workers, max(64, int(geo["slot_bytes"]) >> 10), max(2, int(geo["slots_per_worker"])), False,
                                                  args.cpu_first if args.pin else 0, args.cpu_count if args.pin else 0)
         except Exception as ex:
             log("staged ceiling probe failed:", repr(ex))
