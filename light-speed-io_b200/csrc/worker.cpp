@@ -122,9 +122,11 @@ struct Worker {
 
     // direct_landing 2: the extent is moved by the pull kernel, launched here on this worker's stream: its warps read the
     // pinned slot over PCIe through the mapped address, checksum the bytes and write them at their final place in the
-    // request buffers -- one pass, no copy engine, no device staging ring (pack_crc.cu pull_kernel).  Needs every segment's
-    // slot address congruent to its destination mod 16 (a vector is loaded once; otherwise each would cross PCIe twice)
-    // and at most kPullMaxSegs segments (the descriptors travel as kernel parameters); anything else takes the other paths.
+    // request buffers -- one pass, no copy engine, no device staging ring (pack_crc.cu pull_kernel).  Needs at most kPullMaxSegs
+    // segments (the descriptors travel as kernel parameters) and a payload the slot's scratch can hold (overlapping ranges share
+    // a read's bytes, so payload > slot is possible); without pull_any_shift also every segment's slot address congruent to its
+    // destination mod 16.  Anything else takes the other paths.  (With a shift every destination vector needs two source loads;
+    // the second hits the L2 line the first brought in, so the bytes still cross PCIe once: measured)
     bool try_pull(int slot, StageEntry* ent, uint32_t nsegs) {
         Backend* be = g.be;
         lsio_cuda_segment segs[kPullMaxSegs];
