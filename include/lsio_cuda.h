@@ -74,6 +74,10 @@ int lsio_cuda_pull_strip_crc32c(int device, const lsio_cuda_segment* segs_host_s
 /* XXH64 (seed 0) of n spans; one 64-bit result per span.  Spans are device addresses. */
 int lsio_cuda_xxh64(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n,
                     uint64_t* out_dev, void* stream);
+/* Same, choosing the kernel: 0 = default (the plain kernel: four lanes per chunk, 8-byte loads), 1 = plain, 2 = the chunk staged through
+ * shared memory by the bulk-copy engine (cp.async.bulk): an A/B that measured slower at every shape and is kept for that record. */
+int lsio_cuda_xxh64_variant(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n,
+                            uint64_t* out_dev, void* stream, int variant);
 
 /* Test aid (SURVEY 2.2 verify_pattern): recompute the synthetic content
  * byte(file_id, off) in-kernel for n spans and count mismatching bytes into *mismatch_dev

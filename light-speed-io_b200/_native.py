@@ -59,6 +59,8 @@ lib.lsio_cuda_pack_strip_crc32c.argtypes = [ctypes.c_int, ctypes.POINTER(CudaSeg
                                             ctypes.c_void_p, ctypes.c_void_p]
 lib.lsio_cuda_xxh64.restype = ctypes.c_int
 lib.lsio_cuda_xxh64.argtypes = [ctypes.c_int, c_u64p, c_u64p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+lib.lsio_cuda_xxh64_variant.restype = ctypes.c_int
+lib.lsio_cuda_xxh64_variant.argtypes = [ctypes.c_int, c_u64p, c_u64p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 lib.lsio_cuda_verify_pattern.restype = ctypes.c_int
 lib.lsio_cuda_verify_pattern.argtypes = [ctypes.c_int, c_u64p, c_u64p, c_u64p, c_u64p, ctypes.c_size_t, ctypes.c_void_p,
                                          ctypes.c_void_p]

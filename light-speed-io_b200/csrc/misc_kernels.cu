@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(256) xxh64_kernel(const uint64_t* __restrict__
 }
 
 // ---- xxh64, staged through shared memory by the bulk-copy (TMA) engine ------------------------------------------------------
-// Same arithmetic, different data movement.  The plain kernel above walks thousands of chunks at once with 8-byte loads, 256 B
-// per chunk per round: DRAM sees short bursts scattered over as many pages (51-59 % of the HBM peak).  Here every team of four
+// Same arithmetic, different data movement: an A/B that LOST (numbers at xxh64_launch below) and is kept opt-in.  The plain kernel above
+// walks thousands of chunks at once with 8-byte loads, 256 B per chunk per round: DRAM sees short bursts scattered over as many pages
+// (still 81-88 % of the HBM peak with >= 131k chunks, kernel-only).  Here every team of four
 // lanes owns two 1 KiB buffers in shared memory and its leader streams the chunk into them with cp.async.bulk (one contiguous
 // 1 KiB + 16 B burst per copy, completion on an mbarrier), while the four lanes run the accumulators out of shared memory.
 // A chunk may start at any address: staging starts at the 16-byte boundary below it (`lead` bytes early) and every piece carries
@@ -280,12 +281,12 @@ __global__ void __launch_bounds__(256) fill_kernel(uint8_t* __restrict__ dst, ui
 
 namespace lsio {
 // Asynchronous launch for the pipeline: ptrs/lens/out are device-accessible (mapped pinned) arrays.
-// Variant (measured, tools/xxh_bench.py, whole call incl. the descriptor upload): 524,288 chunks of 16 KiB: staged 2658 GB/s vs plain 648;
-// 131,072 x 64 KiB: 1552 vs 2396; 32,768 x 256 KiB: 1441 vs 1976.  Small chunks are where the plain kernel's scattered 256-byte bursts
-// hurt most and where 1 KiB bulk copies help; with long chunks the staged kernel runs out of warps (12 per SM) before it runs out of
-// bandwidth.  Hence: staged for launches of >= 4096 chunks whose mean length is <= 32 KiB (`small_chunks`), plain otherwise -- the
-// pipeline's own batches (<= 8192 chunks, usually hundreds) stay on the plain kernel.  LSIO_XXH64_VARIANT=1 / 2 forces plain / staged.
-static void xxh64_launch(const uint64_t* ptrs_dev, const uint64_t* lens_dev, size_t n, uint64_t* out_dev, cudaStream_t st, bool small_chunks) {
+// Variant.  Kernel-only durations (ncu, one launch each, profiles/r02_xxh64_kernels.txt): the PLAIN kernel wins everywhere --
+// 524,288 x 16 KiB: 1497 us (5.74 TB/s, 88 % of the measured HBM peak) vs 2203 us staged; 131,072 x 16 KiB: 405 vs 598 us; 131,072 x 64 KiB:
+// 1573 vs 2435 us; 32,768 x 256 KiB: 2359 vs 3057 us.  The staged kernel runs 12 warps per SM (70 KiB of shared memory per CTA) and its
+// 1 KiB bulk copies do not make up for that; the plain kernel's 64 warps per SM hide the scattered 256-byte bursts well enough.  The
+// staged kernel therefore stays an opt-in A/B (variant 2 through lsio_cuda_xxh64_variant or LSIO_XXH64_VARIANT=2), never the default.
+static void xxh64_launch(const uint64_t* ptrs_dev, const uint64_t* lens_dev, size_t n, uint64_t* out_dev, cudaStream_t st, int variant) {
     static const int forced = [] { const char* e = getenv("LSIO_XXH64_VARIANT"); return e ? atoi(e) : 0; }();
     static std::atomic<int> ready[64] = {};  // per device: 0 unknown, 1 attribute set, -1 refused
     int dev = 0;
@@ -293,13 +294,14 @@ static void xxh64_launch(const uint64_t* ptrs_dev, const uint64_t* lens_dev, siz
     dev &= 63;
     if (ready[dev].load(std::memory_order_acquire) == 0)
         ready[dev].store(cudaFuncSetAttribute(xxh64_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXSmem) == cudaSuccess ? 1 : -1, std::memory_order_release);
-    const bool staged = ready[dev].load(std::memory_order_acquire) == 1 && (forced ? forced == 2 : (small_chunks && n >= 4096));
+    if (!variant) variant = forced;
+    const bool staged = ready[dev].load(std::memory_order_acquire) == 1 && variant == 2;
     if (staged) xxh64_tma_kernel<<<(unsigned)((n + kXTeams - 1) / kXTeams), 4 * kXTeams, kXSmem, st>>>(ptrs_dev, lens_dev, n, out_dev);
     else xxh64_kernel<<<(unsigned)((4 * (uint64_t)n + 255) / 256), 256, 0, st>>>(ptrs_dev, lens_dev, n, out_dev);
 }
 int xxh64_launch_async(const uint64_t* ptrs_dev, const uint64_t* lens_dev, size_t n, uint64_t* out_dev, cudaStream_t st) {
     if (!n) return 0;
-    xxh64_launch(ptrs_dev, lens_dev, n, out_dev, st, false);
+    xxh64_launch(ptrs_dev, lens_dev, n, out_dev, st, 0);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -322,7 +324,7 @@ int lsio_cuda_fill_pattern(int device, void* dst_dev, uint64_t len, uint64_t fil
     return 0;
 }
 
-int lsio_cuda_xxh64(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n, uint64_t* out_dev, void* stream) {
+int lsio_cuda_xxh64_variant(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n, uint64_t* out_dev, void* stream, int variant) {
     using namespace lsio;
     if ((!ptrs || !lens || !out_dev) && n) return -EINVAL;
     if (n == 0) return 0;
@@ -333,14 +335,16 @@ int lsio_cuda_xxh64(int device, const uint64_t* ptrs, const uint64_t* lens, size
     LSIO_CUDA_TRY(cudaMallocAsync(&d, 2 * n * sizeof(uint64_t), st));
     LSIO_CUDA_TRY(cudaMemcpyAsync(d, ptrs, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     LSIO_CUDA_TRY(cudaMemcpyAsync(d + n, lens, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    uint64_t total = 0;
-    for (size_t i = 0; i < n; i++) total += lens[i];
-    xxh64_launch(d, d + n, n, out_dev, st, total / n <= (32u << 10));
+    xxh64_launch(d, d + n, n, out_dev, st, variant);
     launch_counter().fetch_add(1, std::memory_order_relaxed);
     LSIO_CUDA_TRY(cudaGetLastError());
     LSIO_CUDA_TRY(cudaFreeAsync(d, st));
     LSIO_CUDA_TRY(cudaStreamSynchronize(st));  // ptrs/lens are pageable host memory: keep the call self-contained
     return 0;
+}
+
+int lsio_cuda_xxh64(int device, const uint64_t* ptrs, const uint64_t* lens, size_t n, uint64_t* out_dev, void* stream) {
+    return lsio_cuda_xxh64_variant(device, ptrs, lens, n, out_dev, stream, 0);
 }
 
 int lsio_cuda_verify_pattern(int device, const uint64_t* ptrs, const uint64_t* lens, const uint64_t* file_ids,

@@ -101,15 +101,15 @@ def pull_strip_crc32c(src_pinned, dst, src_off, dst_off, lens, crc32c=True, stre
     return out
 
 
-def xxh64(buf, offs, lens, stream=None):
+def xxh64(buf, offs, lens, stream=None, variant=0):
     import torch
 
     n = len(lens)
     ptrs = (np.asarray(offs, dtype=np.uint64) + np.uint64(buf.data_ptr())).astype(np.uint64)
     lens = np.ascontiguousarray(lens, dtype=np.uint64)
     out = torch.empty(max(n, 1), dtype=torch.int64, device=buf.device)
-    N.check(N.lib.lsio_cuda_xxh64(buf.device.index, ptrs.ctypes.data_as(N.c_u64p), lens.ctypes.data_as(N.c_u64p), n,
-                                  ctypes.c_void_p(out.data_ptr()), _stream_ptr(stream)), "xxh64")
+    N.check(N.lib.lsio_cuda_xxh64_variant(buf.device.index, ptrs.ctypes.data_as(N.c_u64p), lens.ctypes.data_as(N.c_u64p), n,
+                                          ctypes.c_void_p(out.data_ptr()), _stream_ptr(stream), int(variant)), "xxh64")
     return out[:n]
 
 

@@ -248,9 +248,11 @@ def test_pull_kernel_reads_pinned_host_memory_bit_exact(lsio, oracle, cuda_dev):
         lsio.cuda_ops.pull_strip_crc32c(hsrc, tdst, np.zeros(65, dtype=np.uint64), np.zeros(65, dtype=np.uint64), np.ones(65, dtype=np.uint64))
 
 
-def test_xxh64_staged_kernel_many_chunks(lsio, oracle, cuda_dev):
-    """Launches of >= 4096 chunks take the bulk-copy (TMA) staged XXH64 kernel: chunks of every length class (empty, < 32 B,
-    exact multiples of the 1 KiB piece and of the 32 B stripe, ragged) at every start alignment mod 16, all compared with the oracle."""
+@pytest.mark.parametrize("variant", [2, 1])
+def test_xxh64_staged_kernel_many_chunks(lsio, oracle, cuda_dev, variant):
+    """Both XXH64 kernels (1 = plain, the default; 2 = staged through shared memory with cp.async.bulk, an opt-in A/B) over 6000 chunks
+    of every length class (empty, < 32 B, exact multiples of the 1 KiB piece and of the 32 B stripe, ragged) at every start alignment
+    mod 16, all compared with the oracle."""
     import torch
 
     rng = np.random.default_rng(64)
@@ -265,7 +267,7 @@ def test_xxh64_staged_kernel_many_chunks(lsio, oracle, cuda_dev):
     offs = np.array(offs, dtype=np.uint64)
     data = rng.integers(0, 256, pos + 64, dtype=np.uint8)
     buf = torch.from_numpy(data).to(cuda_dev)
-    got = lsio.cuda_ops.xxh64(buf, offs, lens).cpu().numpy().view(np.uint64)
+    got = lsio.cuda_ops.xxh64(buf, offs, lens, variant=variant).cpu().numpy().view(np.uint64)
     want = np.array([oracle.xxh64(data[int(o):int(o + l)]) for o, l in zip(offs, lens)], dtype=np.uint64)
     bad = np.flatnonzero(got != want)
     assert len(bad) == 0, (len(bad), [(int(i), int(lens[i]), int(offs[i]) % 16) for i in bad[:10]])
