@@ -1,8 +1,8 @@
 """cuobjdump -sass of the shipped library -> per-kernel opcode histogram (profiles/r02_sass_summary.txt).
 Shows what the kernels are made of: 128-bit global loads/stores, shared-memory table lookups, warp shuffles / redux,
 atomics of the tile scheduler; no tensor-core instruction (UTC*MMA / HMMA): nothing here is a contraction.  The bulk-copy engine
-(UBLKCP = cp.async.bulk) appears in exactly one kernel, xxh64_tma_kernel, where it pays (many small chunks); for the pull over PCIe the
-same engine did not beat plain loads (tools/h2d_probe.cu, modes 5-7)."""
+(UBLKCP = cp.async.bulk) appears in exactly one kernel, xxh64_tma_kernel, an opt-in A/B that measured slower than the plain kernel;
+for the pull over PCIe the same engine did not beat plain loads either (tools/h2d_probe.cu, modes 5-7)."""
 import collections, re, subprocess, sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else "light-speed-io_b200/liblsio_b200.so"
