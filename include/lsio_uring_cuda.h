@@ -218,6 +218,16 @@ int lsio_probe_staged_ceiling(const char* const* paths, size_t n_paths, int devi
                               uint32_t slots_per_thread, uint32_t use_copy_engine, uint32_t cpu_first, uint32_t cpu_count, double* seconds,
                               uint64_t* bytes_out);
 
+/* Test aid (no device, no I/O): the request planner's arithmetic on its own -- range resolution (sqe.rs:64-81), the prefix-sum layout of
+ * the request's buffer, and the read plan (merge / split / per-file alignment; sqe.rs:83-119 re-stated for a whole request).
+ * ranges_out: 4 int64 per range {valid, start_off, end_off, dst_off}; reads_out: 6 uint64 per read {file_off, read_len, needed, first_seg,
+ * nsegs, ntiles}; segs_out: 4 uint64 per segment {range, head, payload_len, dst_off}.  *n_reads / *n_segs receive the full counts even
+ * when they exceed the caps.  `buffer_address`: where the request's buffer would start (kernel tiles are counted in destination space). */
+int lsio_uring_cuda_plan_reads(int64_t filesize, const int64_t* starts, const int64_t* ends, size_t n, uint32_t align, uint64_t max_read_bytes,
+                               uint32_t merge_ranges, uint64_t merge_gap_bytes, uint32_t pack_align, uint64_t buffer_address, int64_t* ranges_out,
+                               uint64_t* reads_out, size_t cap_reads, size_t* n_reads, uint64_t* segs_out, size_t cap_segs, size_t* n_segs,
+                               uint64_t* total_bytes);
+
 /* Test aid: host-logic self tests of the shipped components (tracker, user_data, channel, staging
  * log, arena, GF(2) combine), no GPU needed; see csrc/selftest.cpp. 0 = pass. */
 int lsio_uring_cuda_selftest(int which);

@@ -210,6 +210,35 @@ lib.lsio_probe_read_ceiling_ex.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctyp
                                            ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
 
 
+lib.lsio_uring_cuda_plan_reads.restype = ctypes.c_int
+lib.lsio_uring_cuda_plan_reads.argtypes = [ctypes.c_int64, c_i64p, c_i64p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
+                                           ctypes.c_uint64, c_i64p, c_u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), c_u64p, ctypes.c_size_t,
+                                           ctypes.POINTER(ctypes.c_size_t), c_u64p]
+
+
+def plan_reads(filesize, starts, ends, align=512, max_read_bytes=512 << 10, merge_ranges=1, merge_gap_bytes=0, pack_align=1, buffer_address=1 << 30):
+    """The request planner's arithmetic on its own (lsio_uring_cuda_plan_reads; no device): returns (ranges[n,4] int64, reads[r,6] uint64,
+    segs[s,4] uint64, total_bytes)."""
+    import numpy as np
+
+    st = np.ascontiguousarray(starts, dtype=np.int64)
+    en = np.ascontiguousarray(ends, dtype=np.int64)
+    n = len(st)
+    ranges = np.zeros((max(n, 1), 4), dtype=np.int64)
+    nr, ns, tot = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_uint64(0)
+    reads, segs = np.zeros((0, 6), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64)
+    for _ in range(2):  # first call sizes the outputs
+        rc = lib.lsio_uring_cuda_plan_reads(filesize, st.ctypes.data_as(c_i64p), en.ctypes.data_as(c_i64p), n, align, max_read_bytes, merge_ranges, merge_gap_bytes, pack_align,
+                                            buffer_address, ranges.ctypes.data_as(c_i64p), reads.ctypes.data_as(c_u64p), len(reads), ctypes.byref(nr),
+                                            segs.ctypes.data_as(c_u64p), len(segs), ctypes.byref(ns), ctypes.byref(tot))
+        if rc:
+            raise ValueError(f"lsio_uring_cuda_plan_reads: rc={rc}")
+        if len(reads) >= nr.value and len(segs) >= ns.value:
+            break
+        reads, segs = np.zeros((nr.value, 6), dtype=np.uint64), np.zeros((ns.value, 4), dtype=np.uint64)
+    return ranges[:n], reads[: nr.value], segs[: ns.value], tot.value
+
+
 lib.lsio_probe_staged_ceiling.restype = ctypes.c_int
 lib.lsio_probe_staged_ceiling.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                           ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]

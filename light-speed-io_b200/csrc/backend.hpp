@@ -226,6 +226,8 @@ void send_output(Backend* be, lsio_output& o);
 // operation.rs:82-100 maybe_send_error: one Err per failed CQE, with context.
 void send_error(Backend* be, int status, uint8_t opcode, const Request& r, int range, const char* what);
 Start plan_request(Group& g, const std::shared_ptr<Request>& rp, WorkerThread<Op>& wt);
+void resolve_ranges(Request& r, int64_t filesize, uint64_t pack_align, std::vector<uint32_t>* invalid);
+void build_read_plan(Request& r, const lsio_uring_cuda_config& cfg, const uint8_t* block);
 
 // ---- worker.cpp: body of one io worker thread (UringWorker::new + run, worker.rs:32-125) -----------------
 void worker_main(Group& g, WorkerThread<Op>& wt);

@@ -409,3 +409,71 @@ def test_zarr_v3_sharded_array_metadata(lsio, tmp_path):
         ZV.ShardedArray(d)
     _write_zarr_json(d, data_type="bool")
     assert ZV.ShardedArray(d).is_bool
+
+
+@pytest.mark.parametrize("align,max_read,merge,gap,pack_align", [(512, 512 << 10, 1, 0, 1), (512, 4096, 0, 0, 1), (4096, 256 << 10, 1, 4096, 16), (65536, 1 << 20, 1, 0, 512),
+                                                                 (4096, 4096, 1, 0, 1), (512, 65536, 0, 0, 16)])
+def test_read_planner_arithmetic_against_the_oracle(lsio, oracle, align, max_read, merge, gap, pack_align):
+    """The request planner on its own (no device): for random requests -- valid, invalid, negative, EOF, overlapping and duplicate ranges --
+    (1) resolution equals the oracle's restatement of sqe.rs:64-81; (2) the request's buffer is a prefix-sum layout at pack_align;
+    (3) every read starts and ends on the FILE's alignment (open_file.rs:23-25: 512, 4096 or 65536 here), is at most max_read_bytes long
+    and `needed` covers its furthest payload byte; (4) every valid range is covered exactly once, in order, by its segments, and each
+    segment's bytes are the file bytes the range asked for (file_off + head == start_off + position in the range)."""
+    rng = np.random.default_rng(align + max_read + merge)
+    N = lsio._native
+    for trial in range(60):
+        size = int(rng.choice([1, 511, 4096, 70_001, 1_048_576, 3_000_003, 9_437_184 + 17]))
+        rs = []
+        for _ in range(int(rng.integers(1, 60))):
+            kind = rng.integers(0, 10)
+            if kind == 0:
+                rs.append((0, -1))
+            elif kind == 1:
+                rs.append((int(size + rng.integers(1, 100)), int(size + 200)))  # beyond EOF: invalid
+            elif kind == 2:
+                n = int(min(size, rng.integers(1, 3000)))
+                rs.append((-n, -1))
+            elif kind == 3:
+                rs.append((5, 5))  # empty: invalid
+            else:
+                n = int(rng.integers(1, min(size, 2_000_000) + 1))
+                s0 = int(rng.integers(0, size - n + 1))
+                rs.append((s0, s0 + n))
+        starts, ends = [r[0] for r in rs], [r[1] for r in rs]
+        ranges, reads, segs, total = N.plan_reads(size, starts, ends, align, max_read, merge, gap, pack_align, buffer_address=(1 << 30) + 512 * int(rng.integers(0, 8)))
+        dst = 0
+        for i, (s, e) in enumerate(rs):  # (1) + (2)
+            rc, rr = oracle.resolve_range(size, s, e)
+            valid = rc == 0 and rr.end_off <= size and rr.end_off > rr.start_off
+            assert bool(ranges[i, 0]) == valid, (size, s, e)
+            if valid:
+                assert (ranges[i, 1], ranges[i, 2]) == (rr.start_off, rr.end_off)
+                dst = (dst + pack_align - 1) // pack_align * pack_align
+                assert ranges[i, 3] == dst
+                dst += rr.end_off - rr.start_off
+        assert total == dst
+        mr = max(align, max_read // align * align)
+        for k, (fo, ln, needed, first, nsegs, ntiles) in enumerate(reads.tolist()):  # (3)
+            assert fo % align == 0 and ln % align == 0 and 0 < ln <= mr and 0 < needed <= ln and nsegs >= 1
+            sg = segs[first:first + nsegs]
+            assert int((sg[:, 1] + sg[:, 2]).max()) == needed and ntiles >= nsegs
+        owner = np.zeros(len(segs), dtype=np.int64) - 1  # the read each segment belongs to
+        for k, rd in enumerate(reads.tolist()):
+            assert (owner[rd[3]:rd[3] + rd[4]] == -1).all()
+            owner[rd[3]:rd[3] + rd[4]] = k
+        assert (owner >= 0).all()
+        for i in range(len(rs)):  # (4)
+            mine = np.flatnonzero(segs[:, 0] == i)
+            if not ranges[i, 0]:
+                assert len(mine) == 0
+                continue
+            pos = int(ranges[i, 3])
+            for j in mine[np.argsort(segs[mine, 3])]:
+                _, head, plen, doff = segs[j].tolist()
+                assert doff == pos and plen > 0
+                assert reads[owner[j], 0] + head == ranges[i, 1] + (doff - ranges[i, 3])  # the file byte this segment starts at
+                pos += plen
+            assert pos == ranges[i, 3] + (ranges[i, 2] - ranges[i, 1])
+        if not merge:  # the reference's shape: no read serves two ranges (duplicates and overlaps are read again)
+            for rd in reads.tolist():
+                assert len(set(segs[rd[3]:rd[3] + rd[4], 0].tolist())) == 1
