@@ -477,3 +477,33 @@ def test_read_planner_arithmetic_against_the_oracle(lsio, oracle, align, max_rea
         if not merge:  # the reference's shape: no read serves two ranges (duplicates and overlaps are read again)
             for rd in reads.tolist():
                 assert len(set(segs[rd[3]:rd[3] + rd[4], 0].tolist())) == 1
+
+
+def test_ctypes_mirrors_match_the_c_headers(lsio, tmp_path):
+    """The Python mirror lays its structs out by hand (ctypes): compile a C program against include/*.h and compare sizes and the
+    offset of every field.  A struct that grows in the header (round 2 added fields to the config and the stats) must grow in the
+    mirror too, or every later field is read from the wrong place."""
+    import ctypes
+    import subprocess
+
+    N = lsio._native
+    structs = {"lsio_uring_cuda_config": N.CConfig, "lsio_uring_cuda_stats": N.CStats, "lsio_output": N.COutput, "lsio_chunk": N.CChunk,
+               "lsio_cuda_segment": N.CudaSegment, "lsio_bench_result": N.CBenchResult}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "lsio_io.h"', '#include "lsio_cuda.h"', '#include "lsio_uring_cuda.h"', '#include "lsio_bench.h"',
+             'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == want, (cname, field, int(value), want)
