@@ -1000,7 +1000,7 @@ def main():
     ceil["staged_ceiling_gib_s"] = staged
 
     parity = {"expected_crc_source": "oracle", "expected_crc_is": "oracle.crc32c_file_blocks over files written by oracle.write_file (oracle/lsio_oracle.c); every chunk of every timed pass is compared with it",
-              "chunks_checked_timed_legs": (args.steps * len(my_paths) * N_CHUNKS + e["steps"] * len(my_paths) * N_CHUNKS) * 1,
+              "chunks_checked_timed_legs_per_rank": (args.steps + e["steps"]) * len(my_paths) * N_CHUNKS,
               "bad_chunks_all_ranks": v["bad_chunks"] + e["bad_chunks"],
               "kernel_pass_crc_equals_oracle_table": kern["crc_ok"] and kern_ip["crc_ok"]}
     if not args.no_verify:
